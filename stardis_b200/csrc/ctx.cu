@@ -1,0 +1,565 @@
+// ctx.cu -- context, memory, transfers, result access, elementwise kernels and measurement helpers of the
+// C ABI declared in include/stardis_b200.h.
+#include <stdarg.h>
+
+#include "sd_internal.h"
+#include "sd_math.cuh"
+
+int sd_fail(sd_ctx *c, int code, const char *fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    if (c) c->err = buf;
+    return code;
+}
+
+int sd_ensure(sd_ctx *c, DevBuf &b, size_t bytes) {
+    if (bytes == 0) bytes = 16;
+    if (b.cap >= bytes) return SD_OK;
+    if (b.p) {
+        SD_CUDA(c, cudaStreamSynchronize(c->stream));
+        SD_CUDA(c, cudaFree(b.p));
+        b.p = nullptr;
+        b.cap = 0;
+    }
+    size_t want = bytes + bytes / 8 + 256;
+    cudaError_t e = cudaMalloc(&b.p, want);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        b.p = nullptr;
+        return sd_fail(c, SD_ERR_NOMEM, "cudaMalloc of %zu bytes failed: %s", want, cudaGetErrorString(e));
+    }
+    b.cap = want;
+    return SD_OK;
+}
+
+int sd_upload(sd_ctx *c, DevBuf &b, const void *src, size_t bytes) {
+    SD_TRY(sd_ensure(c, b, bytes));
+    if (bytes) SD_CUDA(c, cudaMemcpyAsync(b.p, src, bytes, cudaMemcpyDefault, c->stream));
+    return SD_OK;
+}
+
+int sd_launch_check(sd_ctx *c, const char *what) {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return sd_fail(c, SD_ERR_CUDA, "launch of %s failed: %s", what, cudaGetErrorString(e));
+    return SD_OK;
+}
+
+static void free_buf(DevBuf &b) {
+    if (b.p) cudaFree(b.p);
+    b.p = nullptr;
+    b.cap = 0;
+}
+
+extern "C" {
+
+const char *sd_version(void) { return "stardis_b200 0.1 (sm_100a)"; }
+
+int sd_create(sd_ctx **out, int device) {
+    if (!out) return SD_ERR_ARG;
+    *out = nullptr;
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) return SD_ERR_CUDA;
+    if (device < 0 || device >= n) return SD_ERR_ARG;
+    if (cudaSetDevice(device) != cudaSuccess) return SD_ERR_CUDA;
+    sd_ctx *c = new sd_ctx();
+    c->device = device;
+    if (cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking) != cudaSuccess) {
+        delete c;
+        return SD_ERR_CUDA;
+    }
+    c->stream = c->own_stream;
+    cudaEventCreate(&c->ev0);
+    cudaEventCreate(&c->ev1);
+    cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device);
+    *out = c;
+    return SD_OK;
+}
+
+void sd_destroy(sd_ctx *c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    DevBuf *all[] = {&c->T, &c->ne, &c->nH, &c->nus, &c->d_nu, &c->l_nu, &c->l_Z, &c->l_ion, &c->l_eion, &c->l_eup,
+                     &c->l_elo, &c->l_A, &c->l_mass, &c->l_stark, &c->l_waals, &c->l_alpha, &c->gammas, &c->dws,
+                     &c->line_idx, &c->rec, &c->win_lo, &c->win_hi, &c->win_cls, &c->cls_list, &c->cls_off,
+                     &c->chunk_cnt, &c->stats, &c->alpha_line[0], &c->alpha_line[1], &c->total, &c->cont_small,
+                     &c->F, &c->I_nus, &c->ray_small};
+    for (DevBuf *b : all) free_buf(*b);
+    for (int i = 0; i < SD_MAX_SOURCES; i++) free_buf(c->src[i]);
+    cudaEventDestroy(c->ev0);
+    cudaEventDestroy(c->ev1);
+    cudaStreamDestroy(c->own_stream);
+    delete c;
+}
+
+const char *sd_last_error(const sd_ctx *c) { return c ? c->err.c_str() : "null context"; }
+
+int sd_set_stream(sd_ctx *c, void *s) {
+    if (!c) return SD_ERR_ARG;
+    SD_CUDA(c, cudaSetDevice(c->device));
+    SD_CUDA(c, cudaStreamSynchronize(c->stream));
+    c->stream = s ? (cudaStream_t)s : c->own_stream;
+    return SD_OK;
+}
+
+int sd_synchronize(sd_ctx *c) {
+    if (!c) return SD_ERR_ARG;
+    SD_CUDA(c, cudaStreamSynchronize(c->stream));
+    return SD_OK;
+}
+
+int sd_host_alloc(void **ptr, int64_t bytes) {
+    if (!ptr || bytes < 0) return SD_ERR_ARG;
+    return cudaHostAlloc(ptr, (size_t)bytes, cudaHostAllocDefault) == cudaSuccess ? SD_OK : SD_ERR_NOMEM;
+}
+int sd_host_free(void *ptr) { return cudaFreeHost(ptr) == cudaSuccess ? SD_OK : SD_ERR_CUDA; }
+
+int sd_set_atmosphere(sd_ctx *c, int32_t D, const double *T, const double *ne, const double *nH, double vmic) {
+    if (!c) return SD_ERR_ARG;
+    SD_CHECK(c, D >= 2 && T, SD_ERR_ARG, "sd_set_atmosphere: need n_depth >= 2 and temperatures");
+    SD_CUDA(c, cudaSetDevice(c->device));
+    if (D != c->D) {
+        c->records_ready = false;
+        c->have_alpha[0] = c->have_alpha[1] = c->have_total = c->have_F = c->have_broadening = false;
+    }
+    c->D = D;
+    c->vmic = vmic;
+    SD_TRY(sd_upload(c, c->T, T, sizeof(double) * D));
+    if (ne) SD_TRY(sd_upload(c, c->ne, ne, sizeof(double) * D));
+    if (nH) SD_TRY(sd_upload(c, c->nH, nH, sizeof(double) * D));
+    if (!ne) {
+        SD_TRY(sd_ensure(c, c->ne, sizeof(double) * D));
+        SD_CUDA(c, cudaMemsetAsync(c->ne.p, 0, sizeof(double) * D, c->stream));
+    }
+    if (!nH) {
+        SD_TRY(sd_ensure(c, c->nH, sizeof(double) * D));
+        SD_CUDA(c, cudaMemsetAsync(c->nH.p, 0, sizeof(double) * D, c->stream));
+    }
+    return SD_OK;
+}
+
+int sd_set_grid(sd_ctx *c, int64_t N, const double *nus, int64_t p0, int64_t p1) {
+    if (!c) return SD_ERR_ARG;
+    SD_CHECK(c, N >= 2 && N < (int64_t)2147483000 && nus, SD_ERR_ARG, "sd_set_grid: need 2 <= N < 2^31");
+    SD_CHECK(c, 0 <= p0 && p0 < p1 && p1 <= N, SD_ERR_ARG, "sd_set_grid: need 0 <= p0 < p1 <= N");
+    SD_CUDA(c, cudaSetDevice(c->device));
+    c->N = N;
+    c->p0 = p0;
+    c->p1 = p1;
+    c->records_ready = false;
+    c->have_alpha[0] = c->have_alpha[1] = c->have_total = c->have_F = false;
+    for (int i = 0; i < SD_MAX_SOURCES; i++) c->have_src[i] = false;
+    SD_TRY(sd_upload(c, c->nus, nus, sizeof(double) * N));
+    return SD_OK;
+}
+
+int sd_set_lines(sd_ctx *c, const sd_lines *ln) {
+    if (!c || !ln) return SD_ERR_ARG;
+    SD_CHECK(c, c->D > 0, SD_ERR_STATE, "sd_set_lines: call sd_set_atmosphere first");
+    int64_t L = ln->n_lines;
+    SD_CHECK(c, L >= 0 && L * (int64_t)c->D < (int64_t)4e9, SD_ERR_ARG, "sd_set_lines: bad line count");
+    SD_CHECK(c, L == 0 || (ln->nu && ln->alpha_line), SD_ERR_ARG, "sd_set_lines: nu and alpha_line are required");
+    SD_CUDA(c, cudaSetDevice(c->device));
+    c->L = L;
+    c->records_ready = false;
+    c->have_broadening = false;
+    size_t d8 = sizeof(double) * L;
+    SD_TRY(sd_upload(c, c->l_nu, ln->nu, d8));
+    SD_TRY(sd_upload(c, c->l_alpha, ln->alpha_line, d8 * c->D));
+    if (ln->mass) SD_TRY(sd_upload(c, c->l_mass, ln->mass, d8));
+    c->has_atomic_cols = ln->atomic_number && ln->ion_number && ln->ionization_energy && ln->level_energy_upper &&
+                         ln->level_energy_lower && ln->A_ul && ln->mass;
+    if (c->has_atomic_cols) {
+        SD_TRY(sd_upload(c, c->l_Z, ln->atomic_number, sizeof(int64_t) * L));
+        SD_TRY(sd_upload(c, c->l_ion, ln->ion_number, sizeof(int64_t) * L));
+        SD_TRY(sd_upload(c, c->l_eion, ln->ionization_energy, d8));
+        SD_TRY(sd_upload(c, c->l_eup, ln->level_energy_upper, d8));
+        SD_TRY(sd_upload(c, c->l_elo, ln->level_energy_lower, d8));
+        SD_TRY(sd_upload(c, c->l_A, ln->A_ul, d8));
+    }
+    c->has_vald_cols = ln->stark && ln->waals;
+    if (c->has_vald_cols) {
+        SD_TRY(sd_upload(c, c->l_stark, ln->stark, d8));
+        SD_TRY(sd_upload(c, c->l_waals, ln->waals, d8));
+    }
+    return SD_OK;
+}
+
+int sd_calc_broadening(sd_ctx *c, uint32_t flags) {
+    if (!c) return SD_ERR_ARG;
+    SD_CHECK(c, c->D > 0, SD_ERR_STATE, "sd_calc_broadening: no atmosphere");
+    SD_CHECK(c, c->has_atomic_cols, SD_ERR_STATE, "sd_calc_broadening: line table lacks the level/ion columns");
+    SD_CHECK(c, !(flags & SD_VALD) || c->has_vald_cols, SD_ERR_STATE, "sd_calc_broadening: SD_VALD needs stark/waals");
+    SD_CUDA(c, cudaSetDevice(c->device));
+    SD_TRY(sd_k1_broadening(c, flags));
+    c->gamma_cols = c->D;
+    c->have_broadening = true;
+    c->records_ready = false;
+    return SD_OK;
+}
+
+int sd_set_broadening(sd_ctx *c, const double *gammas, int32_t gamma_cols, const double *dws) {
+    if (!c) return SD_ERR_ARG;
+    SD_CHECK(c, gammas && dws && (gamma_cols == 1 || gamma_cols == c->D), SD_ERR_ARG, "sd_set_broadening: bad arguments");
+    SD_CUDA(c, cudaSetDevice(c->device));
+    SD_TRY(sd_upload(c, c->gammas, gammas, sizeof(double) * c->L * gamma_cols));
+    SD_TRY(sd_upload(c, c->dws, dws, sizeof(double) * c->L * c->D));
+    c->gamma_cols = gamma_cols;
+    c->have_broadening = true;
+    c->records_ready = false;
+    return SD_OK;
+}
+
+int sd_calc_alpha_line(sd_ctx *c, int32_t slot) {
+    if (!c) return SD_ERR_ARG;
+    SD_CHECK(c, slot == 0 || slot == 1, SD_ERR_ARG, "sd_calc_alpha_line: slot must be 0 or 1");
+    SD_CHECK(c, c->N > 0 && c->D > 0, SD_ERR_STATE, "sd_calc_alpha_line: grid/atmosphere not set");
+    SD_CHECK(c, c->have_broadening || c->L == 0, SD_ERR_STATE, "sd_calc_alpha_line: no broadening (K1) yet");
+    SD_CUDA(c, cudaSetDevice(c->device));
+    if (!c->records_ready) SD_TRY(sd_k2_prepare(c));
+    SD_TRY(sd_k2_lines(c, slot));
+    c->have_alpha[slot] = true;
+    return SD_OK;
+}
+
+int sd_set_line_stats(sd_ctx *c, int32_t on) {
+    if (!c) return SD_ERR_ARG;
+    c->line_stats = on != 0;
+    return SD_OK;
+}
+
+int sd_line_stats(sd_ctx *c, int64_t out[8]) {
+    if (!c || !out) return SD_ERR_ARG;
+    SD_CHECK(c, c->stats.p, SD_ERR_STATE, "sd_line_stats: nothing computed yet");
+    unsigned long long h[8];
+    SD_CUDA(c, cudaMemcpyAsync(h, c->stats.p, sizeof h, cudaMemcpyDeviceToHost, c->stream));
+    SD_CUDA(c, cudaStreamSynchronize(c->stream));
+    for (int i = 0; i < 8; i++) out[i] = (int64_t)h[i];
+    return SD_OK;
+}
+
+int sd_calc_continuum(sd_ctx *c, const sd_continuum *desc, uint32_t store_mask) {
+    if (!c || !desc) return SD_ERR_ARG;
+    SD_CHECK(c, c->N > 0 && c->D > 0, SD_ERR_STATE, "sd_calc_continuum: grid/atmosphere not set");
+    SD_CHECK(c, desc->n_tables >= 0 && desc->n_tables <= SD_MAX_TABLES, SD_ERR_ARG, "sd_calc_continuum: too many tables");
+    SD_CUDA(c, cudaSetDevice(c->device));
+    SD_TRY(sd_k3_continuum(c, desc, store_mask));
+    c->have_total = true;
+    return SD_OK;
+}
+
+int sd_raytrace(sd_ctx *c, int32_t n_theta, const double *ray_ds, const double *weights, int32_t inward, double scale,
+                int32_t track) {
+    if (!c) return SD_ERR_ARG;
+    SD_CHECK(c, n_theta >= 1 && ray_ds && weights, SD_ERR_ARG, "sd_raytrace: bad arguments");
+    SD_CHECK(c, c->have_total, SD_ERR_STATE, "sd_raytrace: no total opacity (sd_calc_continuum / sd_set_total)");
+    SD_CUDA(c, cudaSetDevice(c->device));
+    SD_TRY(sd_k4_raytrace(c, n_theta, ray_ds, weights, inward, scale, track));
+    c->have_F = true;
+    c->n_theta_tracked = track ? n_theta : 0;
+    return SD_OK;
+}
+
+static int find_buffer(sd_ctx *c, int which, DevBuf **b, int64_t *rows, int64_t *cols) {
+    int64_t W = c->W();
+    switch (which) {
+        case SD_BUF_GAMMAS:
+            SD_CHECK(c, c->have_broadening, SD_ERR_STATE, "gammas not computed");
+            *b = &c->gammas; *rows = c->L; *cols = c->gamma_cols; return SD_OK;
+        case SD_BUF_DOPPLER:
+            SD_CHECK(c, c->have_broadening, SD_ERR_STATE, "doppler widths not computed");
+            *b = &c->dws; *rows = c->L; *cols = c->D; return SD_OK;
+        case SD_BUF_ALPHA_LINE:
+        case SD_BUF_ALPHA_MOLECULE: {
+            int s = which - SD_BUF_ALPHA_LINE;
+            SD_CHECK(c, c->have_alpha[s], SD_ERR_STATE, "alpha_line slot %d not computed", s);
+            *b = &c->alpha_line[s]; *rows = c->D; *cols = W; return SD_OK;
+        }
+        case SD_BUF_TOTAL:
+            SD_CHECK(c, c->have_total, SD_ERR_STATE, "total opacity not computed");
+            *b = &c->total; *rows = c->D; *cols = W; return SD_OK;
+        case SD_BUF_F_NU:
+            SD_CHECK(c, c->have_F, SD_ERR_STATE, "F_nu not computed");
+            *b = &c->F; *rows = c->D; *cols = W; return SD_OK;
+        case SD_BUF_I_NUS:
+            SD_CHECK(c, c->have_F && c->n_theta_tracked > 0, SD_ERR_STATE, "I_nus not tracked");
+            *b = &c->I_nus; *rows = c->D; *cols = W * c->n_theta_tracked; return SD_OK;
+        default:
+            if (which >= SD_BUF_SOURCE0 && which < SD_BUF_SOURCE0 + SD_MAX_SOURCES) {
+                int s = which - SD_BUF_SOURCE0;
+                SD_CHECK(c, c->have_src[s], SD_ERR_STATE, "continuum source %d was not stored", s);
+                *b = &c->src[s]; *rows = c->D; *cols = W; return SD_OK;
+            }
+    }
+    return sd_fail(c, SD_ERR_ARG, "unknown buffer id %d", which);
+}
+
+int sd_get(sd_ctx *c, int32_t which, double *dst, int64_t count) {
+    if (!c || !dst) return SD_ERR_ARG;
+    DevBuf *b; int64_t rows, cols;
+    SD_TRY(find_buffer(c, which, &b, &rows, &cols));
+    SD_CHECK(c, count == rows * cols, SD_ERR_ARG, "sd_get: count %lld != buffer size %lld", (long long)count, (long long)(rows * cols));
+    SD_CUDA(c, cudaSetDevice(c->device));
+    if (count) SD_CUDA(c, cudaMemcpyAsync(dst, b->p, sizeof(double) * count, cudaMemcpyDefault, c->stream));
+    return SD_OK;
+}
+
+int sd_get_row(sd_ctx *c, int32_t which, int32_t row, double *dst, int64_t count) {
+    if (!c || !dst) return SD_ERR_ARG;
+    DevBuf *b; int64_t rows, cols;
+    SD_TRY(find_buffer(c, which, &b, &rows, &cols));
+    if (row < 0) row += (int32_t)rows;
+    SD_CHECK(c, row >= 0 && row < rows && count == cols, SD_ERR_ARG, "sd_get_row: bad row/count");
+    SD_CUDA(c, cudaSetDevice(c->device));
+    SD_CUDA(c, cudaMemcpyAsync(dst, b->as<double>() + (size_t)row * cols, sizeof(double) * cols, cudaMemcpyDefault, c->stream));
+    return SD_OK;
+}
+
+int sd_set_total(sd_ctx *c, const double *total, int64_t count) {
+    if (!c || !total) return SD_ERR_ARG;
+    SD_CHECK(c, c->N > 0 && c->D > 0 && count == c->D * c->W(), SD_ERR_ARG, "sd_set_total: count must be D*(p1-p0)");
+    SD_CUDA(c, cudaSetDevice(c->device));
+    SD_TRY(sd_upload(c, c->total, total, sizeof(double) * count));
+    c->have_total = true;
+    return SD_OK;
+}
+
+int sd_buffer(sd_ctx *c, int32_t which, void **ptr, int64_t *count) {
+    if (!c || !ptr || !count) return SD_ERR_ARG;
+    DevBuf *b; int64_t rows, cols;
+    SD_TRY(find_buffer(c, which, &b, &rows, &cols));
+    *ptr = b->p;
+    *count = rows * cols;
+    return SD_OK;
+}
+
+}  // extern "C"
+
+// ------------------------------------------------------------------------------- elementwise kernels
+namespace {
+
+// Operands may live on the host: stage them through scratch device buffers.
+struct Staged {
+    sd_ctx *c;
+    DevBuf in[8];
+    DevBuf out[4];
+    ~Staged() {
+        cudaStreamSynchronize(c->stream);
+        for (auto &b : in) free_buf(b);
+        for (auto &b : out) free_buf(b);
+    }
+};
+
+__global__ void k_ew_faddeeva(int64_t n, const double *zr, const double *zi, double *wr, double *wi) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i < n) sdm::humlicek_complex(zr[i], zi[i], wr[i], wi[i]);
+}
+__global__ void k_ew_voigt(int64_t n, const double *dnu, const double *dw, const double *g, double *phi) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i < n) phi[i] = sdm::voigt_profile(dnu[i], dw[i], g[i]);
+}
+__global__ void k_ew_doppler(int64_t n, const double *nu, const double *T, const double *m, double vmic, double *o) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i < n) o[i] = sdm::doppler_width(nu[i], T[i], m[i], vmic);
+}
+__global__ void k_ew_neff(int64_t n, const double *z, const double *ei, const double *el, double *o) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i < n) o[i] = sdm::n_effective(z[i], ei[i], el[i]);
+}
+__global__ void k_ew_lstark(int64_t n, const double *a, const double *b, const double *ne, double *o) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i < n) o[i] = sdm::gamma_linear_stark(a[i], b[i], ne[i]);
+}
+__global__ void k_ew_qstark(int64_t n, const double *z, const double *a, const double *b, const double *ne, const double *T, double *o) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i < n) o[i] = sdm::gamma_quadratic_stark(z[i], a[i], b[i], ne[i], T[i]);
+}
+__global__ void k_ew_vdw(int64_t n, const double *z, const double *a, const double *b, const double *T, const double *nH, double *o) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i < n) o[i] = sdm::gamma_van_der_waals(z[i], a[i], b[i], T[i], nH[i]);
+}
+__global__ void k_ew_blackbody(int D, int64_t N, const double *nus, const double *T, double *o) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    int d = blockIdx.y;
+    if (i < N) o[(int64_t)d * N + i] = sdm::planck(nus[i], T[d]);
+}
+__global__ void k_ew_weights(int64_t n, const double *tau, double *w0, double *w1, double *w2) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i < n) sdm::rt_weights(tau[i], w0[i], w1[i], w2[i]);
+}
+
+inline unsigned nblk(int64_t n) { return (unsigned)((n + 255) / 256); }
+
+}  // namespace
+
+#define EW_BEGIN(nin, nout)                                        \
+    if (!c) return SD_ERR_ARG;                                     \
+    SD_CHECK(c, n >= 0, SD_ERR_ARG, "negative element count");      \
+    SD_CUDA(c, cudaSetDevice(c->device));                          \
+    if (n == 0) return SD_OK;                                      \
+    Staged st{c};                                                  \
+    const void *ins[] = {EW_INS};                                  \
+    void *outs[] = {EW_OUTS};                                      \
+    for (int k = 0; k < nin; k++) SD_TRY(sd_upload(c, st.in[k], ins[k], sizeof(double) * n)); \
+    for (int k = 0; k < nout; k++) SD_TRY(sd_ensure(c, st.out[k], sizeof(double) * n));
+#define EW_END(nout, what)                                         \
+    SD_TRY(sd_launch_check(c, what));                              \
+    for (int k = 0; k < nout; k++)                                 \
+        SD_CUDA(c, cudaMemcpyAsync(outs[k], st.out[k].p, sizeof(double) * n, cudaMemcpyDefault, c->stream)); \
+    return SD_OK;
+#define I(k) st.in[k].as<double>()
+#define O(k) st.out[k].as<double>()
+
+extern "C" {
+
+int sd_ew_faddeeva(sd_ctx *c, int64_t n, const double *zr, const double *zi, double *wr, double *wi) {
+#define EW_INS zr, zi
+#define EW_OUTS wr, wi
+    EW_BEGIN(2, 2)
+    k_ew_faddeeva<<<nblk(n), 256, 0, c->stream>>>(n, I(0), I(1), O(0), O(1));
+    EW_END(2, "k_ew_faddeeva")
+#undef EW_INS
+#undef EW_OUTS
+}
+int sd_ew_voigt_profile(sd_ctx *c, int64_t n, const double *dnu, const double *dw, const double *g, double *phi) {
+#define EW_INS dnu, dw, g
+#define EW_OUTS phi
+    EW_BEGIN(3, 1)
+    k_ew_voigt<<<nblk(n), 256, 0, c->stream>>>(n, I(0), I(1), I(2), O(0));
+    EW_END(1, "k_ew_voigt")
+#undef EW_INS
+#undef EW_OUTS
+}
+int sd_ew_doppler_width(sd_ctx *c, int64_t n, const double *nu, const double *T, const double *m, double vmic, double *out) {
+#define EW_INS nu, T, m
+#define EW_OUTS out
+    EW_BEGIN(3, 1)
+    k_ew_doppler<<<nblk(n), 256, 0, c->stream>>>(n, I(0), I(1), I(2), vmic, O(0));
+    EW_END(1, "k_ew_doppler")
+#undef EW_INS
+#undef EW_OUTS
+}
+int sd_ew_n_effective(sd_ctx *c, int64_t n, const double *z, const double *ei, const double *el, double *out) {
+#define EW_INS z, ei, el
+#define EW_OUTS out
+    EW_BEGIN(3, 1)
+    k_ew_neff<<<nblk(n), 256, 0, c->stream>>>(n, I(0), I(1), I(2), O(0));
+    EW_END(1, "k_ew_neff")
+#undef EW_INS
+#undef EW_OUTS
+}
+int sd_ew_gamma_linear_stark(sd_ctx *c, int64_t n, const double *a, const double *b, const double *ne, double *out) {
+#define EW_INS a, b, ne
+#define EW_OUTS out
+    EW_BEGIN(3, 1)
+    k_ew_lstark<<<nblk(n), 256, 0, c->stream>>>(n, I(0), I(1), I(2), O(0));
+    EW_END(1, "k_ew_lstark")
+#undef EW_INS
+#undef EW_OUTS
+}
+int sd_ew_gamma_quadratic_stark(sd_ctx *c, int64_t n, const double *z, const double *a, const double *b, const double *ne,
+                                const double *T, double *out) {
+#define EW_INS z, a, b, ne, T
+#define EW_OUTS out
+    EW_BEGIN(5, 1)
+    k_ew_qstark<<<nblk(n), 256, 0, c->stream>>>(n, I(0), I(1), I(2), I(3), I(4), O(0));
+    EW_END(1, "k_ew_qstark")
+#undef EW_INS
+#undef EW_OUTS
+}
+int sd_ew_gamma_van_der_waals(sd_ctx *c, int64_t n, const double *z, const double *a, const double *b, const double *T,
+                              const double *nH, double *out) {
+#define EW_INS z, a, b, T, nH
+#define EW_OUTS out
+    EW_BEGIN(5, 1)
+    k_ew_vdw<<<nblk(n), 256, 0, c->stream>>>(n, I(0), I(1), I(2), I(3), I(4), O(0));
+    EW_END(1, "k_ew_vdw")
+#undef EW_INS
+#undef EW_OUTS
+}
+int sd_ew_calc_weights(sd_ctx *c, int64_t n, const double *tau, double *w0, double *w1, double *w2) {
+#define EW_INS tau
+#define EW_OUTS w0, w1, w2
+    EW_BEGIN(1, 3)
+    k_ew_weights<<<nblk(n), 256, 0, c->stream>>>(n, I(0), O(0), O(1), O(2));
+    EW_END(3, "k_ew_weights")
+#undef EW_INS
+#undef EW_OUTS
+}
+
+int sd_ew_blackbody(sd_ctx *c, int32_t D, int64_t N, const double *nus, const double *T, double *out) {
+    if (!c) return SD_ERR_ARG;
+    SD_CHECK(c, D > 0 && N > 0 && D < 65536, SD_ERR_ARG, "sd_ew_blackbody: bad shape");
+    SD_CUDA(c, cudaSetDevice(c->device));
+    Staged st{c};
+    SD_TRY(sd_upload(c, st.in[0], nus, sizeof(double) * N));
+    SD_TRY(sd_upload(c, st.in[1], T, sizeof(double) * D));
+    SD_TRY(sd_ensure(c, st.out[0], sizeof(double) * N * D));
+    k_ew_blackbody<<<dim3(nblk(N), D), 256, 0, c->stream>>>(D, N, I(0), I(1), O(0));
+    SD_TRY(sd_launch_check(c, "k_ew_blackbody"));
+    SD_CUDA(c, cudaMemcpyAsync(out, st.out[0].p, sizeof(double) * N * D, cudaMemcpyDefault, c->stream));
+    return SD_OK;
+}
+
+}  // extern "C"
+
+// ------------------------------------------------------------------------------- measurement helpers
+namespace {
+// 8 independent FMA chains per thread, no memory traffic: the FP64 FMA-pipe ceiling of the chip.
+__global__ void __launch_bounds__(256) k_dfma(int iters, double seed, double *sink) {
+    double a0 = seed + threadIdx.x, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+    const double m = 0.999999, b = 1e-7;
+#pragma unroll 1
+    for (int i = 0; i < iters; i++) {
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+            a0 = fma(a0, m, b); a1 = fma(a1, m, b); a2 = fma(a2, m, b); a3 = fma(a3, m, b);
+            a4 = fma(a4, m, b); a5 = fma(a5, m, b); a6 = fma(a6, m, b); a7 = fma(a7, m, b);
+        }
+    }
+    double s = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+    if (s == 123.456) sink[0] = s;
+}
+}  // namespace
+
+extern "C" {
+
+int sd_bench_dfma(sd_ctx *c, int32_t iters, double *tflops) {
+    if (!c || !tflops || iters <= 0) return SD_ERR_ARG;
+    SD_CUDA(c, cudaSetDevice(c->device));
+    SD_TRY(sd_ensure(c, c->stats, 64));
+    int blocks = c->sm_count * 8;
+    k_dfma<<<blocks, 256, 0, c->stream>>>(iters / 8 + 1, 1.0, c->stats.as<double>() + 7);  // warm-up
+    float best = 1e30f;
+    for (int rep = 0; rep < 3; rep++) {
+        SD_CUDA(c, cudaEventRecord(c->ev0, c->stream));
+        k_dfma<<<blocks, 256, 0, c->stream>>>(iters, 1.0, c->stats.as<double>() + 7);
+        SD_CUDA(c, cudaEventRecord(c->ev1, c->stream));
+        SD_CUDA(c, cudaEventSynchronize(c->ev1));
+        float ms = 0;
+        SD_CUDA(c, cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+        if (ms < best) best = ms;
+    }
+    SD_TRY(sd_launch_check(c, "k_dfma"));
+    double fmas = (double)blocks * 256.0 * (double)iters * 64.0;
+    *tflops = 2.0 * fmas / (best * 1e-3) / 1e12;
+    return SD_OK;
+}
+
+int sd_timer_start(sd_ctx *c) {
+    if (!c) return SD_ERR_ARG;
+    SD_CUDA(c, cudaEventRecord(c->ev0, c->stream));
+    return SD_OK;
+}
+int sd_timer_stop(sd_ctx *c, float *ms) {
+    if (!c || !ms) return SD_ERR_ARG;
+    SD_CUDA(c, cudaEventRecord(c->ev1, c->stream));
+    SD_CUDA(c, cudaEventSynchronize(c->ev1));
+    SD_CUDA(c, cudaEventElapsedTime(ms, c->ev0, c->ev1));
+    return SD_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,120 @@
+// sd_internal.h -- context object and helpers shared by the translation units of libstardis_b200.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include <string>
+
+#include "../../include/stardis_b200.h"
+
+// ---- K2 line-record layout (device global memory, depth-major: rec[d * L + l]) ----------------------
+struct __align__(16) LineRec {
+    double nu;      // line frequency
+    double inv_dw;  // 1 / doppler width
+    double dw;      // doppler width (exact division in the near-core path)
+    double y;       // (gamma / (sqrt(pi) pi)) / dw            voigt.py:148
+    double K;       // alpha_line / (sqrt(pi) dw)              voigt.py:149, base.py:627
+    double thr;     // x^2 above which the pixel is certainly Humlicek region I (or -1: always)
+    double pad0, pad1;
+};
+static_assert(sizeof(LineRec) == 64, "LineRec must be 64 bytes");
+
+constexpr int SD_NCLS = 8;          // half-width classes
+constexpr int SD_CLS0_HW = 64;      // class 0: hw <= 64; class k: hw <= 64 * 4^k; last class: everything wider
+constexpr int SD_MAX_SOURCES = 4 + SD_MAX_TABLES;
+
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    template <class T>
+    T *as() const { return reinterpret_cast<T *>(p); }
+};
+
+struct sd_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;      // stream in use
+    cudaStream_t own_stream = nullptr;  // created by sd_create
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    std::string err;
+    int sm_count = 148;
+
+    // atmosphere
+    int D = 0;
+    double vmic = 0.0;
+    DevBuf T, ne, nH;
+
+    // grid
+    int64_t N = 0, p0 = 0, p1 = 0;
+    DevBuf nus;   // [N]
+    DevBuf d_nu;  // [1]
+
+    // lines
+    int64_t L = 0;
+    bool has_atomic_cols = false, has_vald_cols = false;
+    DevBuf l_nu, l_Z, l_ion, l_eion, l_eup, l_elo, l_A, l_mass, l_stark, l_waals, l_alpha;
+    DevBuf gammas, dws;
+    int gamma_cols = 0;
+    bool have_broadening = false;
+
+    // K2 preparation
+    DevBuf line_idx;   // int32 [L]
+    DevBuf rec;        // LineRec [D*L]
+    DevBuf win_lo;     // int32 [D*L]
+    DevBuf win_hi;     // int32 [D*L]
+    DevBuf win_cls;    // uint8 [D*L]
+    DevBuf cls_list;   // int32 [D*L]   per depth: lines of class 1.. concatenated by class (stable in l)
+    DevBuf cls_off;    // int32 [D*(NCLS+1)] offsets into cls_list row d (class 0 is not listed)
+    DevBuf chunk_cnt;  // int32 [D * nchunks * NCLS]
+    DevBuf stats;      // uint64 [8]
+    DevBuf alpha_line[2];
+    bool have_alpha[2] = {false, false};
+    bool records_ready = false;
+    bool line_stats = false;  // run the statistics-collecting instantiation of k_lines
+
+    // K3 / K4
+    DevBuf total;
+    bool have_total = false;
+    DevBuf src[SD_MAX_SOURCES];
+    bool have_src[SD_MAX_SOURCES] = {};
+    DevBuf cont_small;  // packed small arrays of the continuum descriptor
+    DevBuf F, I_nus, ray_small;
+    bool have_F = false;
+    int n_theta_tracked = 0;
+
+    int64_t W() const { return p1 - p0; }
+};
+
+int sd_fail(sd_ctx *c, int code, const char *fmt, ...);
+
+#define SD_CUDA(c, call)                                                                              \
+    do {                                                                                              \
+        cudaError_t _e = (call);                                                                      \
+        if (_e != cudaSuccess)                                                                        \
+            return sd_fail((c), SD_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(_e), \
+                           __FILE__, __LINE__);                                                       \
+    } while (0)
+
+#define SD_CHECK(c, cond, code, ...) \
+    do {                             \
+        if (!(cond)) return sd_fail((c), (code), __VA_ARGS__); \
+    } while (0)
+
+#define SD_TRY(expr)          \
+    do {                      \
+        int _r = (expr);      \
+        if (_r != SD_OK) return _r; \
+    } while (0)
+
+// grow-only device allocation / transfers (host or device source, UVA)
+int sd_ensure(sd_ctx *c, DevBuf &b, size_t bytes);
+int sd_upload(sd_ctx *c, DevBuf &b, const void *src, size_t bytes);
+int sd_launch_check(sd_ctx *c, const char *what);
+
+// kernel launchers implemented in the other translation units
+int sd_k1_broadening(sd_ctx *c, uint32_t flags);
+int sd_k2_prepare(sd_ctx *c);
+int sd_k2_lines(sd_ctx *c, int slot);
+int sd_k3_continuum(sd_ctx *c, const sd_continuum *desc, uint32_t store_mask);
+int sd_k4_raytrace(sd_ctx *c, int n_theta, const double *ray_ds, const double *weights, int inward, double scale,
+                   int track);

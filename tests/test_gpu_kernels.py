@@ -1,0 +1,198 @@
+"""GPU parity tests, kernel level: every CUDA kernel called through the C ABI (ctypes) against
+  * the golden vectors generated from the reference's unmodified code (tests/golden/), and
+  * the CPU oracle (oracle/) on seeded synthetic inputs.
+Tolerances are the north-star ones: rtol 1e-8 on alpha[depth, nu], 1e-6 on F_nu (most checks are far tighter)."""
+import numpy as np
+import pytest
+
+from conftest import golden
+
+pytestmark = pytest.mark.gpu
+
+RTOL_ALPHA = 1e-8
+RTOL_F = 1e-6
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    from stardis_b200.device import DeviceContext
+
+    c = DeviceContext(0)
+    yield c
+    c.close()
+
+
+def test_library_reports_blackwell(ctx):
+    assert b"sm_100a" in ctx.lib.sd_version()
+
+
+# ------------------------------------------------------------------ elementwise twins vs reference goldens
+def test_elementwise_vs_reference_golden(ctx):
+    g = golden("kernels_golden.npz")
+    w = ctx.faddeeva(g["fad_z"])
+    np.testing.assert_allclose(w.real, g["fad_w"].real, rtol=1e-11, atol=1e-300)
+    np.testing.assert_allclose(w.imag, g["fad_w"].imag, rtol=1e-10, atol=1e-17)
+    np.testing.assert_allclose(ctx.voigt_profile(g["vp_dnu"], g["vp_dw"], g["vp_gamma"]), g["vp_phi"], rtol=1e-11)
+    w0, w1, w2 = ctx.calc_weights(g["w_tau"])
+    np.testing.assert_allclose(w0, g["w0"], rtol=1e-13)
+    # w1, w2 are differences of O(tau^2) terms (base.py:41-45): the reference's own rounding noise is a few
+    # ulp of tau^2, hence the absolute floor
+    np.testing.assert_allclose(w1, g["w1"], rtol=1e-12, atol=2e-15)
+    np.testing.assert_allclose(w2, g["w2"], rtol=1e-12, atol=2e-15)
+    np.testing.assert_allclose(ctx.blackbody(g["bb_nus"], g["bb_T"]), g["bb"], rtol=1e-12)
+    np.testing.assert_allclose(ctx.gamma_linear_stark(g["b_nu"], g["b_nl"], g["b_ne"]), g["b_linear_stark"], rtol=1e-12)
+    np.testing.assert_allclose(ctx.gamma_quadratic_stark(g["b_zeff"], g["b_nu"], g["b_nl"], g["b_ne"], g["b_T"]),
+                               g["b_quadratic_stark"], rtol=1e-12)
+    np.testing.assert_allclose(ctx.gamma_van_der_waals(g["b_zeff"], g["b_nu"], g["b_nl"], g["b_T"], g["b_nH"]),
+                               g["b_van_der_waals"], rtol=1e-12)
+    np.testing.assert_allclose(ctx.n_effective(g["b_zeff"], g["b_eion"], g["b_elev"]), g["b_neff"], rtol=1e-13, equal_nan=True)
+    np.testing.assert_allclose(ctx.doppler_width(g["b_nuline"], g["b_T"], g["b_mass"], 1.3e5), g["b_doppler"], rtol=1e-13)
+
+
+def test_known_answers(ctx):
+    # the reference's own unit tests (test_voigt.py:22-37, 151-178; test_broadening.py:40-72, 146-177)
+    assert ctx.faddeeva(np.array([0.0 + 0j]))[0] == 1 + 0j
+    np.testing.assert_allclose(ctx.voigt_profile(0.0, 1.0, 0.0), 1 / np.sqrt(np.pi))
+    np.testing.assert_allclose(ctx.voigt_profile(0.0, 2.0, 0.0), 1 / (2 * np.sqrt(np.pi)))
+    np.testing.assert_allclose(ctx.doppler_width(2.99792458e10, 0.5, 1.380649e-16, 0.0), 1.0)
+    np.testing.assert_allclose(ctx.n_effective(1.0, 6.62607015e-27 * 2.99792458e10 * 109737.31568160, 0.0), 1.0)
+
+
+# ------------------------------------------------------------------ K1 broadening
+def _lines(g):
+    return {k[5:]: g[k] for k in g.files if k.startswith("line_")}
+
+
+@pytest.mark.parametrize("vald", [False, True])
+def test_k1_broadening_vs_reference_golden(ctx, vald):
+    from stardis_b200 import _lib as L
+
+    g = golden("broadening_golden.npz")
+    ln = _lines(g)
+    ctx.set_atmosphere(g["T"], g["n_e"], g["n_H"], float(g["vmic"]))
+    ctx.set_lines(ln["nu"], ln["alpha_line"], mass=ln["mass"], atomic_number=ln["atomic_number"], ion_number=ln["ion_number"],
+                  ionization_energy=ln["ionization_energy"], level_energy_upper=ln["level_energy_upper"],
+                  level_energy_lower=ln["level_energy_lower"], A_ul=ln["A_ul"], stark=ln["stark"], waals=ln["waals"])
+    cases = (15, 2, 4, 9) if vald else (0, 1, 2, 4, 8, 15, 10, 5)
+    for flags in cases:
+        ctx.calc_broadening(flags | (L.VALD if vald else 0))
+        gam = ctx.get(L.BUF_GAMMAS)
+        dws = ctx.get(L.BUF_DOPPLER)
+        ref = g[f"vald_gamma_{flags}"] if vald else g[f"gamma_{flags}"]
+        np.testing.assert_allclose(gam, ref, rtol=1e-11, equal_nan=True)
+        np.testing.assert_allclose(dws, g["doppler"], rtol=1e-13)
+
+
+# ------------------------------------------------------------------ K2 line opacity
+@pytest.mark.parametrize("case", ["a", "b", "c"])
+def test_k2_alan_entries_vs_reference_golden(ctx, oracle, case):
+    from stardis_b200 import _lib as L
+
+    g = golden("alan_golden.npz")
+    nus, ln, dws, gam, al = (g[f"{case}_{k}"] for k in ("nus", "line_nus", "dws", "gammas", "alphas"))
+    ref = g[f"{case}_out"]
+    D = dws.shape[1]
+    ctx.set_atmosphere(np.full(D, 5000.0))
+    ctx.set_grid(nus)
+    ctx.set_lines(ln, al)
+    ctx.set_broadening(gam, dws)
+    ctx.set_line_stats(True)
+    ctx.calc_alpha_line(0)
+    out = ctx.get(L.BUF_ALPHA_LINE)
+    st = ctx.line_stats()
+    ctx.set_line_stats(False)
+    assert np.array_equal(np.isnan(out), np.isnan(ref))
+    np.testing.assert_allclose(out, ref, rtol=RTOL_ALPHA, atol=1e-300, equal_nan=True)
+    np.testing.assert_allclose(out, ref, rtol=1e-10, atol=1e-300, equal_nan=True)  # in fact far tighter
+    assert np.array_equal(out == 0, ref == 0)  # identical windows: untouched pixels are exactly zero in both
+    # evaluation count and Humlicek region histogram are identical to the oracle's (same windows, same regions)
+    _, evals, hist = oracle.calc_alan_entries(D, nus, ln, dws, gam, al, with_stats=True)
+    assert st["evals"] == evals
+    assert np.array_equal(st["region_evals"], hist)
+    # deterministic: a second run is bitwise identical
+    ctx.calc_alpha_line(0)
+    assert np.array_equal(ctx.get(L.BUF_ALPHA_LINE), out, equal_nan=True)
+    # nu shard == the same columns of the full result
+    p0, p1 = nus.size // 3, nus.size // 3 + 300
+    ctx.set_grid(nus, p0, p1)
+    ctx.calc_alpha_line(0)
+    assert np.array_equal(ctx.get(L.BUF_ALPHA_LINE), out[:, p0:p1], equal_nan=True)
+
+
+def test_k2_vs_oracle_wide_and_narrow_classes(ctx, oracle):
+    """Seeded synthetic case with every half-width class populated (10 px ... full grid) on a grid of several
+    tiles, checked against the CPU oracle."""
+    from stardis_b200 import _lib as L
+
+    rng = np.random.default_rng(7)
+    N, Ln, D = 6000, 700, 5
+    lam = np.linspace(5000.0, 5060.0, N, endpoint=False)
+    nus = 2.99792458e18 / lam
+    line_nus = np.sort(rng.uniform(nus.min(), nus.max(), Ln))
+    dws = rng.uniform(1.5e9, 4e9, (Ln, D))
+    gam = 10.0 ** rng.uniform(7, 10, (Ln, D))
+    d_nu = oracle.d_nu(nus)
+    target_hw = 10.0 ** rng.uniform(0.5, 4.2, (Ln, D))  # 3 ... 16000 pixels
+    al = target_hw * d_nu / 20.0 / (gam + dws)
+    ref, evals, hist = oracle.calc_alan_entries(D, nus, line_nus, dws, gam, al, with_stats=True)
+    ctx.set_atmosphere(np.full(D, 5000.0))
+    ctx.set_grid(nus)
+    ctx.set_lines(line_nus, al)
+    ctx.set_broadening(gam, dws)
+    ctx.set_line_stats(True)
+    ctx.calc_alpha_line(0)
+    out = ctx.get(L.BUF_ALPHA_LINE)
+    st = ctx.line_stats()
+    ctx.set_line_stats(False)
+    assert st["evals"] == evals and np.array_equal(st["region_evals"], hist)
+    assert hist.min() > 0  # all four Humlicek regions exercised
+    np.testing.assert_allclose(out, ref, rtol=1e-10, atol=0)
+
+
+# ------------------------------------------------------------------ K4 formal solver
+def test_k4_raytrace_vs_reference_golden(ctx, oracle):
+    from stardis_b200 import _lib as L
+
+    g = golden("raytrace_golden.npz")
+    nus, T, alphas = g["nus"], g["T"], g["alphas"]
+    ctx.set_atmosphere(T)
+    ctx.set_grid(nus)
+    ctx.set_total(alphas)
+    # single angle == single_theta_trace_parallel
+    th = g["thetas_3"][1]
+    ctx.raytrace((np.diff(g["r"]) / np.cos(th)).reshape(-1, 1), np.array([1.0]))
+    I = ctx.get(L.BUF_F_NU)
+    np.testing.assert_allclose(I, g["I_single"], rtol=1e-9, atol=1e-300)
+    # plane-parallel, 10 angles, tracked intensities
+    th, w = oracle.thetas_and_weights(10)
+    ds = np.diff(g["r_pp"]).reshape(-1, 1) / np.cos(th)
+    ctx.raytrace(ds, w, track=True)
+    np.testing.assert_allclose(ctx.get(L.BUF_F_NU), g["F_pp"], rtol=RTOL_F, atol=1e-300)
+    np.testing.assert_allclose(ctx.get(L.BUF_F_NU), g["F_pp"], rtol=1e-9, atol=1e-300)
+    np.testing.assert_allclose(ctx.get(L.BUF_I_NUS), g["I_pp"], rtol=1e-9, atol=1e-300)
+    # spherical with inward rays
+    th, w = oracle.thetas_and_weights(4)
+    ds = oracle.calculate_spherical_ray(th, g["r_sph"])
+    np.testing.assert_allclose(ds, g["sph_ray"], rtol=1e-13, atol=1e-300)
+    scale = (g["r_sph"][-1] / float(g["refr_sph"])) ** 2
+    ctx.raytrace(ds, w, inward_rays=True, scale=scale, track=True)
+    np.testing.assert_allclose(ctx.get(L.BUF_F_NU), g["F_sph"], rtol=1e-9, atol=1e-300)
+    np.testing.assert_allclose(ctx.get(L.BUF_I_NUS), g["I_sph"], rtol=1e-9, atol=1e-300)
+    # emergent row accessor
+    np.testing.assert_allclose(ctx.get_row(L.BUF_F_NU, -1), g["F_sph"][-1], rtol=1e-9)
+
+
+def test_k4_many_angles_chunked(ctx, oracle):
+    """More than 20 angles takes several launches that accumulate into F_nu."""
+    from stardis_b200 import _lib as L
+
+    g = golden("raytrace_golden.npz")
+    nus, T, alphas = g["nus"][:64], g["T"], np.ascontiguousarray(g["alphas"][:, :64])
+    th, w = oracle.thetas_and_weights(27)
+    F, I_nus = oracle.raytrace(T, alphas, nus, th, w, dist=np.diff(g["r_pp"]), track=True)
+    ctx.set_atmosphere(T)
+    ctx.set_grid(nus)
+    ctx.set_total(alphas)
+    ctx.raytrace(np.diff(g["r_pp"]).reshape(-1, 1) / np.cos(th), w, track=True)
+    np.testing.assert_allclose(ctx.get(L.BUF_F_NU), F, rtol=1e-9, atol=1e-300)
+    np.testing.assert_allclose(ctx.get(L.BUF_I_NUS), I_nus, rtol=1e-9, atol=1e-300)

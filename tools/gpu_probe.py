@@ -1,0 +1,44 @@
+"""Quick device probe: FP64 FMA peak, K1/K2 throughput on a slice of the solar workload (not the bench)."""
+import os
+import sys
+import time
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from stardis_b200 import _lib as L  # noqa: E402
+from stardis_b200.device import DeviceContext  # noqa: E402
+from stardis_b200.synthetic import make_workload  # noqa: E402
+
+n_lines = int(sys.argv[1]) if len(sys.argv) > 1 else 20000
+ctx = DeviceContext(0)
+print("dfma TFLOP/s", ctx.bench_dfma(4096), ctx.bench_dfma(8192))
+w = make_workload("solar_full", n_lines=n_lines)
+p, m = w["plasma"], w["model"]
+lt = p.line_table.with_masses(m.composition.nuclide_masses)
+T = w["atmosphere"]["T"]
+ctx.set_atmosphere(T, p.electron_densities.values, p.ion_number_density.loc[1, 0].values, w["atmosphere"]["vmic"])
+ctx.set_grid(w["nus"])
+ctx.set_lines(lt.nu, lt.alpha_line, mass=lt.mass, atomic_number=lt.atomic_number, ion_number=lt.ion_number,
+              ionization_energy=lt.ionization_energy, level_energy_upper=lt.level_energy_upper,
+              level_energy_lower=lt.level_energy_lower, A_ul=lt.A_ul)
+ctx.synchronize()
+for rep in range(3):
+    ctx.timer_start()
+    ctx.calc_broadening(15)
+    t1 = ctx.timer_stop()
+    ctx.timer_start()
+    ctx.calc_alpha_line(0)
+    t2 = ctx.timer_stop()
+    print(f"rep {rep}: K1 {t1:.3f} ms, K2(prep+lines) {t2:.3f} ms")
+ctx.set_line_stats(True)
+ctx.calc_alpha_line(0)
+st = ctx.line_stats()
+ctx.set_line_stats(False)
+print("stats", st)
+ctx.timer_start()
+ctx.calc_alpha_line(0)
+t2 = ctx.timer_stop()
+print(f"K2 lines only {t2:.3f} ms -> {st['evals'] / t2 / 1e6:.1f} Gevals/s")
+a = ctx.get(L.BUF_ALPHA_LINE)
+print("alpha_line finite", np.isfinite(a).all(), a.min(), a.max())
