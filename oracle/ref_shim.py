@@ -257,6 +257,7 @@ class Reference:
         self.blackbody = _load(
             "stardis.radiation_field.source_functions.blackbody", base + "source_functions/blackbody.py"
         )
+        self.opacities_container = _load("stardis.radiation_field.opacities.base", base + "opacities/base.py")
         self.solver = _load(
             "stardis.radiation_field.radiation_field_solvers.base", base + "radiation_field_solvers/base.py"
         )

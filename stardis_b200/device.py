@@ -7,6 +7,7 @@ every copy itself (UVA).  Nothing here falls back to the CPU.
 from __future__ import annotations
 
 import ctypes as C
+import weakref
 
 import numpy as np
 
@@ -29,6 +30,8 @@ class DeviceContext:
         self.p0 = self.p1 = 0
         self.L = 0
         self.n_theta = 0
+        self._live = weakref.WeakSet()  # DeviceArray results that still point into this context's buffers
+        self.owner = None               # token of the RadiationField whose opacities/flux the buffers hold
         if stream is not None:
             self.set_stream(stream)
 
@@ -67,6 +70,18 @@ class DeviceContext:
     @property
     def W(self):
         return self.p1 - self.p0
+
+    def track(self, device_array):
+        self._live.add(device_array)
+        return device_array
+
+    def evict(self):
+        """Copy every still-referenced, not yet materialised result to the host: called before the buffers are
+        reused for another radiation field."""
+        for a in list(self._live):
+            a.detach_to_host()
+        self._live.clear()
+        self.owner = None
 
     # ------------------------------------------------------------------ inputs
     def set_atmosphere(self, T, n_e=None, n_HI=None, vmic_cgs=0.0):

@@ -1,0 +1,162 @@
+"""Broadening (stardis/radiation_field/opacities/opacities_solvers/broadening.py), computed on the device.
+
+Elementwise functions (``calc_doppler_width``, ``calc_n_effective``, ``calc_gamma_linear_stark``,
+``calc_gamma_quadratic_stark``, ``calc_gamma_van_der_waals`` and their ``*_cuda`` namesakes, broadening.py:32-547)
+broadcast their arguments like the reference's numba ufuncs and run the ``sd_ew_*`` kernels.  ``calculate_broadening``
+/ ``calculate_molecule_broadening`` (broadening.py:659-821) take the reference's arguments and run kernel K1
+(csrc/k1_broadening.cu) for all (line, depth) pairs at once.
+"""
+from __future__ import annotations
+
+import logging
+
+import numpy as np
+
+from .... import _lib as L
+from .... import units as u
+from ....device import default_context
+
+logger = logging.getLogger(__name__)
+
+_FLAG = {"linear_stark": L.LINEAR_STARK, "quadratic_stark": L.QUADRATIC_STARK, "van_der_waals": L.VAN_DER_WAALS,
+         "radiation": L.RADIATION}
+
+
+def broadening_flags(broadening_line_opacity_config):
+    """Membership tests of broadening.py:688-691 -> kernel flag word."""
+    return sum(bit for name, bit in _FLAG.items() if name in broadening_line_opacity_config)
+
+
+def calc_doppler_width(nu_line, temperature, atomic_mass, microturbulence=0.0):
+    """broadening.py:32-71."""
+    return _scalarize(default_context().doppler_width(nu_line, temperature, atomic_mass, float(microturbulence)),
+                      nu_line, temperature, atomic_mass)
+
+
+def calc_n_effective(ion_number, ionization_energy, level_energy):
+    """broadening.py:114-146 (NaN where the level lies above the ionisation energy)."""
+    return _scalarize(default_context().n_effective(ion_number, ionization_energy, level_energy), ion_number,
+                      ionization_energy, level_energy)
+
+
+def calc_gamma_linear_stark(n_eff_upper, n_eff_lower, electron_density):
+    """broadening.py:193-234."""
+    return _scalarize(default_context().gamma_linear_stark(n_eff_upper, n_eff_lower, electron_density), n_eff_upper,
+                      n_eff_lower, electron_density)
+
+
+def calc_gamma_quadratic_stark(ion_number, n_eff_upper, n_eff_lower, electron_density, temperature):
+    """broadening.py:281-360."""
+    return _scalarize(default_context().gamma_quadratic_stark(ion_number, n_eff_upper, n_eff_lower, electron_density,
+                                                              temperature), ion_number, n_eff_upper, n_eff_lower,
+                      electron_density, temperature)
+
+
+def calc_gamma_van_der_waals(ion_number, n_eff_upper, n_eff_lower, temperature, h_density):
+    """broadening.py:420-490."""
+    return _scalarize(default_context().gamma_van_der_waals(ion_number, n_eff_upper, n_eff_lower, temperature, h_density),
+                      ion_number, n_eff_upper, n_eff_lower, temperature, h_density)
+
+
+def _scalarize(out, *args):
+    return float(out) if all(np.ndim(a) == 0 for a in args) else out
+
+
+def _cuda_alias(fn):
+    def wrapper(*args, nthreads=256, ret_np_ndarray=True, dtype=float):
+        return fn(*args)
+
+    wrapper.__doc__ = f"numba.cuda twin of {fn.__name__} in the reference; same kernel here."
+    return wrapper
+
+
+calc_doppler_width_cuda = _cuda_alias(calc_doppler_width)
+calc_n_effective_cuda = _cuda_alias(calc_n_effective)
+calc_gamma_linear_stark_cuda = _cuda_alias(calc_gamma_linear_stark)
+calc_gamma_quadratic_stark_cuda = _cuda_alias(calc_gamma_quadratic_stark)
+calc_gamma_van_der_waals_cuda = _cuda_alias(calc_gamma_van_der_waals)
+
+
+def _line_columns(lines):
+    """Per-line columns from a pandas DataFrame (reference) or a ColumnarLines (fast path)."""
+    get = (lambda k: lines[k].values) if hasattr(lines, "columns") else (lambda k: getattr(lines, k))
+    has = (lambda k: k in lines.columns) if hasattr(lines, "columns") else (lambda k: getattr(lines, k, None) is not None)
+    return get, has
+
+
+def upload_lines_and_broaden(ctx, lines, alphas_array, masses, stellar_model, stellar_plasma, flags):
+    """Upload a (sorted, range-selected) line table and run K1.  ``lines``: DataFrame or ColumnarLines."""
+    get, has = _line_columns(lines)
+    vald = bool(flags & L.VALD)
+    ctx.set_lines(get("nu"), alphas_array, mass=masses, atomic_number=get("atomic_number"), ion_number=get("ion_number"),
+                  ionization_energy=get("ionization_energy"), level_energy_upper=get("level_energy_upper"),
+                  level_energy_lower=get("level_energy_lower"), A_ul=get("A_ul"),
+                  stark=get("stark") if vald and has("stark") else None,
+                  waals=get("waals") if vald and has("waals") else None)
+    ctx.calc_broadening(flags)
+
+
+def set_device_atmosphere(ctx, stellar_model, stellar_plasma):
+    T = u.values_of(stellar_model.temperatures)
+    n_e = np.asarray(stellar_plasma.electron_densities.values, dtype=np.float64) if stellar_plasma is not None else None
+    n_H = (np.asarray(stellar_plasma.ion_number_density.loc[1, 0].values, dtype=np.float64)
+           if stellar_plasma is not None else None)
+    vmic = float(u.cgs_values_of(stellar_model.microturbulence))
+    ctx.set_atmosphere(T, n_e, n_H, vmic)
+
+
+def _masses_of(lines, stellar_model):
+    get, has = _line_columns(lines)
+    if has("mass"):
+        return np.asarray(get("mass"), dtype=np.float64)
+    return np.asarray(stellar_model.composition.nuclide_masses.loc[get("atomic_number")].values, dtype=np.float64)
+
+
+def calculate_broadening(lines, stellar_model, stellar_plasma, broadening_line_opacity_config, use_vald_broadening=False):
+    """broadening.py:659-732 -> (gammas (L,D), doppler_widths (L,D)) as numpy arrays."""
+    flags = broadening_flags(broadening_line_opacity_config) | (L.VALD if use_vald_broadening else 0)
+    logger.info("Using VALD broadening parameters." if use_vald_broadening else "Calculating broadening parameters.")
+    ctx = default_context()
+    ctx.evict()
+    set_device_atmosphere(ctx, stellar_model, stellar_plasma)
+    get, _ = _line_columns(lines)
+    n = len(get("nu"))
+    dummy_alpha = np.zeros((n, stellar_model.no_of_depth_points))
+    upload_lines_and_broaden(ctx, lines, dummy_alpha, _masses_of(lines, stellar_model), stellar_model, stellar_plasma, flags)
+    return ctx.get(L.BUF_GAMMAS), ctx.get(L.BUF_DOPPLER)
+
+
+def molecule_masses(lines, stellar_model, stellar_plasma):
+    """Sum of the two constituent nuclide masses (broadening.py:808-813)."""
+    ions = stellar_plasma.molecule_ion_map.loc[lines.molecule]
+    m1 = stellar_model.composition.nuclide_masses.loc[ions.Ion1].values
+    m2 = stellar_model.composition.nuclide_masses.loc[ions.Ion2].values
+    return np.asarray(m1 + m2, dtype=np.float64)
+
+
+def molecule_gammas(lines, stellar_model, broadening_line_opacity_config):
+    """Non-VALD branch of calculate_molecule_broadening (broadening.py:799-806): gamma = A_ul with shape (L,1) when
+    radiation broadening is configured.  Without it the reference dereferences a non-existent attribute
+    (``geometry.no_of_depth_points``) and raises AttributeError; the same exception type is raised here."""
+    if "radiation" in broadening_line_opacity_config:
+        return np.ascontiguousarray(lines.A_ul.values[:, np.newaxis], dtype=np.float64)
+    raise AttributeError("'Radial1DGeometry' object has no attribute 'no_of_depth_points'")
+
+
+def calculate_molecule_broadening(lines, stellar_model, stellar_plasma, broadening_line_opacity_config,
+                                  use_vald_broadening=False):
+    """broadening.py:735-821 for the branch the reference actually reaches (use_vald_broadening is never passed by
+    its caller, opacities_solvers/base.py:469-474).  Doppler widths on the device."""
+    if use_vald_broadening:
+        raise NotImplementedError("molecular VALD broadening is unreachable in the reference's call graph")
+    gammas = molecule_gammas(lines, stellar_model, broadening_line_opacity_config)
+    masses = molecule_masses(lines, stellar_model, stellar_plasma)
+    T = u.values_of(stellar_model.temperatures)
+    vmic = float(u.cgs_values_of(stellar_model.microturbulence))
+    dws = default_context().doppler_width(lines.nu.values[:, np.newaxis], T[np.newaxis, :], masses[:, np.newaxis], vmic)
+    return gammas, dws
+
+
+def rotation_broadening(*args, **kwargs):
+    """Out of the hot-path scope (post-hoc spectrum convolution, broadening.py:824-877)."""
+    raise NotImplementedError("rotation_broadening is outside the B200 hot path; use the reference implementation")
