@@ -25,16 +25,18 @@ DEPTH_ROWS = [0, 11, 27, 40, 50, 55]
 # configurations exercised (opacity section of the YAML, as dicts)
 CASES = {
     # benchmark_config.yml-like: H- bf file, H I bf+ff, all four broadenings
+    # (use_vald_broadening: false makes the reference drop auto-ionising lines, opacities_solvers/base.py:413-421)
     "bench": dict(file={"Hminus_bf": "Hminus_bf"}, bf={"H_I": {}}, ff={"H_I": {}}, rayleigh=[],
                   disable_electron_scattering=False,
-                  line=dict(disable=False, broadening=["radiation", "linear_stark", "quadratic_stark", "van_der_waals"])),
+                  line=dict(disable=False, broadening=["radiation", "linear_stark", "quadratic_stark", "van_der_waals"],
+                            vald_linelist=dict(use_vald_broadening=False))),
     # stardis_test_config_broadening.yml-like: three file opacities + Rayleigh
     "broadening": dict(file={"Hminus_bf": "Hminus_bf", "Hminus_ff": "Hminus_ff", "H2plus_bf": "H2plus_bf"}, bf={"H_I": {}},
                        ff={"H_I": {}}, rayleigh=["H", "He", "H2"], disable_electron_scattering=False,
                        line=dict(disable=False, broadening=["radiation", "linear_stark", "quadratic_stark", "van_der_waals"])),
     # stardis_test_config.yml-like: no electron scattering, no broadening
     "plain": dict(file={}, bf={"H_I": {}}, ff={"H_I": {}}, rayleigh=[], disable_electron_scattering=True,
-                  line=dict(disable=False, broadening=[])),
+                  line=dict(disable=False, broadening=[], vald_linelist=dict(use_vald_broadening=False))),
     # VALD line list with VALD broadening parameters
     "vald": dict(file={}, bf={}, ff={}, rayleigh=["H"], disable_electron_scattering=False,
                  line=dict(disable=False, broadening=["radiation", "quadratic_stark", "van_der_waals"],
@@ -63,9 +65,15 @@ def case_inputs(name, opacity, table_paths):
     vald = cfg.opacity.line.vald_linelist.use_linelist
     plasma = create_synthetic_plasma(atm, 300, nus.min() * 0.999, nus.max() * 1.001, seed=11, strong_fraction=0.02, vald=vald,
                                      log_alpha=(-2.0, 6.0), log_alpha_strong=(7.0, 9.0))
-    # a few auto-ionising lines: dropped by the non-VALD path, kept (NaN-free: VALD parameters) otherwise
-    lt = plasma.line_table
-    lt.level_energy_upper[::47] = lt.ionization_energy[::47] * 1.02
+    # A few auto-ionising lines where the reference drops them (use_vald_broadening false) or where their broadening
+    # does not involve n_eff (VALD parameters).  With the default flag they would carry NaN gammas, and what the
+    # reference's fastmath-compiled line loop does with NaN depends on the numba specialisation (observed: NaN
+    # written to +-10 pixels for one array layout, nothing written for another) -- not a parity target.
+    lt = plasma._line_table
+    if name in ("bench", "plain", "vald"):
+        lt.level_energy_upper[::47] = lt.ionization_energy[::47] * 1.02
+        if vald:
+            lt.waals[::47] = -7.5  # scaled-gamma form: no n_eff involved
     return cfg, model, plasma, nus
 
 
@@ -110,7 +118,7 @@ def main(R):
         out[f"{name}__total"] = np.asarray(total)
         out[f"{name}__F_nu"] = srf.F_nu
         out[f"{name}__I_nus_emergent"] = srf.I_nus[-1]
-        out[f"{name}__fingerprint"] = np.array([plasma.line_table.nu.sum(), plasma.line_table.alpha_line.sum(),
+        out[f"{name}__fingerprint"] = np.array([plasma._line_table.nu.sum(), plasma._line_table.alpha_line.sum(),
                                                 plasma.electron_densities.values.sum(), nus.sum()])
         print(name, {k: np.shape(v) for k, v in srf.opacities.opacities_dict.items()})
     np.savez_compressed(os.path.join(OUT, "pipeline_golden.npz"), **out)

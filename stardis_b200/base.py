@@ -81,11 +81,16 @@ class STARDISOutput:
         self.lambdas = u.Quantity(u.values_of(self.nus), u.Hz).to(u.AA, u.spectral())
         emergent = np.asarray(stellar_radiation_field.F_nu[-1], dtype=np.float64)
         shard = getattr(stellar_radiation_field, "shard", None)
-        if shard is not None and emergent.shape[0] != len(self.nus):
-            from .distributed import allgather_spectrum
-
-            emergent = allgather_spectrum(emergent, shard, len(self.nus))
         nus = u.values_of(self.nus)
+        lambdas = self.lambdas.value
+        if shard is not None and emergent.shape[0] != len(nus):
+            from .distributed import allgather_spectrum, dist_info
+
+            if dist_info()[0] is not None:
+                emergent = allgather_spectrum(emergent, shard, len(nus))
+            else:  # single process evaluating one shard: the spectrum covers pixels [p0, p1) only
+                self.shard = (int(shard[0]), int(shard[1]))
+                nus, lambdas = nus[shard[0]:shard[1]], lambdas[shard[0]:shard[1]]
         self.spectrum_nu = u.Quantity(emergent, "erg/s/cm2/Hz")
         # F_lambda [erg/s/cm^2/A] = F_nu * nu / lambda
-        self.spectrum_lambda = u.Quantity(emergent * nus / self.lambdas.value, "erg/s/cm2/AA")
+        self.spectrum_lambda = u.Quantity(emergent * nus / lambdas, "erg/s/cm2/AA")

@@ -30,7 +30,7 @@ class DeviceContext:
         self.p0 = self.p1 = 0
         self.L = 0
         self.n_theta = 0
-        self._live = weakref.WeakSet()  # DeviceArray results that still point into this context's buffers
+        self._live = []  # weak references to DeviceArray results that still point into this context's buffers
         self.owner = None               # token of the RadiationField whose opacities/flux the buffers hold
         if stream is not None:
             self.set_stream(stream)
@@ -72,14 +72,16 @@ class DeviceContext:
         return self.p1 - self.p0
 
     def track(self, device_array):
-        self._live.add(device_array)
+        self._live.append(weakref.ref(device_array))
         return device_array
 
     def evict(self):
         """Copy every still-referenced, not yet materialised result to the host: called before the buffers are
         reused for another radiation field."""
-        for a in list(self._live):
-            a.detach_to_host()
+        for ref in self._live:
+            a = ref()
+            if a is not None:
+                a.detach_to_host()
         self._live.clear()
         self.owner = None
 

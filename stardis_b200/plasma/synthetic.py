@@ -37,7 +37,8 @@ class SyntheticPlasma:
         self.h_minus_density = pd.Series(h_minus, index=cols)
         self.h2_density = pd.Series(h2, index=cols)
         self.h2_plus_density = pd.Series(h2_plus, index=cols)
-        self.line_table = line_table
+        self._line_table = line_table
+        self.expose_columnar = True  # False: only the tardis-style pandas tables are visible (adapter tests)
         self.molecule_line_table = molecule_table
         # hydrogen levels for the hydrogenic bound-free opacity
         if h_levels is None:
@@ -48,9 +49,14 @@ class SyntheticPlasma:
         self.levels = lidx
         self.excitation_energy = pd.Series(e_exc, index=lidx)
         self.level_number_density = pd.DataFrame(n_lev, index=lidx, columns=cols)
-        iidx = pd.MultiIndex.from_tuples([(1, 1), (2, 1), (2, 2)], names=["atomic_number", "ion_number"])
-        self.ionization_data = pd.Series(np.array([13.598434, 24.587388, 54.417763]) * EV_ERG, index=iidx,
-                                         name="ionization_energy")
+        ion_rows = {(2, 1): 24.587388, (2, 2): 54.417763}
+        for z, (first, second) in IONIZATION_EV.items():
+            ion_rows[(z, 1)] = first
+            if z > 1:
+                ion_rows[(z, 2)] = second
+        keys = sorted(ion_rows)
+        iidx = pd.MultiIndex.from_tuples(keys, names=["atomic_number", "ion_number"])
+        self.ionization_data = pd.Series(np.array([ion_rows[k] for k in keys]) * EV_ERG, index=iidx, name="ionization_energy")
         self._pandas = None
 
     # ---- pandas views with the reference's layout (built on demand; used by the golden generator and the
@@ -58,7 +64,7 @@ class SyntheticPlasma:
     def _build_pandas(self):
         if self._pandas is not None:
             return self._pandas
-        lt = self.line_table
+        lt = self._line_table
         L = len(lt)
         # give every line its own (lower, upper) level numbers so that the reference's merges are exercised
         lower = np.arange(L) * 2
@@ -70,14 +76,14 @@ class SyntheticPlasma:
                                              np.stack([lower, upper], 1).ravel()],
                                             names=["atomic_number", "ion_number", "level_number"])
         energy = pd.Series(np.stack([lt.level_energy_lower, lt.level_energy_upper], 1).ravel(), index=lev_idx, name="energy")
-        # ionisation energies per (Z, ion+1): lines of one ion share the value of their first line
-        key = pd.MultiIndex.from_arrays([lt.atomic_number, lt.ion_number + 1], names=["atomic_number", "ion_number"])
-        ion = pd.Series(lt.ionization_energy, index=key, name="ionization_energy")
-        ion = ion[~ion.index.duplicated()]
         alpha = pd.DataFrame(lt.alpha_line, index=lines.index)
         alpha["nu"] = lt.nu
-        self._pandas = dict(lines=lines, levels_energy=energy, ionization=ion, alpha=alpha)
+        self._pandas = dict(lines=lines, levels_energy=energy, alpha=alpha)
         return self._pandas
+
+    @property
+    def line_table(self):
+        return self._line_table if self.expose_columnar else None
 
     @property
     def lines(self):
@@ -93,7 +99,7 @@ class SyntheticPlasma:
 
     @property
     def lines_from_linelist(self):
-        lt = self.line_table
+        lt = self._line_table
         df = pd.DataFrame({k: getattr(lt, k) for k in ("nu", "atomic_number", "ion_number", "ionization_energy",
                                                        "level_energy_lower", "level_energy_upper", "A_ul")})
         if lt.stark is not None:
@@ -102,9 +108,16 @@ class SyntheticPlasma:
 
     @property
     def alpha_line_from_linelist(self):
-        a = pd.DataFrame(self.line_table.alpha_line)
-        a["nu"] = self.line_table.nu
+        a = pd.DataFrame(self._line_table.alpha_line)
+        a["nu"] = self._line_table.nu
         return a
+
+
+# first and second ionisation energies [eV] of the elements the synthetic line list draws from
+IONIZATION_EV = {1: (13.598434, 13.598434), 6: (11.2603, 24.3833), 7: (14.5341, 29.6013), 8: (13.6181, 35.1211),
+                 11: (5.1391, 47.2864), 12: (7.6462, 15.0353), 13: (5.9858, 18.8286), 14: (8.1517, 16.3459),
+                 20: (6.1132, 11.8717), 22: (6.8281, 13.5755), 23: (6.7462, 14.618), 24: (6.7665, 16.4857),
+                 25: (7.4340, 15.6400), 26: (7.9025, 16.1992), 27: (7.8810, 17.084), 28: (7.6399, 18.1688)}
 
 
 def saha_hydrogen(T, n_e):
@@ -126,13 +139,15 @@ def synthetic_line_table(rng, n_lines, nu_min, nu_max, T, strong_fraction=0.005,
     pz = np.array([2, 3, 2, 3, 2, 4, 2, 4, 5, 8, 5, 8, 5, 30, 6, 11], dtype=float)
     Z = rng.choice(zs, size=L, p=pz / pz.sum()).astype(np.int64)
     ion = np.where(Z == 1, 0, (rng.random(L) < 0.35).astype(np.int64)).astype(np.int64)
-    e_ion = np.where(Z == 1, 13.598434, rng.uniform(5.5, 11.5, L) + 8.0 * ion) * EV_ERG
+    h_nu = H_CGS * nu
+    # ionisation energy is a property of the ion (the reference joins it on (atomic_number, ion_number));
     # upper level at least `gap` below the continuum so that n_eff stays in the physical range (<~ 8)
     gap = 0.25 * EV_ERG * (ion + 1.0) ** 2
-    h_nu = H_CGS * nu
-    room = e_ion - gap - h_nu
-    low = room <= 0  # photon energy too large for this ion: raise the ionisation energy
-    e_ion[low] = (h_nu[low] + gap[low]) * rng.uniform(1.05, 1.6, int(low.sum()))
+    e_ion = np.array([IONIZATION_EV[z][i] for z, i in zip(Z, ion)]) * EV_ERG
+    tight = e_ion - gap - h_nu <= 0.05 * EV_ERG  # photon does not fit below this ion's continuum: make it Fe II
+    Z[tight], ion[tight] = 26, 1
+    gap = 0.25 * EV_ERG * (ion + 1.0) ** 2
+    e_ion = np.array([IONIZATION_EV[z][i] for z, i in zip(Z, ion)]) * EV_ERG
     room = e_ion - gap - h_nu
     e_lo = rng.uniform(0.0, 1.0, L) * np.minimum(room, 0.8 * e_ion)
     e_up = e_lo + h_nu

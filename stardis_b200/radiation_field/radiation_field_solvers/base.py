@@ -11,7 +11,7 @@ import numpy as np
 from ... import _lib as L
 from ... import units as u
 from ...device import default_context
-from ...device_array import DeviceArray
+from ...device_array import DeviceArray, as_host
 
 
 def calc_weights_parallel(delta_tau):
@@ -87,10 +87,15 @@ def raytrace(stellar_model, stellar_radiation_field):
         scale = float((r[-1] / float(u.cgs_values_of(stellar_model.geometry.reference_r))) ** 2)
     track = bool(getattr(srf, "track_individual_intensities", False))
     previous = srf._F_nu if hasattr(srf, "_F_nu") else getattr(srf, "F_nu", None)
+    prev_host = None
+    if previous is not None:
+        arr = as_host(previous)  # materialises a device-backed F_nu BEFORE its buffer is overwritten
+        if np.any(arr != 0):
+            prev_host = arr
     ctx.raytrace(ds, np.asarray(srf.I_nus_weights, dtype=np.float64), inward_rays=inward, scale=scale, track=track)
     F = ctx.track(DeviceArray(ctx, L.BUF_F_NU, (D, W)))
-    if previous is not None and not isinstance(previous, DeviceArray) and np.any(np.asarray(previous) != 0):
-        F = (np.asarray(previous) * scale) + F.numpy()  # `F_nu +=` then `*= correction` (base.py:336-344)
+    if prev_host is not None:
+        F = (prev_host * scale) + F.numpy()  # `F_nu +=` then `*= correction` (base.py:336-344)
     srf.F_nu = F
     if track:
         srf.I_nus = ctx.track(DeviceArray(ctx, L.BUF_I_NUS, (D, W, len(srf.thetas))))
