@@ -52,7 +52,8 @@ int sd_create(sd_ctx **ctx, int device);
 void sd_destroy(sd_ctx *ctx);
 const char *sd_last_error(const sd_ctx *ctx);
 const char *sd_version(void);
-int sd_set_stream(sd_ctx *ctx, void *cuda_stream); /* cudaStream_t; NULL = the context's own stream */
+int sd_set_stream(sd_ctx *ctx, void *cuda_stream); /* cudaStream_t; NULL = the context's own stream;
+                                                     * pass cudaStreamLegacy (0x1) for the legacy default stream */
 int sd_synchronize(sd_ctx *ctx);
 /* pinned host staging buffers for callers without torch (cudaHostAlloc / cudaFreeHost) */
 int sd_host_alloc(void **ptr, int64_t bytes);
@@ -200,6 +201,8 @@ int sd_ew_calc_weights(sd_ctx *ctx, int64_t n, const double *tau, double *w0, do
 int sd_bench_dfma(sd_ctx *ctx, int32_t iters, double *tflops);
 /* time of the device work enqueued between the two calls, in ms, measured with CUDA events on the
  * context's stream (sd_timer_stop synchronises). */
+/* number of kernels this context has launched so far (bench.py's gpu_launches claim) */
+int64_t sd_launch_count(const sd_ctx *ctx);
 int sd_timer_start(sd_ctx *ctx);
 int sd_timer_stop(sd_ctx *ctx, float *ms);
 

@@ -3,8 +3,6 @@ every continuum term) and raytrace, run UNMODIFIED on the duck-typed synthetic p
 
 TEST INFRASTRUCTURE (build container only; see make_golden.py).  Writes
   tests/golden/pipeline_golden.npz   reference outputs per configuration + fingerprints of the seeded inputs
-  tests/golden/tables.npz            numeric content of the three cross-section tables shipped with the reference
-                                     (stardis/data/*.dat), so that tests can recreate the files on the GPU box
 """
 from __future__ import annotations
 
@@ -79,17 +77,6 @@ def case_inputs(name, opacity, table_paths):
 
 def main(R):
     os.makedirs(OUT, exist_ok=True)
-    tables = {}
-    for src, fn in TABLE_FILES.items():
-        path = os.path.join(DATA, fn)
-        if src == "Hminus_bf":
-            tab = np.array([[float(v) for v in ln.split(",")] for ln in open(path).read().splitlines()
-                            if ln.strip() and not ln.lstrip().startswith("#")])
-            tables[f"{src}_x"], tables[f"{src}_values"] = tab[:, 0], tab[:, 1]
-        else:
-            xs, ys, vals = O._read_table_2d(path, src)
-            tables[f"{src}_x"], tables[f"{src}_y"], tables[f"{src}_values"] = (xs / 10.0 if src == "H2plus_bf" else xs), ys, vals
-    np.savez_compressed(os.path.join(OUT, "tables.npz"), **tables)
     table_paths = {src: os.path.join(DATA, fn) for src, fn in TABLE_FILES.items()}
 
     out = {}

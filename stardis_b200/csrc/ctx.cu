@@ -42,6 +42,7 @@ int sd_upload(sd_ctx *c, DevBuf &b, const void *src, size_t bytes) {
 }
 
 int sd_launch_check(sd_ctx *c, const char *what) {
+    c->launches++;
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return sd_fail(c, SD_ERR_CUDA, "launch of %s failed: %s", what, cudaGetErrorString(e));
     return SD_OK;
@@ -548,6 +549,8 @@ int sd_bench_dfma(sd_ctx *c, int32_t iters, double *tflops) {
     *tflops = 2.0 * fmas / (best * 1e-3) / 1e12;
     return SD_OK;
 }
+
+int64_t sd_launch_count(const sd_ctx *c) { return c ? c->launches : 0; }
 
 int sd_timer_start(sd_ctx *c) {
     if (!c) return SD_ERR_ARG;

@@ -38,6 +38,7 @@ struct sd_ctx {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     std::string err;
     int sm_count = 148;
+    int64_t launches = 0;  // kernels launched so far
 
     // atmosphere
     int D = 0;

@@ -54,6 +54,8 @@ class DeviceContext:
     def set_stream(self, stream):
         """stream: raw cudaStream_t (int) or a torch.cuda.Stream; None restores the context's own stream."""
         raw = getattr(stream, "cuda_stream", stream)
+        if stream is not None and not raw:
+            raw = 1  # torch's default stream has handle 0 == cudaStreamLegacy; NULL would select the context's own stream
         self._ck(self.lib.sd_set_stream(self.h, raw))
 
     def synchronize(self):
@@ -267,6 +269,9 @@ class DeviceContext:
         t = C.c_double()
         self._ck(self.lib.sd_bench_dfma(self.h, int(iters), C.byref(t)))
         return t.value
+
+    def launch_count(self):
+        return int(self.lib.sd_launch_count(self.h))
 
     def timer_start(self):
         self._ck(self.lib.sd_timer_start(self.h))

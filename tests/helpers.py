@@ -9,34 +9,9 @@ GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 def write_table_files(dirpath):
     """Write the three cross-section tables in the text formats the reference ships (stardis/data/*.dat)."""
-    t = np.load(os.path.join(GOLDEN, "tables.npz"))
-    paths = {}
-    p = os.path.join(dirpath, "h_minus_bf.dat")
-    with open(p, "w") as fh:
-        fh.write("# wavelength [A], cross-section [cm^2]\n")
-        for x, v in zip(t["Hminus_bf_x"], t["Hminus_bf_values"]):
-            fh.write(f"{float(x)!r},{float(v)!r}\n")
-    paths["Hminus_bf"] = p
-    p = os.path.join(dirpath, "h_minus_ff.dat")
-    with open(p, "w") as fh:
-        fh.write("#comment line\n")
-        fh.write(", " + ",  ".join(repr(float(y)) for y in t["Hminus_ff_y"]) + "\n")
-        for x, row in zip(t["Hminus_ff_x"], t["Hminus_ff_values"]):
-            fh.write(f"{int(x)} " + " ".join(repr(float(v)) for v in row) + "\n")
-    paths["Hminus_ff"] = p
-    p = os.path.join(dirpath, "h2_plus_bf.dat")
-    with open(p, "w") as fh:
-        fh.write("#comment line\n")
-        fh.write("(nxn)\t" + "\t".join(str(int(y)) for y in t["H2plus_bf_y"]) + "\t\n")
-        for x, row in zip(t["H2plus_bf_x"], t["H2plus_bf_values"]):
-            fh.write(f"{int(x)}\t" + "\t".join(_stancil(v) for v in row) + "\t\n")
-    paths["H2plus_bf"] = p
-    return paths
+    from stardis_b200.data import write_cross_section_files
 
-
-def _stancil(v):
-    """Exact decimal representation (the product's reader accepts both plain floats and Stancil's '7.34-5' form)."""
-    return repr(float(v))
+    return write_cross_section_files(dirpath)
 
 
 def write_marcs_mod(path, name="sun"):

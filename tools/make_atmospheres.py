@@ -26,3 +26,19 @@ for name, rel in SRC.items():
 dst = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "stardis_b200", "data", "atmospheres.npz")
 np.savez_compressed(dst, **out)
 print(dst, os.path.getsize(dst))
+
+# ---- numeric content of the three cross-section tables the reference ships in stardis/data/ (Wishart 1979 H- bf,
+# Bell & Berrington 1987 H- ff, Stancil 1994 H2+ bf) -> stardis_b200/data/cross_sections.npz
+from stardis_b200.radiation_field.opacities.opacities_solvers.util import read_table  # noqa: E402
+
+TABLES = {"Hminus_bf": "h_minus_bf_W1979.dat", "Hminus_ff": "h_minus_ff_B1987.dat", "H2plus_bf": "h2_plus_bf_S1994.dat"}
+cs = {}
+for src, fn in TABLES.items():
+    t = read_table(os.path.join(REF, "stardis", "data", fn), src)
+    cs[f"{src}_x"] = t["x"] / (10.0 if src == "H2plus_bf" else 1.0)  # keep the file's own wavelength unit (nm for H2+)
+    cs[f"{src}_values"] = t["values"]
+    if t["y"] is not None:
+        cs[f"{src}_y"] = t["y"]
+dst = os.path.join(os.path.dirname(dst), "cross_sections.npz")
+np.savez_compressed(dst, **cs)
+print(dst, os.path.getsize(dst))
