@@ -201,6 +201,9 @@ int sd_ew_calc_weights(sd_ctx *ctx, int64_t n, const double *tau, double *w0, do
 int sd_bench_dfma(sd_ctx *ctx, int32_t iters, double *tflops);
 /* time of the device work enqueued between the two calls, in ms, measured with CUDA events on the
  * context's stream (sd_timer_stop synchronises). */
+/* accuracy probe of the reciprocal used in the far-wing loop: MUFU.RCP64H seed, seed + one Newton step, seed + one
+ * cubic step (tests only) */
+int sd_debug_rcp(sd_ctx *ctx, int64_t n, const double *x, double *seed, double *quad, double *cubic);
 /* number of kernels this context has launched so far (bench.py's gpu_launches claim) */
 int64_t sd_launch_count(const sd_ctx *ctx);
 int sd_timer_start(sd_ctx *ctx);

@@ -524,7 +524,27 @@ __global__ void __launch_bounds__(256) k_dfma(int iters, double seed, double *si
     double s = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
     if (s == 123.456) sink[0] = s;
 }
+
+__global__ void k_debug_rcp(int64_t n, const double *x, double *seed, double *quad, double *cubic) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x[i]));
+    seed[i] = r;
+    quad[i] = sdm::rcp_fast2(x[i]);
+    cubic[i] = sdm::rcp_fast(x[i]);
+}
 }  // namespace
+
+extern "C" int sd_debug_rcp(sd_ctx *c, int64_t n, const double *x, double *seed, double *quad, double *cubic) {
+#define EW_INS x
+#define EW_OUTS seed, quad, cubic
+    EW_BEGIN(1, 3)
+    k_debug_rcp<<<nblk(n), 256, 0, c->stream>>>(n, I(0), O(0), O(1), O(2));
+    EW_END(3, "k_debug_rcp")
+#undef EW_INS
+#undef EW_OUTS
+}
 
 extern "C" {
 

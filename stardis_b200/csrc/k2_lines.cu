@@ -14,12 +14,15 @@
 //     entries (per-(line,depth) constants hoisted once per CTA, incl. per-warp "fully inside the window and
 //     entirely in Humlicek region I" flags) and then consumed by all 8 warps with broadcast LDS;
 //   * the hot loop is the far-wing (region I) form  Kf (q + c1) / (q (q + b) + c),  q = x^2:
-//     10 FP64 instructions + 1 MUFU.RCP64H per evaluation, no branches, no divisions;
+//     8 FP64 instructions + 1 MUFU.RCP64H per evaluation (x, q, 2 for the denominator, numerator, 2 for the Newton
+//     step on the reciprocal seed, accumulate), no branches, no divisions;
 //   * pixels that are not certainly in region I take the exact path: x = dnu / dw (IEEE division) and the
 //     reference's own region tests, so the Humlicek classification is identical to the reference's.
 //
 // Roofline: FP64 FMA pipe (no dense contraction -> no tensor cores).  Memory traffic is negligible:
 // 64 B per candidate record per tile, 8 B per output cell.
+#include <stdlib.h>
+
 #include "sd_internal.h"
 #include "sd_math.cuh"
 
@@ -37,7 +40,7 @@ struct __align__(16) SEntry {
     double thr;     // q > thr  =>  region I for certain
     double b;       // 2 y^2 - 1
     double c;       // (y^2 + 1/2)^2
-    double c1;      // y^2 + 1/2
+    double Kc;      // Kf (y^2 + 1/2)
     double Kf;      // alpha y / (pi dw)
     int lo, hi;     // window
     // exact path (32 B)
@@ -73,7 +76,7 @@ __device__ __noinline__ double exact_contribution(double nu_i, double nu_l, doub
     return sdm::humlicek_re(x, y) * K;
 }
 
-template <int P, bool STATS>
+template <int P, bool STATS, int RCP>
 __global__ void __launch_bounds__(THREADS) k_lines(int64_t L, int D, int64_t N, int64_t p0, int64_t p1,
                                                    const double *__restrict__ nus, const int *__restrict__ line_idx,
                                                    const LineRec *__restrict__ rec, const int *__restrict__ win_lo,
@@ -178,10 +181,11 @@ __global__ void __launch_bounds__(THREADS) k_lines(int64_t L, int D, int64_t N, 
                 e.xl = r.nu * r.inv_dw;
                 e.inv_dw = r.inv_dw;
                 e.thr = r.thr;
-                e.c1 = yy + 0.5;
+                const double c1 = yy + 0.5;
                 e.b = 2.0 * yy - 1.0;
-                e.c = e.c1 * e.c1;
+                e.c = c1 * c1;
                 e.Kf = r.K * r.y * sdm::INV_SQRT_PI;
+                e.Kc = e.Kf * c1;
                 e.lo = lo;
                 e.hi = hi;
                 e.nu = r.nu;
@@ -213,15 +217,15 @@ __global__ void __launch_bounds__(THREADS) k_lines(int64_t L, int D, int64_t N, 
                 const SEntry &e = s_ent[k];
                 const unsigned mo = e.m_overlap, mf = e.m_fullfar;
                 if (!((mo >> warp) & 1u)) continue;
-                const double xl = e.xl, inv_dw = e.inv_dw, eb = e.b, ec = e.c, ec1 = e.c1, Kf = e.Kf;
+                const double xl = e.xl, inv_dw = e.inv_dw, eb = e.b, ec = e.c, Kc = e.Kc, Kf = e.Kf;
                 if ((mf >> warp) & 1u) {
 #pragma unroll
                     for (int p = 0; p < P; p++) {
                         double x = fma(nu_i[p], inv_dw, -xl);
                         double q = x * x;
                         double den = fma(q, q + eb, ec);
-                        double num = Kf * (q + ec1);
-                        acc[p] = fma(num, sdm::rcp_fast(den), acc[p]);
+                        double num = fma(Kf, q, Kc);
+                        acc[p] = fma(num, RCP == 2 ? sdm::rcp_fast2(den) : sdm::rcp_fast(den), acc[p]);
                     }
                     if (STATS) h0 += nvalid;
                 } else {
@@ -236,8 +240,8 @@ __global__ void __launch_bounds__(THREADS) k_lines(int64_t L, int D, int64_t N, 
                         double q = x * x;
                         bool fast = inwin && (q > thr);
                         double den = fma(q, q + eb, ec);
-                        double num = Kf * (q + ec1);
-                        double v = num * sdm::rcp_fast(den);
+                        double num = fma(Kf, q, Kc);
+                        double v = num * (RCP == 2 ? sdm::rcp_fast2(den) : sdm::rcp_fast(den));
                         if (fast) acc[p] += v;
                         if (inwin && !fast) acc[p] += exact_contribution(nu_i[p], e.nu, e.dw, e.y, e.K);
                         if (STATS && inwin) {
@@ -273,7 +277,7 @@ __global__ void __launch_bounds__(THREADS) k_lines(int64_t L, int D, int64_t N, 
 }
 
 template <int P>
-int launch(sd_ctx *c, int slot, bool stats) {
+int launch(sd_ctx *c, int slot, bool stats, int rcp) {
     int64_t W = c->W();
     dim3 grid((unsigned)((W + THREADS * P - 1) / (THREADS * P)), (unsigned)c->D);
     auto args = [&](auto kern) {
@@ -282,8 +286,16 @@ int launch(sd_ctx *c, int slot, bool stats) {
                                               c->win_cls.as<uint8_t>(), c->cls_list.as<int>(), c->cls_off.as<int>(),
                                               c->alpha_line[slot].as<double>(), c->stats.as<unsigned long long>());
     };
-    if (stats) args(k_lines<P, true>); else args(k_lines<P, false>);
+    // the counting instantiation uses the production arithmetic (Newton reciprocal) so that both are bitwise equal
+    if (stats) args(k_lines<P, true, 2>);
+    else if (rcp == 3) args(k_lines<P, false, 3>);
+    else args(k_lines<P, false, 2>);
     return sd_launch_check(c, "k_lines");
+}
+
+int env_int(const char *name, int dflt) {
+    const char *v = getenv(name);
+    return v ? atoi(v) : dflt;
 }
 
 }  // namespace
@@ -297,10 +309,18 @@ int sd_k2_lines(sd_ctx *c, int slot) {
     }
     if (c->line_stats) SD_CUDA(c, cudaMemsetAsync(c->stats.p, 0, 4 * sizeof(unsigned long long), c->stream));
     // pixels per thread: enough CTAs to fill the chip several times over, otherwise as much register reuse
-    // of the staged entries as possible
-    int64_t ctas4 = ((W + 1023) / 1024) * c->D;
-    if (ctas4 >= 4LL * c->sm_count) return launch<4>(c, slot, c->line_stats);
-    int64_t ctas2 = ((W + 511) / 512) * c->D;
-    if (ctas2 >= 4LL * c->sm_count) return launch<2>(c, slot, c->line_stats);
-    return launch<1>(c, slot, c->line_stats);
+    // of the staged entries as possible.  SD_K2_P / SD_K2_RCP override the choice (tuning experiments).
+    static const int force_p = env_int("SD_K2_P", 0);
+    static const int rcp = env_int("SD_K2_RCP", 2);
+    int P = 1;
+    if (((W + 2047) / 2048) * c->D >= 8LL * c->sm_count) P = 8;
+    else if (((W + 1023) / 1024) * c->D >= 4LL * c->sm_count) P = 4;
+    else if (((W + 511) / 512) * c->D >= 4LL * c->sm_count) P = 2;
+    if (force_p) P = force_p;
+    switch (P) {
+        case 8: return launch<8>(c, slot, c->line_stats, rcp);
+        case 4: return launch<4>(c, slot, c->line_stats, rcp);
+        case 2: return launch<2>(c, slot, c->line_stats, rcp);
+        default: return launch<1>(c, slot, c->line_stats, rcp);
+    }
 }

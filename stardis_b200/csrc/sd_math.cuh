@@ -48,6 +48,20 @@ SD_HD double rcp_fast(double d) {
 #endif
 }
 
+// Same seed with ONE Newton step r(1 + e): relative error = e^2 <= 1e-12 (seed error measured on B200: 9.9e-7).
+// Default in the far-wing loop: every term is positive, so alpha_line inherits at most this relative error, four
+// orders of magnitude inside the 1e-8 parity tolerance.
+SD_HD double rcp_fast2(double d) {
+#if defined(__CUDA_ARCH__)
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(d));
+    double e = fma(-d, r, 1.0);
+    return fma(r, e, r);
+#else
+    return 1.0 / d;
+#endif
+}
+
 // ---------------------------------------------------------------------------- Humlicek W4, Re(w)
 // Region I (s > 15): w = (i/sqrt(pi)) z / (z^2 - 1/2).  With q = x^2:
 //   Re w = y (q + y^2 + 1/2) / (sqrt(pi) ((q - y^2 - 1/2)^2 + 4 q y^2))

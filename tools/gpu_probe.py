@@ -13,6 +13,13 @@ from stardis_b200.synthetic import make_workload  # noqa: E402
 n_lines = int(sys.argv[1]) if len(sys.argv) > 1 else 20000
 ctx = DeviceContext(0)
 print("dfma TFLOP/s", ctx.bench_dfma(4096), ctx.bench_dfma(8192))
+import ctypes as C
+x = 10.0 ** np.random.default_rng(0).uniform(0, 30, 1 << 20)
+outs = [np.empty_like(x) for _ in range(3)]
+ctx._ck(ctx.lib.sd_debug_rcp(ctx.h, x.size, L.ptr(x), *[L.ptr(o) for o in outs]))
+ctx.synchronize()
+for name, o in zip(("seed", "seed+newton", "seed+cubic"), outs):
+    print("rcp", name, "max rel err", np.max(np.abs(o * x - 1.0)))
 w = make_workload("solar_full", n_lines=n_lines)
 p, m = w["plasma"], w["model"]
 lt = p.line_table.with_masses(m.composition.nuclide_masses)
