@@ -293,7 +293,7 @@ def _read_table_2d(fpath, source):
 
 def _stancil(tok):
     """'7.34-5' -> 7.34e-5 (util.py:41 replaces '-' by 'e-')."""
-    return tok.replace("-", "e-") if "-" in tok[1:] else tok
+    return tok.replace("-", "e-") if "-" in tok[1:] and "e" not in tok.lower() else tok
 
 
 def sigma_file(tracing_lambdas, temperatures, fpath, opacity_source=None):

@@ -44,7 +44,7 @@ def allgather_spectrum(local, shard, n_total, device=None):
     bounds = all_shards(n_total, world)
     if tuple(bounds[rank]) != tuple(int(x) for x in shard):
         raise ValueError(f"rank {rank}: shard {shard} does not match the balanced partition {bounds[rank]}")
-    is_tensor = hasattr(local, "device")
+    is_tensor = isinstance(local, torch.Tensor)
     t = local if is_tensor else torch.from_numpy(np.ascontiguousarray(local, dtype=np.float64))
     if device is not None:
         t = t.to(device)
@@ -66,7 +66,7 @@ def allgather_columns(local, shard, n_total):
     dist, rank, world = dist_info()
     if dist is None or world == 1:
         return local
-    is_tensor = hasattr(local, "device")
+    is_tensor = isinstance(local, torch.Tensor)
     t = local if is_tensor else torch.from_numpy(np.ascontiguousarray(local, dtype=np.float64))
     D = t.shape[0]
     bounds = all_shards(n_total, world)
