@@ -201,6 +201,12 @@ int sd_ew_calc_weights(sd_ctx *ctx, int64_t n, const double *tau, double *w0, do
 int sd_bench_dfma(sd_ctx *ctx, int32_t iters, double *tflops);
 /* time of the device work enqueued between the two calls, in ms, measured with CUDA events on the
  * context's stream (sd_timer_stop synchronises). */
+/* FP64 issue-rate probes (DFMA TFLOP/s): mode 0 = constant second/third operands (same as sd_bench_dfma),
+ * 1 = three distinct register operands per DFMA, 2 = two distinct, 3 = mode 0 + one MUFU.RCP64H per 8 DFMA */
+int sd_bench_fp64(sd_ctx *ctx, int32_t mode, int32_t iters, double *tflops);
+/* the far-wing evaluation of k_lines in isolation (registers only): Gevals/s.  variant 0 = full body, 1 = no
+ * reciprocal, 2 = MUFU seed without the Newton step */
+int sd_bench_fareval(sd_ctx *ctx, int32_t variant, int32_t iters, double *gevals);
 /* accuracy probe of the reciprocal used in the far-wing loop: MUFU.RCP64H seed, seed + one Newton step, seed + one
  * cubic step (tests only) */
 int sd_debug_rcp(sd_ctx *ctx, int64_t n, const double *x, double *seed, double *quad, double *cubic);

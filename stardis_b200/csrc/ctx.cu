@@ -525,6 +525,75 @@ __global__ void __launch_bounds__(256) k_dfma(int iters, double seed, double *si
     if (s == 123.456) sink[0] = s;
 }
 
+// FP64 issue-rate probes.  mode 1: every DFMA reads three DISTINCT register pairs (no operand reuse);
+// mode 2: two distinct pairs + one reused; mode 3: mode 0 plus one MUFU.RCP64H per 8 DFMA.
+template <int MODE>
+__global__ void __launch_bounds__(256) k_fp64_probe(int iters, double seed, double *sink) {
+    double a[8], b[8], c[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        a[i] = seed + threadIdx.x + i;
+        b[i] = 0.999999 + 1e-9 * i + 1e-12 * threadIdx.x;
+        c[i] = 1e-7 * (i + 1);
+    }
+    const double m = 0.999999, k = 1e-7;
+#pragma unroll 1
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+                if (MODE == 1) a[i] = fma(b[i], c[i], a[i]);
+                else if (MODE == 2) a[i] = fma(a[i], b[i], k);
+                else a[i] = fma(a[i], m, k);
+            }
+            if (MODE == 3) {
+                double r;
+                asm volatile("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(a[u]));
+                c[u] = r;
+            }
+        }
+    }
+    double s = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) s += a[i] + c[i];
+    if (s == 123.456) sink[0] = s;
+}
+
+// The far-wing evaluation of k_lines in isolation: 8 pixels per thread, entry constants in registers (perturbed per
+// iteration so nothing is hoisted), no shared memory, no window logic.  VARIANT 0: full body; 1: without the
+// reciprocal (den used directly: no MUFU, no Newton); 2: MUFU seed only (no Newton).
+template <int VARIANT>
+__global__ void __launch_bounds__(256, 2) k_fareval_probe(int iters, double seed, double *sink) {
+    double nu[8], acc[8];
+#pragma unroll
+    for (int p = 0; p < 8; p++) {
+        nu[p] = 5.0e14 + 1.0e9 * (threadIdx.x + 256 * p);
+        acc[p] = 0.0;
+    }
+    double inv_dw = 4.0e-10 * seed, xl = 1.9e5, eb = -0.98, ec = 0.26, Kc = 1e-3, Kf = 2e-3;
+#pragma unroll 1
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+        for (int p = 0; p < 8; p++) {
+            double x = fma(nu[p], inv_dw, -xl);
+            double q = x * x;
+            double den = fma(q, q + eb, ec);
+            double num = fma(Kf, q, Kc);
+            double r;
+            if (VARIANT == 1) r = den;
+            else if (VARIANT == 2) { asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(den)); }
+            else r = sdm::rcp_fast2(den);
+            acc[p] = fma(num, r, acc[p]);
+        }
+        xl += 1.0; eb += 1e-9; Kf += 1e-12;  // 3 extra FP64 per 8 evaluations (accounted for below)
+    }
+    double s = 0;
+#pragma unroll
+    for (int p = 0; p < 8; p++) s += acc[p];
+    if (s == 123.456) sink[0] = s;
+}
+
 __global__ void k_debug_rcp(int64_t n, const double *x, double *seed, double *quad, double *cubic) {
     int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -567,6 +636,55 @@ int sd_bench_dfma(sd_ctx *c, int32_t iters, double *tflops) {
     SD_TRY(sd_launch_check(c, "k_dfma"));
     double fmas = (double)blocks * 256.0 * (double)iters * 64.0;
     *tflops = 2.0 * fmas / (best * 1e-3) / 1e12;
+    return SD_OK;
+}
+
+int sd_bench_fp64(sd_ctx *c, int32_t mode, int32_t iters, double *tflops) {
+    if (!c || !tflops || iters <= 0 || mode < 0 || mode > 3) return SD_ERR_ARG;
+    SD_CUDA(c, cudaSetDevice(c->device));
+    SD_TRY(sd_ensure(c, c->stats, 64));
+    int blocks = c->sm_count * 8;
+    double *sink = c->stats.as<double>() + 7;
+    float best = 1e30f;
+    for (int rep = 0; rep < 4; rep++) {
+        SD_CUDA(c, cudaEventRecord(c->ev0, c->stream));
+        switch (mode) {
+            case 0: k_fp64_probe<0><<<blocks, 256, 0, c->stream>>>(iters, 1.0, sink); break;
+            case 1: k_fp64_probe<1><<<blocks, 256, 0, c->stream>>>(iters, 1.0, sink); break;
+            case 2: k_fp64_probe<2><<<blocks, 256, 0, c->stream>>>(iters, 1.0, sink); break;
+            default: k_fp64_probe<3><<<blocks, 256, 0, c->stream>>>(iters, 1.0, sink); break;
+        }
+        SD_CUDA(c, cudaEventRecord(c->ev1, c->stream));
+        SD_CUDA(c, cudaEventSynchronize(c->ev1));
+        float ms = 0;
+        SD_CUDA(c, cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+        if (rep > 0 && ms < best) best = ms;
+    }
+    SD_TRY(sd_launch_check(c, "k_fp64_probe"));
+    *tflops = 2.0 * (double)blocks * 256.0 * (double)iters * 64.0 / (best * 1e-3) / 1e12;
+    return SD_OK;
+}
+
+int sd_bench_fareval(sd_ctx *c, int32_t variant, int32_t iters, double *gevals) {
+    if (!c || !gevals || iters <= 0) return SD_ERR_ARG;
+    SD_CUDA(c, cudaSetDevice(c->device));
+    SD_TRY(sd_ensure(c, c->stats, 64));
+    int blocks = c->sm_count * 2;
+    double *sink = c->stats.as<double>() + 7;
+    float best = 1e30f;
+    for (int rep = 0; rep < 4; rep++) {
+        SD_CUDA(c, cudaEventRecord(c->ev0, c->stream));
+        if (variant == 1) k_fareval_probe<1><<<blocks, 256, 0, c->stream>>>(iters, 1.0, sink);
+        else if (variant == 2) k_fareval_probe<2><<<blocks, 256, 0, c->stream>>>(iters, 1.0, sink);
+        else k_fareval_probe<0><<<blocks, 256, 0, c->stream>>>(iters, 1.0, sink);
+        SD_CUDA(c, cudaEventRecord(c->ev1, c->stream));
+        SD_CUDA(c, cudaEventSynchronize(c->ev1));
+        float ms = 0;
+        SD_CUDA(c, cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+        if (rep > 0 && ms < best) best = ms;
+    }
+    SD_TRY(sd_launch_check(c, "k_fareval_probe"));
+    *gevals = (double)blocks * 256.0 * (double)iters * 8.0 / (best * 1e-3) / 1e9;
     return SD_OK;
 }
 

@@ -10,9 +10,11 @@
 //   * the (line, depth) pairs that can touch the tile are found per half-width class (class 0: contiguous
 //     range of the nu-sorted line list; class k >= 1: contiguous range of the per-depth class list built by
 //     k1_broadening.cu; 32-ary warp binary searches on the monotone window centres);
-//   * candidates are tested against the tile, compacted in line order, expanded into 112-byte shared-memory
-//     entries (per-(line,depth) constants hoisted once per CTA, incl. per-warp "fully inside the window and
-//     entirely in Humlicek region I" flags) and then consumed by all 8 warps with broadcast LDS;
+//   * every WARP streams the candidates in batches of 32 on its own (no CTA barrier in the main loop): test against
+//     the warp's 32*P-pixel span, expand the passing (line, depth) records into 96-byte shared-memory entries
+//     (constants hoisted once per warp), entries whose window covers the span and whose span lies entirely in
+//     Humlicek region I packed first ("far" list), the others from the back ("mixed" list), then consume them with
+//     broadcast LDS; summation order per pixel is fixed (class, batch, far entries in line order, mixed reversed);
 //   * the hot loop is the far-wing (region I) form  Kf (q + c1) / (q (q + b) + c),  q = x^2:
 //     8 FP64 instructions + 1 MUFU.RCP64H per evaluation (x, q, 2 for the denominator, numerator, 2 for the Newton
 //     step on the reciprocal seed, accumulate), no branches, no divisions;
@@ -30,26 +32,23 @@ namespace {
 
 constexpr int THREADS = 256;
 constexpr int WARPS = THREADS / 32;
-constexpr int STAGE = 256;  // entries staged per round (one candidate per thread)
 static_assert(WARPS == SD_NCLS, "one warp per half-width class in the range search");
 
-struct __align__(16) SEntry {
-    // fast path (64 B)
+struct __align__(16) WEntry {
+    // far-wing path (48 B)
     double xl;      // nu_l / dw
     double inv_dw;  // 1 / dw
-    double thr;     // q > thr  =>  region I for certain
     double b;       // 2 y^2 - 1
     double c;       // (y^2 + 1/2)^2
     double Kc;      // Kf (y^2 + 1/2)
     double Kf;      // alpha y / (pi dw)
-    int lo, hi;     // window
+    // window + region-I threshold (16 B)
+    double thr;     // q > thr  =>  region I for certain
+    int lo, hi;
     // exact path (32 B)
     double nu, dw, y, K;
-    // per-warp flags: bit w = warp w's span overlaps the window / lies fully inside it and fully in region I
-    unsigned m_overlap, m_fullfar;
-    unsigned pad0, pad1;
 };
-static_assert(sizeof(SEntry) == 112, "SEntry layout");
+static_assert(sizeof(WEntry) == 96, "WEntry layout");
 
 // smallest j in [a, b] with (j == b or key(j) < X); key non-increasing in j.  Warp-cooperative 32-ary search.
 template <class KeyFn>
@@ -76,8 +75,8 @@ __device__ __noinline__ double exact_contribution(double nu_i, double nu_l, doub
     return sdm::humlicek_re(x, y) * K;
 }
 
-template <int P, bool STATS, int RCP>
-__global__ void __launch_bounds__(THREADS) k_lines(int64_t L, int D, int64_t N, int64_t p0, int64_t p1,
+template <int P, bool STATS, int RCP, bool U2, int MINB>
+__global__ void __launch_bounds__(THREADS, MINB) k_lines(int64_t L, int D, int64_t N, int64_t p0, int64_t p1,
                                                    const double *__restrict__ nus, const int *__restrict__ line_idx,
                                                    const LineRec *__restrict__ rec, const int *__restrict__ win_lo,
                                                    const int *__restrict__ win_hi, const uint8_t *__restrict__ win_cls,
@@ -85,12 +84,11 @@ __global__ void __launch_bounds__(THREADS) k_lines(int64_t L, int D, int64_t N, 
                                                    double *__restrict__ out, unsigned long long *__restrict__ stats) {
     constexpr int TILE = THREADS * P;
     constexpr int SPAN = 32 * P;
-    __shared__ SEntry s_ent[STAGE];
-    __shared__ double s_edge[WARPS][2];
+    __shared__ WEntry s_ent[WARPS][32];  // every warp streams its own batches: no CTA barrier in the main loop
     __shared__ int s_ja[SD_NCLS], s_jb[SD_NCLS];
-    __shared__ int s_wcnt[WARPS];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const unsigned lt_mask = (1u << lane) - 1u;
     const int d = blockIdx.y;
     const int64_t t0 = p0 + (int64_t)blockIdx.x * TILE;
     const int64_t t1 = (t0 + TILE < p1) ? t0 + TILE : p1;
@@ -107,11 +105,9 @@ __global__ void __launch_bounds__(THREADS) k_lines(int64_t L, int D, int64_t N, 
         nu_i[p] = nus[pix < N ? pix : N - 1];
         acc[p] = 0.0;
     }
-    if (lane == 0) {
-        int64_t a = ws < N ? ws : N - 1, b = (we - 1 >= ws) ? we - 1 : a;
-        s_edge[warp][0] = nus[a];
-        s_edge[warp][1] = nus[b < N ? b : N - 1];
-    }
+    // frequencies at the two ends of this warp's span (x is monotone in the pixel index)
+    const double nu_first = nus[ws < N ? ws : N - 1];
+    const double nu_last = nus[(we - 1 >= ws && we - 1 < N) ? we - 1 : (ws < N ? ws : N - 1)];
 
     // candidate ranges of all classes, one warp per class
     {
@@ -147,11 +143,27 @@ __global__ void __launch_bounds__(THREADS) k_lines(int64_t L, int D, int64_t N, 
 #pragma unroll
     for (int p = 0; p < P; p++) nvalid += (ws + p * 32 + lane) < t1;
 
-    for (int cls = 0; cls < SD_NCLS; cls++) {
+    WEntry *const my = s_ent[warp];
+    const bool warp_has_pixels = ws < t1;
+
+    // far-wing (region I) evaluation of one staged entry for the P pixels of this lane
+    auto far_eval = [&](const double xl, const double inv_dw, const double eb, const double ec, const double Kc,
+                        const double Kf) {
+#pragma unroll
+        for (int p = 0; p < P; p++) {
+            double x = fma(nu_i[p], inv_dw, -xl);
+            double q = x * x;
+            double den = fma(q, q + eb, ec);
+            double num = fma(Kf, q, Kc);
+            acc[p] = fma(num, RCP == 2 ? sdm::rcp_fast2(den) : sdm::rcp_fast(den), acc[p]);
+        }
+    };
+
+    for (int cls = 0; cls < SD_NCLS && warp_has_pixels; cls++) {
         const int ja = s_ja[cls], jb = s_jb[cls];
-        for (int base = ja; base < jb; base += STAGE) {
-            // ---- test + ordered compaction ---------------------------------------------------------
-            int j = base + tid;
+        for (int base = ja; base < jb; base += 32) {
+            // ---- test the 32 candidates of this batch against THIS WARP's span ------------------------
+            const int j = base + lane;
             bool pass = false;
             size_t o = 0;
             int lo = 0, hi = 0;
@@ -160,98 +172,79 @@ __global__ void __launch_bounds__(THREADS) k_lines(int64_t L, int D, int64_t N, 
                 o = drow + l;
                 lo = win_lo[o];
                 hi = win_hi[o];
-                pass = (lo < t1) && (hi > t0) && (hi > lo) && (cls != 0 || win_cls[o] == 0);
+                pass = (lo < we) && (hi > ws) && (hi > lo) && (cls != 0 || win_cls[o] == 0);
             }
-            unsigned bal = __ballot_sync(0xffffffffu, pass);
-            if (lane == 0) s_wcnt[warp] = __popc(bal);
-            __syncthreads();
-            int pos = __popc(bal & ((1u << lane) - 1u));
-            int total = 0;
-#pragma unroll
-            for (int w = 0; w < WARPS; w++) {
-                int cw = s_wcnt[w];
-                if (w < warp) pos += cw;
-                total += cw;
-            }
-            // ---- stage: hoist the per-(line, depth) constants once per CTA ------------------------
+            if (!__any_sync(0xffffffffu, pass)) continue;
+            // ---- stage: hoist the per-(line, depth) constants; far entries first, mixed ones from the back -----
+            WEntry e;
+            bool ff = false;
             if (pass) {
                 const LineRec r = rec[o];
-                SEntry e;
-                double yy = r.y * r.y;
+                const double yy = r.y * r.y;
+                const double c1 = yy + 0.5;
                 e.xl = r.nu * r.inv_dw;
                 e.inv_dw = r.inv_dw;
-                e.thr = r.thr;
-                const double c1 = yy + 0.5;
                 e.b = 2.0 * yy - 1.0;
                 e.c = c1 * c1;
                 e.Kf = r.K * r.y * sdm::INV_SQRT_PI;
                 e.Kc = e.Kf * c1;
+                e.thr = r.thr;
                 e.lo = lo;
                 e.hi = hi;
                 e.nu = r.nu;
                 e.dw = r.dw;
                 e.y = r.y;
                 e.K = r.K;
-                unsigned mo = 0, mf = 0;
-#pragma unroll
-                for (int w = 0; w < WARPS; w++) {
-                    int64_t a = t0 + (int64_t)w * SPAN;
-                    int64_t b = (a + SPAN < t1) ? a + SPAN : t1;
-                    if (a < b && lo < b && hi > a) {
-                        mo |= 1u << w;
-                        if (lo <= a && hi >= b) {
-                            double xa = fma(s_edge[w][0], e.inv_dw, -e.xl);
-                            double xb = fma(s_edge[w][1], e.inv_dw, -e.xl);
-                            if (xa * xb > 0.0 && fmin(xa * xa, xb * xb) > e.thr) mf |= 1u << w;
-                        }
-                    }
+                if (lo <= ws && hi >= we) {  // window covers the whole span: is the span entirely in region I?
+                    double xa = fma(nu_first, e.inv_dw, -e.xl);
+                    double xb = fma(nu_last, e.inv_dw, -e.xl);
+                    ff = (xa * xb > 0.0) && (fmin(xa * xa, xb * xb) > e.thr);
                 }
-                e.m_overlap = mo;
-                e.m_fullfar = mf;
-                e.pad0 = e.pad1 = 0;
-                s_ent[pos] = e;
             }
-            __syncthreads();
-            // ---- consume: every warp walks the staged entries for its own pixel span ---------------
-            for (int k = 0; k < total; k++) {
-                const SEntry &e = s_ent[k];
-                const unsigned mo = e.m_overlap, mf = e.m_fullfar;
-                if (!((mo >> warp) & 1u)) continue;
-                const double xl = e.xl, inv_dw = e.inv_dw, eb = e.b, ec = e.c, Kc = e.Kc, Kf = e.Kf;
-                if ((mf >> warp) & 1u) {
+            const unsigned m_far = __ballot_sync(0xffffffffu, pass && ff);
+            const unsigned m_mix = __ballot_sync(0xffffffffu, pass && !ff);
+            const int n_far = __popc(m_far), n_mix = __popc(m_mix);
+            if (pass) my[ff ? __popc(m_far & lt_mask) : 31 - __popc(m_mix & lt_mask)] = e;
+            __syncwarp();
+            // ---- consume: far-wing entries, two per iteration (independent chains, loads hoisted) ----------
+            int k = 0;
+            for (; U2 && k + 1 < n_far; k += 2) {
+                const WEntry &a = my[k], &b = my[k + 1];
+                const double a0 = a.xl, a1 = a.inv_dw, a2 = a.b, a3 = a.c, a4 = a.Kc, a5 = a.Kf;
+                const double b0 = b.xl, b1 = b.inv_dw, b2 = b.b, b3 = b.c, b4 = b.Kc, b5 = b.Kf;
+                far_eval(a0, a1, a2, a3, a4, a5);
+                far_eval(b0, b1, b2, b3, b4, b5);
+            }
+            for (; k < n_far; k++) {
+                const WEntry &a = my[k];
+                far_eval(a.xl, a.inv_dw, a.b, a.c, a.Kc, a.Kf);
+            }
+            if (STATS) h0 += (unsigned long long)n_far * nvalid;
+            // ---- mixed entries: window edge inside the span and/or pixels near the line core --------------
+            for (int m = 0; m < n_mix; m++) {
+                const WEntry &e2 = my[31 - m];
+                const int lo2 = e2.lo, hi2 = e2.hi;
+                const double thr = e2.thr, xl = e2.xl, inv_dw = e2.inv_dw, eb = e2.b, ec = e2.c, Kc = e2.Kc, Kf = e2.Kf;
 #pragma unroll
-                    for (int p = 0; p < P; p++) {
-                        double x = fma(nu_i[p], inv_dw, -xl);
-                        double q = x * x;
-                        double den = fma(q, q + eb, ec);
-                        double num = fma(Kf, q, Kc);
-                        acc[p] = fma(num, RCP == 2 ? sdm::rcp_fast2(den) : sdm::rcp_fast(den), acc[p]);
-                    }
-                    if (STATS) h0 += nvalid;
-                } else {
-                    const int lo2 = e.lo, hi2 = e.hi;
-                    const double thr = e.thr;
-#pragma unroll
-                    for (int p = 0; p < P; p++) {
-                        int64_t pix = ws + p * 32 + lane;
-                        bool inwin = (pix >= lo2) && (pix < hi2) && (pix < t1);
-                        if (!__any_sync(0xffffffffu, inwin)) continue;
-                        double x = fma(nu_i[p], inv_dw, -xl);
-                        double q = x * x;
-                        bool fast = inwin && (q > thr);
-                        double den = fma(q, q + eb, ec);
-                        double num = fma(Kf, q, Kc);
-                        double v = num * (RCP == 2 ? sdm::rcp_fast2(den) : sdm::rcp_fast(den));
-                        if (fast) acc[p] += v;
-                        if (inwin && !fast) acc[p] += exact_contribution(nu_i[p], e.nu, e.dw, e.y, e.K);
-                        if (STATS && inwin) {
-                            int r = sdm::humlicek_region((nu_i[p] - e.nu) / e.dw, e.y);
-                            h0 += (r == 0); h1 += (r == 1); h2 += (r == 2); h3 += (r == 3);
-                        }
+                for (int p = 0; p < P; p++) {
+                    int64_t pix = ws + p * 32 + lane;
+                    bool inwin = (pix >= lo2) && (pix < hi2) && (pix < t1);
+                    if (!__any_sync(0xffffffffu, inwin)) continue;
+                    double x = fma(nu_i[p], inv_dw, -xl);
+                    double q = x * x;
+                    bool fast = inwin && (q > thr);
+                    double den = fma(q, q + eb, ec);
+                    double num = fma(Kf, q, Kc);
+                    double v = num * (RCP == 2 ? sdm::rcp_fast2(den) : sdm::rcp_fast(den));
+                    if (fast) acc[p] += v;
+                    if (inwin && !fast) acc[p] += exact_contribution(nu_i[p], e2.nu, e2.dw, e2.y, e2.K);
+                    if (STATS && inwin) {
+                        int r = sdm::humlicek_region((nu_i[p] - e2.nu) / e2.dw, e2.y);
+                        h0 += (r == 0); h1 += (r == 1); h2 += (r == 2); h3 += (r == 3);
                     }
                 }
             }
-            __syncthreads();
+            __syncwarp();
         }
     }
 
@@ -276,6 +269,11 @@ __global__ void __launch_bounds__(THREADS) k_lines(int64_t L, int D, int64_t N, 
     }
 }
 
+int env_int(const char *name, int dflt) {
+    const char *v = getenv(name);
+    return v ? atoi(v) : dflt;
+}
+
 template <int P>
 int launch(sd_ctx *c, int slot, bool stats, int rcp) {
     int64_t W = c->W();
@@ -287,15 +285,16 @@ int launch(sd_ctx *c, int slot, bool stats, int rcp) {
                                               c->alpha_line[slot].as<double>(), c->stats.as<unsigned long long>());
     };
     // the counting instantiation uses the production arithmetic (Newton reciprocal) so that both are bitwise equal
-    if (stats) args(k_lines<P, true, 2>);
-    else if (rcp == 3) args(k_lines<P, false, 3>);
-    else args(k_lines<P, false, 2>);
+    static const int u2 = env_int("SD_K2_U2", 0);
+    static const int minb = env_int("SD_K2_MINB", 2);
+    if (stats) args(k_lines<P, true, 2, false, 2>);
+    else if (rcp == 3) args(k_lines<P, false, 3, false, 2>);
+    else if (u2) args(k_lines<P, false, 2, true, 2>);
+    else if (minb == 1) args(k_lines<P, false, 2, false, 1>);
+    else if (minb == 3) args(k_lines<P, false, 2, false, 3>);
+    else if (minb == 4) args(k_lines<P, false, 2, false, 4>);
+    else args(k_lines<P, false, 2, false, 2>);
     return sd_launch_check(c, "k_lines");
-}
-
-int env_int(const char *name, int dflt) {
-    const char *v = getenv(name);
-    return v ? atoi(v) : dflt;
 }
 
 }  // namespace

@@ -14,6 +14,10 @@ n_lines = int(sys.argv[1]) if len(sys.argv) > 1 else 20000
 ctx = DeviceContext(0)
 print("dfma TFLOP/s", ctx.bench_dfma(4096), ctx.bench_dfma(8192))
 import ctypes as C
+for v in range(3):
+    t = C.c_double(); ctx._ck(ctx.lib.sd_bench_fareval(ctx.h, v, 20000, C.byref(t))); print("fareval probe variant", v, "Gevals/s", t.value)
+for mode in range(4):
+    t = C.c_double(); ctx._ck(ctx.lib.sd_bench_fp64(ctx.h, mode, 4096, C.byref(t))); print("fp64 probe mode", mode, "TFLOP/s", t.value)
 x = 10.0 ** np.random.default_rng(0).uniform(0, 30, 1 << 20)
 outs = [np.empty_like(x) for _ in range(3)]
 ctx._ck(ctx.lib.sd_debug_rcp(ctx.h, x.size, L.ptr(x), *[L.ptr(o) for o in outs]))
