@@ -104,6 +104,13 @@ int sd_set_broadening(sd_ctx *ctx, const double *gammas, int32_t gamma_cols, con
  *          voigt_profile / _faddeeva voigt.py:17-155) -> alpha_line[slot] (D, p1-p0) --------------- */
 /* slot 0 = atomic lines ("alpha_line_at_nu"), slot 1 = molecular lines ("molecule_alpha_line_at_nu"). */
 int sd_calc_alpha_line(sd_ctx *ctx, int32_t slot);
+/* Far-field expansion of region-I wings per pixel tile (default ON).  A (line, depth) pair whose window covers a
+ * whole 256*P-pixel tile and whose line centre is at least 4 tile half-widths away is not evaluated pixel by pixel:
+ * its profile (two Lorentzians in Humlicek region I) is expanded in a degree-20 Taylor polynomial about the tile
+ * centre, the coefficients of all such pairs of a tile are summed once and the polynomial is added per pixel
+ * (relative deviation from the direct evaluation <= 6e-12, all terms positive).  sd_set_farfield(ctx, 0) evaluates
+ * every (line, depth, pixel) triple directly, exactly like the reference's loop. */
+int sd_set_farfield(sd_ctx *ctx, int32_t on);
 /* Statistics.  sd_set_line_stats(ctx, 1) makes the following sd_calc_alpha_line calls run the counting
  * instantiation of the kernel (slower; for tests and workload descriptions only).  sd_line_stats synchronises:
  * out[0..3] = Voigt evaluations per Humlicek region I..IV, out[4] = (line, depth) pairs with a non-empty

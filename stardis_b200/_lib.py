@@ -60,6 +60,7 @@ SIGNATURES = {
     "sd_calc_broadening": (C.c_int, [_V, C.c_uint32]),
     "sd_set_broadening": (C.c_int, [_V, _V, C.c_int32, _V]),
     "sd_calc_alpha_line": (C.c_int, [_V, C.c_int32]),
+    "sd_set_farfield": (C.c_int, [_V, C.c_int32]),
     "sd_set_line_stats": (C.c_int, [_V, C.c_int32]),
     "sd_line_stats": (C.c_int, [_V, _ip]),
     "sd_calc_continuum": (C.c_int, [_V, C.POINTER(SdContinuum), C.c_uint32]),

@@ -86,7 +86,7 @@ void sd_destroy(sd_ctx *c) {
     DevBuf *all[] = {&c->T, &c->ne, &c->nH, &c->nus, &c->d_nu, &c->l_nu, &c->l_Z, &c->l_ion, &c->l_eion, &c->l_eup,
                      &c->l_elo, &c->l_A, &c->l_mass, &c->l_stark, &c->l_waals, &c->l_alpha, &c->gammas, &c->dws,
                      &c->line_idx, &c->rec, &c->win_lo, &c->win_hi, &c->win_cls, &c->cls_list, &c->cls_off,
-                     &c->chunk_cnt, &c->stats, &c->alpha_line[0], &c->alpha_line[1], &c->total, &c->cont_small,
+                     &c->chunk_cnt, &c->stats, &c->near_tiles, &c->tile_geom, &c->far_coef, &c->batch_win, &c->batch_near, &c->alpha_line[0], &c->alpha_line[1], &c->total, &c->cont_small,
                      &c->F, &c->I_nus, &c->ray_small};
     for (DevBuf *b : all) free_buf(*b);
     for (int i = 0; i < SD_MAX_SOURCES; i++) free_buf(c->src[i]);
@@ -223,6 +223,13 @@ int sd_calc_alpha_line(sd_ctx *c, int32_t slot) {
     if (!c->records_ready) SD_TRY(sd_k2_prepare(c));
     SD_TRY(sd_k2_lines(c, slot));
     c->have_alpha[slot] = true;
+    return SD_OK;
+}
+
+int sd_set_farfield(sd_ctx *c, int32_t on) {
+    if (!c) return SD_ERR_ARG;
+    if (c->farfield != (on != 0)) c->records_ready = false;  // the near-tile intervals belong to the preparation pass
+    c->farfield = on != 0;
     return SD_OK;
 }
 

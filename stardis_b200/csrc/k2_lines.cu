@@ -5,24 +5,33 @@
 // parallel over lines with one private (D,N) slab per numba thread) and voigt.py:17-155.
 //
 // B200 design (gather, no atomics, deterministic):
-//   * one CTA owns a tile of 256*P consecutive pixels of ONE depth point and keeps the P accumulators of
-//     every thread in registers for the whole kernel; the result is written exactly once, coalesced;
-//   * the (line, depth) pairs that can touch the tile are found per half-width class (class 0: contiguous
-//     range of the nu-sorted line list; class k >= 1: contiguous range of the per-depth class list built by
-//     k1_broadening.cu; 32-ary warp binary searches on the monotone window centres);
-//   * every WARP streams the candidates in batches of 32 on its own (no CTA barrier in the main loop): test against
-//     the warp's 32*P-pixel span, expand the passing (line, depth) records into 96-byte shared-memory entries
+//   * one CTA owns a GLOBAL tile of 256*P consecutive pixels of ONE depth point (tiles are aligned to the global grid
+//     so that a nu shard reproduces the full-grid result bit for bit) and keeps the P accumulators of every thread in
+//     registers for the whole kernel; the result is written exactly once, coalesced;
+//   * the (line, depth) pairs that can touch the tile are found per half-width class (class 0: contiguous range of
+//     the nu-sorted line list; class k >= 1: contiguous range of the per-depth class list built by k1_broadening.cu;
+//     32-ary warp binary searches on the monotone window centres);
+//   * k_lines: every WARP streams the candidates in batches of 32 on its own (no CTA barrier in the main loop): test
+//     against the warp's 32*P-pixel span, expand the passing (line, depth) records into 96-byte shared-memory entries
 //     (constants hoisted once per warp), entries whose window covers the span and whose span lies entirely in
-//     Humlicek region I packed first ("far" list), the others from the back ("mixed" list), then consume them with
-//     broadcast LDS; summation order per pixel is fixed (class, batch, far entries in line order, mixed reversed);
-//   * the hot loop is the far-wing (region I) form  Kf (q + c1) / (q (q + b) + c),  q = x^2:
-//     8 FP64 instructions + 1 MUFU.RCP64H per evaluation (x, q, 2 for the denominator, numerator, 2 for the Newton
-//     step on the reciprocal seed, accumulate), no branches, no divisions;
+//     Humlicek region I packed first ("far-wing" list), the others from the back ("mixed" list), then consume them
+//     with broadcast LDS; summation order per pixel is fixed;
+//   * far-wing hot loop (region I):  Kf (q + c1) / (q (q + b) + c),  q = x^2:  8 FP64 instructions + 1 MUFU.RCP64H
+//     per evaluation (x, q, 2 for the denominator, numerator, 2 for the Newton step on the reciprocal seed,
+//     accumulate), no branches, no divisions;
 //   * pixels that are not certainly in region I take the exact path: x = dnu / dw (IEEE division) and the
-//     reference's own region tests, so the Humlicek classification is identical to the reference's.
+//     reference's own region tests, so the Humlicek classification is identical to the reference's;
+//   * FAR FIELD (k_far_coeffs + polynomial epilogue of k_lines): a pair whose window covers the whole tile and whose
+//     line centre is at least 4 tile half-widths away contributes a function that is analytic over the tile.  In
+//     region I,  Re w = (1/(2 sqrt(pi))) [ y/((x-a)^2+y^2) + y/((x+a)^2+y^2) ],  a = 1/sqrt(2): two Lorentzians, i.e.
+//     the imaginary part of two simple poles p = nu_l -+ dw/sqrt(2) + i y dw.  Their Taylor series about the tile
+//     centre nu_c,  1/(nu - p) = sum_k (-1)^k (nu - nu_c)^k / (nu_c - p)^(k+1),  converges with ratio <= 1/4; degree
+//     20 reproduces the direct evaluation to <= 6e-12 (relative, worst case; all terms are positive).
+//     k_far_coeffs accumulates the 21 coefficients of ALL far pairs of a tile (one pair per thread, ~230 FP64
+//     operations instead of 8 per pixel), k_lines skips exactly those pairs (same integer test on the per-pair
+//     "near tile interval" computed by k_build_records) and adds the polynomial at the end.
 //
-// Roofline: FP64 FMA pipe (no dense contraction -> no tensor cores).  Memory traffic is negligible:
-// 64 B per candidate record per tile, 8 B per output cell.
+// Roofline: FP64 FMA pipe (no dense contraction -> no tensor cores).  Memory traffic is negligible.
 #include <stdlib.h>
 
 #include "sd_internal.h"
@@ -50,6 +59,26 @@ struct __align__(16) WEntry {
 };
 static_assert(sizeof(WEntry) == 96, "WEntry layout");
 
+struct LineArgs {
+    int64_t L, N, p0, p1;
+    int D;
+    int tile0;     // global index of the first tile of this launch
+    int n_tiles;   // global number of tiles
+    const double *nus;
+    const int *line_idx;
+    const LineRec *rec;
+    const int *win_lo, *win_hi;
+    const uint8_t *win_cls;
+    const unsigned *near_tiles;  // nullptr: far field disabled
+    const int *cls_list, *cls_off;
+    const int4 *batch_win;       // per 32 class-list entries: {max lo, min hi, min lo, max hi}
+    const unsigned *batch_near;  //                            {min near-lo, max near-hi}
+    const double *tile_geom;
+    double *far_coef;            // (D, n_tiles_launch, SD_FAR_K + 1)
+    double *out;                 // (D, p1 - p0)
+    unsigned long long *stats;
+};
+
 // smallest j in [a, b] with (j == b or key(j) < X); key non-increasing in j.  Warp-cooperative 32-ary search.
 template <class KeyFn>
 __device__ __forceinline__ int warp_first_below(KeyFn key, int a, int b, int X) {
@@ -70,18 +99,121 @@ __device__ __forceinline__ int warp_first_below(KeyFn key, int a, int b, int X) 
     return a;
 }
 
+__device__ __forceinline__ int clamp_i32(long long v) {
+    return (int)(v > 2147483647LL ? 2147483647LL : (v < -2147483647LL ? -2147483647LL : v));
+}
+
+// Candidate range [ja, jb) of half-width class `cls` for the pixel interval [t0, t1) at depth d; executed by one warp.
+__device__ __forceinline__ void class_range(const LineArgs &a, int d, int cls, int64_t t0, int64_t t1, int &ja, int &jb) {
+    const int *line_idx = a.line_idx;
+    if (cls == 0) {
+        auto key = [&](int j) { return line_idx[j]; };
+        ja = warp_first_below(key, 0, (int)a.L, clamp_i32(t1 + SD_CLS0_HW));        // idx <  t1 + H
+        jb = warp_first_below(key, ja, (int)a.L, clamp_i32(t0 - SD_CLS0_HW + 1));   // idx <= t0 - H
+        return;
+    }
+    const int lo = a.cls_off[d * (SD_NCLS + 1) + cls], hi = a.cls_off[d * (SD_NCLS + 1) + cls + 1];
+    if (cls == SD_NCLS - 1) {
+        ja = lo;
+        jb = hi;
+        return;
+    }
+    const int *list_d = a.cls_list + (size_t)d * a.L;
+    const long long H = (long long)SD_CLS0_HW << (2 * cls);
+    auto key = [&](int j) { return line_idx[list_d[j]]; };
+    ja = warp_first_below(key, lo, hi, clamp_i32(t1 + H));
+    jb = warp_first_below(key, ja, hi, clamp_i32(t0 - H + 1));
+}
+
 __device__ __noinline__ double exact_contribution(double nu_i, double nu_l, double dw, double y, double K) {
     double x = (nu_i - nu_l) / dw;  // voigt.py:148, IEEE division
     return sdm::humlicek_re(x, y) * K;
 }
 
-template <int P, bool STATS, int RCP, bool U2, int MINB>
-__global__ void __launch_bounds__(THREADS, MINB) k_lines(int64_t L, int D, int64_t N, int64_t p0, int64_t p1,
-                                                   const double *__restrict__ nus, const int *__restrict__ line_idx,
-                                                   const LineRec *__restrict__ rec, const int *__restrict__ win_lo,
-                                                   const int *__restrict__ win_hi, const uint8_t *__restrict__ win_cls,
-                                                   const int *__restrict__ cls_list, const int *__restrict__ cls_off,
-                                                   double *__restrict__ out, unsigned long long *__restrict__ stats) {
+// The same integer test in both kernels: the pair covers the whole global tile and the tile lies outside the pair's
+// near interval -> it is expanded (k_far_coeffs) and must be skipped by the direct kernel.
+__device__ __forceinline__ bool pair_is_far(int lo, int hi, unsigned near, int64_t t0, int64_t t1, int tile) {
+    const int nl = (int)(near & 0xffffu), nh = (int)(near >> 16);
+    return (lo <= t0) && (hi >= t1) && (tile < nl || tile >= nh);
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// Far-field coefficients of one (tile, depth): C_k = -W Im(w+^(k+1) + w-^(k+1)),  w = -h / (nu_c - p),
+// W = K dw / (2 sqrt(pi) h);  the contribution of the pair at pixel nu is  sum_k C_k ((nu - nu_c)/h)^k.
+__global__ void __launch_bounds__(THREADS) k_far_coeffs(LineArgs a, int tile_px, int count_stats) {
+    constexpr int K1 = SD_FAR_K + 1;
+    __shared__ int s_ja[SD_NCLS], s_jb[SD_NCLS];
+    __shared__ double s_red[WARPS][K1];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int d = blockIdx.y;
+    const int tile = a.tile0 + blockIdx.x;
+    const int64_t t0 = (int64_t)tile * tile_px;
+    const int64_t t1 = (t0 + tile_px < a.N) ? t0 + tile_px : a.N;
+    const double nu_c = a.tile_geom[2 * tile], h = a.tile_geom[2 * tile + 1];
+    const size_t drow = (size_t)d * a.L;
+    const int *list_d = a.cls_list + drow;
+    {
+        int ja = 0, jb = 0;
+        if (warp >= 1) class_range(a, d, warp, t0, t1, ja, jb);  // class 0 windows (<= 128 px) never cover a tile
+        if (lane == 0) { s_ja[warp] = ja; s_jb[warp] = jb; }
+    }
+    __syncthreads();
+    double C[K1];
+#pragma unroll
+    for (int k = 0; k < K1; k++) C[k] = 0.0;
+    unsigned long long n_far = 0;
+    const double inv_h = 1.0 / h;
+    for (int cls = 1; cls < SD_NCLS; cls++) {
+        const int ja = s_ja[cls], jb = s_jb[cls];
+        for (int j = ja + tid; j < jb; j += THREADS) {
+            const size_t o = drow + list_d[j];
+            const int lo = a.win_lo[o], hi = a.win_hi[o];
+            if (!pair_is_far(lo, hi, a.near_tiles[o], t0, t1, tile)) continue;
+            const LineRec r = a.rec[o];
+            const double g = r.y * r.dw;                                       // Lorentz half-width in Hz
+            const double Wn = -r.K * r.dw * (0.5 * sdm::INV_SQRT_PI) * inv_h;  // -W
+            const double adw = 0.7071067811865476 * r.dw;
+            // w = -h / (D - i g) = -h (D + i g) / (D^2 + g^2) for the two poles
+            const double D1 = nu_c - (r.nu + adw), D2 = nu_c - (r.nu - adw);
+            const double i1 = -h * sdm::rcp_fast(fma(D1, D1, g * g)), i2 = -h * sdm::rcp_fast(fma(D2, D2, g * g));
+            const double w1r = D1 * i1, w1i = g * i1, w2r = D2 * i2, w2i = g * i2;
+            double p1r = w1r, p1i = w1i, p2r = w2r, p2i = w2i;
+#pragma unroll
+            for (int k = 0; k < K1; k++) {
+                C[k] = fma(Wn, p1i + p2i, C[k]);
+                if (k + 1 < K1) {
+                    double t;
+                    t = fma(p1r, w1r, -p1i * w1i); p1i = fma(p1r, w1i, p1i * w1r); p1r = t;
+                    t = fma(p2r, w2r, -p2i * w2i); p2i = fma(p2r, w2i, p2i * w2r); p2r = t;
+                }
+            }
+            n_far++;
+        }
+    }
+    // deterministic block reduction: lanes by shuffle, warps through shared memory in fixed order
+#pragma unroll
+    for (int k = 0; k < K1; k++) {
+        double v = C[k];
+        for (int o2 = 16; o2; o2 >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o2);
+        if (lane == 0) s_red[warp][k] = v;
+    }
+    __syncthreads();
+    if (tid < K1) {
+        double v = 0.0;
+#pragma unroll
+        for (int w = 0; w < WARPS; w++) v += s_red[w][tid];
+        a.far_coef[((size_t)d * gridDim.x + blockIdx.x) * K1 + tid] = v;
+    }
+    if (count_stats) {  // every far pair stands for one region-I evaluation per tile pixel inside the shard
+        for (int o2 = 16; o2; o2 >>= 1) n_far += __shfl_xor_sync(0xffffffffu, n_far, o2);
+        const int64_t e0 = t0 > a.p0 ? t0 : a.p0, e1 = t1 < a.p1 ? t1 : a.p1;
+        if (lane == 0 && n_far && e1 > e0) atomicAdd(&a.stats[0], n_far * (unsigned long long)(e1 - e0));
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+template <int P, bool STATS, int RCP, int MINB>
+__global__ void __launch_bounds__(THREADS, MINB) k_lines(LineArgs a) {
     constexpr int TILE = THREADS * P;
     constexpr int SPAN = 32 * P;
     __shared__ WEntry s_ent[WARPS][32];  // every warp streams its own batches: no CTA barrier in the main loop
@@ -90,12 +222,16 @@ __global__ void __launch_bounds__(THREADS, MINB) k_lines(int64_t L, int D, int64
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const unsigned lt_mask = (1u << lane) - 1u;
     const int d = blockIdx.y;
-    const int64_t t0 = p0 + (int64_t)blockIdx.x * TILE;
-    const int64_t t1 = (t0 + TILE < p1) ? t0 + TILE : p1;
-    const int64_t ws = t0 + (int64_t)warp * SPAN;                 // first pixel of this warp's span
-    const int64_t we = (ws + SPAN < t1) ? ws + SPAN : t1;         // one past its last valid pixel
+    const int64_t N = a.N, p0 = a.p0, p1 = a.p1, L = a.L;
+    const int tile = a.tile0 + blockIdx.x;
+    const int64_t t0 = (int64_t)tile * TILE;                       // GLOBAL tile [t0, t1)
+    const int64_t t1 = (t0 + TILE < N) ? t0 + TILE : N;
+    const int64_t ws = t0 + (int64_t)warp * SPAN;                  // this warp's global span [ws, we)
+    const int64_t we = (ws + SPAN < t1) ? ws + SPAN : t1;
     const size_t drow = (size_t)d * L;
-    const int *list_d = cls_list + drow;
+    const int *list_d = a.cls_list + drow;
+    const double *__restrict__ nus = a.nus;
+    const bool use_far = a.near_tiles != nullptr;
 
     // pixel frequencies and accumulators live in registers for the whole kernel
     double nu_i[P], acc[P];
@@ -109,42 +245,23 @@ __global__ void __launch_bounds__(THREADS, MINB) k_lines(int64_t L, int D, int64
     const double nu_first = nus[ws < N ? ws : N - 1];
     const double nu_last = nus[(we - 1 >= ws && we - 1 < N) ? we - 1 : (ws < N ? ws : N - 1)];
 
-    // candidate ranges of all classes, one warp per class
-    {
-        const int cls = warp;  // WARPS == SD_NCLS
+    {   // candidate ranges of all classes, one warp per class
         int ja, jb;
-        if (cls == 0) {
-            auto key = [&](int j) { return line_idx[j]; };
-            long long Xa = t1 + SD_CLS0_HW, Xb = t0 - SD_CLS0_HW + 1;  // idx < t1+H ; idx <= t0-H
-            ja = warp_first_below(key, 0, (int)L, (int)(Xa > 2147483647LL ? 2147483647LL : Xa));
-            jb = warp_first_below(key, ja, (int)L, (int)(Xb < -2147483647LL ? -2147483647LL : Xb));
-        } else {
-            int a = cls_off[d * (SD_NCLS + 1) + cls], b = cls_off[d * (SD_NCLS + 1) + cls + 1];
-            if (cls == SD_NCLS - 1) {
-                ja = a;
-                jb = b;
-            } else {
-                long long H = (long long)SD_CLS0_HW << (2 * cls);
-                auto key = [&](int j) { return line_idx[list_d[j]]; };
-                long long Xa = t1 + H, Xb = t0 - H + 1;
-                ja = warp_first_below(key, a, b, (int)(Xa > 2147483647LL ? 2147483647LL : Xa));
-                jb = warp_first_below(key, ja, b, (int)(Xb < -2147483647LL ? -2147483647LL : Xb));
-            }
-        }
-        if (lane == 0) {
-            s_ja[cls] = ja;
-            s_jb[cls] = jb;
-        }
+        class_range(a, d, warp, t0, t1, ja, jb);
+        if (lane == 0) { s_ja[warp] = ja; s_jb[warp] = jb; }
     }
     __syncthreads();
 
     unsigned long long h0 = 0, h1 = 0, h2 = 0, h3 = 0;
-    int nvalid = 0;  // this lane's pixels inside the tile (statistics only)
+    int nvalid = 0;  // this lane's pixels that belong to the shard (statistics only)
 #pragma unroll
-    for (int p = 0; p < P; p++) nvalid += (ws + p * 32 + lane) < t1;
+    for (int p = 0; p < P; p++) {
+        int64_t pix = ws + p * 32 + lane;
+        nvalid += (pix < t1) && (pix >= p0) && (pix < p1);
+    }
 
     WEntry *const my = s_ent[warp];
-    const bool warp_has_pixels = ws < t1;
+    const bool warp_has_pixels = (ws < t1) && (ws < p1) && (we > p0);
 
     // far-wing (region I) evaluation of one staged entry for the P pixels of this lane
     auto far_eval = [&](const double xl, const double inv_dw, const double eb, const double ec, const double Kc,
@@ -159,27 +276,58 @@ __global__ void __launch_bounds__(THREADS, MINB) k_lines(int64_t L, int D, int64
         }
     };
 
+    const int64_t nb_row = (L + 31) / 32;
+    const int4 *__restrict__ bwin = a.batch_win + (size_t)d * nb_row;
+    const unsigned *__restrict__ bnear = a.batch_near + (size_t)d * nb_row;
     for (int cls = 0; cls < SD_NCLS && warp_has_pixels; cls++) {
         const int ja = s_ja[cls], jb = s_jb[cls];
-        for (int base = ja; base < jb; base += 32) {
+        if (jb <= ja) continue;
+        // Class 0 walks the nu-sorted line list directly.  Classes >= 1 walk the class list in batches of 32 row
+        // positions; 32 batch summaries are checked at a time (one per lane) and only batches that overlap this
+        // warp's span and are not entirely far-field for the tile are opened.
+        const int b_first = (cls == 0) ? 0 : ja >> 5, b_last = (cls == 0) ? (jb - ja - 1) >> 5 : (jb - 1) >> 5;
+        for (int b0 = b_first; b0 <= b_last; b0 += 32) {
+            unsigned open_mask = 0xffffffffu;
+            if (cls != 0) {
+                bool need = false;
+                const int bb = b0 + lane;
+                if (bb <= b_last) {
+                    const int4 s4 = bwin[bb];
+                    need = (s4.z < we) && (s4.w > ws);  // some window may overlap the span
+                    if (need && use_far) {
+                        const unsigned nr = bnear[bb];
+                        const bool all_far = (s4.x <= t0) && (s4.y >= t1) &&
+                                             (tile < (int)(nr & 0xffffu) || tile >= (int)(nr >> 16));
+                        need = !all_far;
+                    }
+                }
+                open_mask = __ballot_sync(0xffffffffu, need);
+            } else if (b0 + 32 > b_last + 1) {
+                open_mask = (b_last - b0 + 1 >= 32) ? 0xffffffffu : ((1u << (b_last - b0 + 1)) - 1u);
+            }
+            while (open_mask) {
+                const int bsel = __ffs(open_mask) - 1;
+                open_mask &= open_mask - 1;
+                const int base = (cls == 0) ? ja + ((b0 + bsel) << 5) : (b0 + bsel) << 5;
             // ---- test the 32 candidates of this batch against THIS WARP's span ------------------------
             const int j = base + lane;
             bool pass = false;
             size_t o = 0;
             int lo = 0, hi = 0;
-            if (j < jb) {
+            if (j < jb && j >= ja) {
                 int l = (cls == 0) ? j : list_d[j];
                 o = drow + l;
-                lo = win_lo[o];
-                hi = win_hi[o];
-                pass = (lo < we) && (hi > ws) && (hi > lo) && (cls != 0 || win_cls[o] == 0);
+                lo = a.win_lo[o];
+                hi = a.win_hi[o];
+                pass = (lo < we) && (hi > ws) && (hi > lo) && (cls != 0 || a.win_cls[o] == 0);
+                if (pass && use_far && cls != 0) pass = !pair_is_far(lo, hi, a.near_tiles[o], t0, t1, tile);
             }
             if (!__any_sync(0xffffffffu, pass)) continue;
-            // ---- stage: hoist the per-(line, depth) constants; far entries first, mixed ones from the back -----
+            // ---- stage: hoist the per-(line, depth) constants; far-wing entries first, mixed ones from the back
             WEntry e;
             bool ff = false;
             if (pass) {
-                const LineRec r = rec[o];
+                const LineRec r = a.rec[o];
                 const double yy = r.y * r.y;
                 const double c1 = yy + 0.5;
                 e.xl = r.nu * r.inv_dw;
@@ -206,18 +354,10 @@ __global__ void __launch_bounds__(THREADS, MINB) k_lines(int64_t L, int D, int64
             const int n_far = __popc(m_far), n_mix = __popc(m_mix);
             if (pass) my[ff ? __popc(m_far & lt_mask) : 31 - __popc(m_mix & lt_mask)] = e;
             __syncwarp();
-            // ---- consume: far-wing entries, two per iteration (independent chains, loads hoisted) ----------
-            int k = 0;
-            for (; U2 && k + 1 < n_far; k += 2) {
-                const WEntry &a = my[k], &b = my[k + 1];
-                const double a0 = a.xl, a1 = a.inv_dw, a2 = a.b, a3 = a.c, a4 = a.Kc, a5 = a.Kf;
-                const double b0 = b.xl, b1 = b.inv_dw, b2 = b.b, b3 = b.c, b4 = b.Kc, b5 = b.Kf;
-                far_eval(a0, a1, a2, a3, a4, a5);
-                far_eval(b0, b1, b2, b3, b4, b5);
-            }
-            for (; k < n_far; k++) {
-                const WEntry &a = my[k];
-                far_eval(a.xl, a.inv_dw, a.b, a.c, a.Kc, a.Kf);
+            // ---- consume the far-wing entries ---------------------------------------------------------
+            for (int k = 0; k < n_far; k++) {
+                const WEntry &w = my[k];
+                far_eval(w.xl, w.inv_dw, w.b, w.c, w.Kc, w.Kf);
             }
             if (STATS) h0 += (unsigned long long)n_far * nvalid;
             // ---- mixed entries: window edge inside the span and/or pixels near the line core --------------
@@ -238,20 +378,43 @@ __global__ void __launch_bounds__(THREADS, MINB) k_lines(int64_t L, int D, int64
                     double v = num * (RCP == 2 ? sdm::rcp_fast2(den) : sdm::rcp_fast(den));
                     if (fast) acc[p] += v;
                     if (inwin && !fast) acc[p] += exact_contribution(nu_i[p], e2.nu, e2.dw, e2.y, e2.K);
-                    if (STATS && inwin) {
+                    if (STATS && inwin && pix >= p0 && pix < p1) {
                         int r = sdm::humlicek_region((nu_i[p] - e2.nu) / e2.dw, e2.y);
                         h0 += (r == 0); h1 += (r == 1); h2 += (r == 2); h3 += (r == 3);
                     }
                 }
             }
             __syncwarp();
+            }  // open batches
         }
+    }
+
+    // ---- far field: polynomial of the tile (Horner in t = (nu - nu_c) / h) -----------------------------------
+    if (use_far && warp_has_pixels) {
+        constexpr int K1 = SD_FAR_K + 1;
+        const double nu_c = a.tile_geom[2 * tile], inv_h = 1.0 / a.tile_geom[2 * tile + 1];
+        const double *__restrict__ C = a.far_coef + ((size_t)d * gridDim.x + blockIdx.x) * K1;
+        double tt[P], poly[P];
+        const double ck = C[K1 - 1];
+#pragma unroll
+        for (int p = 0; p < P; p++) {
+            tt[p] = (nu_i[p] - nu_c) * inv_h;
+            poly[p] = ck;
+        }
+#pragma unroll
+        for (int k = K1 - 2; k >= 0; k--) {
+            const double c = C[k];
+#pragma unroll
+            for (int p = 0; p < P; p++) poly[p] = fma(poly[p], tt[p], c);
+        }
+#pragma unroll
+        for (int p = 0; p < P; p++) acc[p] += poly[p];
     }
 
 #pragma unroll
     for (int p = 0; p < P; p++) {
         int64_t pix = ws + p * 32 + lane;
-        if (pix < t1) out[(size_t)d * (p1 - p0) + (pix - p0)] = acc[p];
+        if (pix < t1 && pix >= p0 && pix < p1) a.out[(size_t)d * (p1 - p0) + (pix - p0)] = acc[p];
     }
     if (STATS) {
         for (int o2 = 16; o2; o2 >>= 1) {
@@ -261,10 +424,10 @@ __global__ void __launch_bounds__(THREADS, MINB) k_lines(int64_t L, int D, int64
             h3 += __shfl_xor_sync(0xffffffffu, h3, o2);
         }
         if (lane == 0) {
-            if (h0) atomicAdd(&stats[0], h0);
-            if (h1) atomicAdd(&stats[1], h1);
-            if (h2) atomicAdd(&stats[2], h2);
-            if (h3) atomicAdd(&stats[3], h3);
+            if (h0) atomicAdd(&a.stats[0], h0);
+            if (h1) atomicAdd(&a.stats[1], h1);
+            if (h2) atomicAdd(&a.stats[2], h2);
+            if (h3) atomicAdd(&a.stats[3], h3);
         }
     }
 }
@@ -275,51 +438,65 @@ int env_int(const char *name, int dflt) {
 }
 
 template <int P>
-int launch(sd_ctx *c, int slot, bool stats, int rcp) {
-    int64_t W = c->W();
-    dim3 grid((unsigned)((W + THREADS * P - 1) / (THREADS * P)), (unsigned)c->D);
-    auto args = [&](auto kern) {
-        kern<<<grid, THREADS, 0, c->stream>>>(c->L, c->D, c->N, c->p0, c->p1, c->nus.as<double>(), c->line_idx.as<int>(),
-                                              c->rec.as<LineRec>(), c->win_lo.as<int>(), c->win_hi.as<int>(),
-                                              c->win_cls.as<uint8_t>(), c->cls_list.as<int>(), c->cls_off.as<int>(),
-                                              c->alpha_line[slot].as<double>(), c->stats.as<unsigned long long>());
-    };
-    // the counting instantiation uses the production arithmetic (Newton reciprocal) so that both are bitwise equal
-    static const int u2 = env_int("SD_K2_U2", 0);
+int launch(sd_ctx *c, const LineArgs &a, dim3 grid, bool stats, int rcp) {
     static const int minb = env_int("SD_K2_MINB", 2);
-    if (stats) args(k_lines<P, true, 2, false, 2>);
-    else if (rcp == 3) args(k_lines<P, false, 3, false, 2>);
-    else if (u2) args(k_lines<P, false, 2, true, 2>);
-    else if (minb == 1) args(k_lines<P, false, 2, false, 1>);
-    else if (minb == 3) args(k_lines<P, false, 2, false, 3>);
-    else if (minb == 4) args(k_lines<P, false, 2, false, 4>);
-    else args(k_lines<P, false, 2, false, 2>);
+    // the counting instantiation uses the production arithmetic (Newton reciprocal) so that both are bitwise equal
+    if (stats) k_lines<P, true, 2, 2><<<grid, THREADS, 0, c->stream>>>(a);
+    else if (rcp == 3) k_lines<P, false, 3, 2><<<grid, THREADS, 0, c->stream>>>(a);
+    else if (minb == 3) k_lines<P, false, 2, 3><<<grid, THREADS, 0, c->stream>>>(a);
+    else k_lines<P, false, 2, 2><<<grid, THREADS, 0, c->stream>>>(a);
     return sd_launch_check(c, "k_lines");
 }
 
 }  // namespace
 
+// pixels per thread: enough CTAs to fill the chip several times over, otherwise as much register reuse of the staged
+// entries as possible.  SD_K2_P overrides the choice (tuning experiments).
+int sd_k2_choose_P(sd_ctx *c) {
+    static const int force_p = env_int("SD_K2_P", 0);
+    if (force_p == 1 || force_p == 2 || force_p == 4 || force_p == 8) return force_p;
+    const int64_t W = c->W();
+    if (((W + 2047) / 2048) * c->D >= 8LL * c->sm_count) return 8;
+    if (((W + 1023) / 1024) * c->D >= 4LL * c->sm_count) return 4;
+    if (((W + 511) / 512) * c->D >= 4LL * c->sm_count) return 2;
+    return 1;
+}
+
 int sd_k2_lines(sd_ctx *c, int slot) {
-    int64_t W = c->W();
+    const int64_t W = c->W();
     SD_TRY(sd_ensure(c, c->alpha_line[slot], sizeof(double) * c->D * W));
     if (c->L == 0) {
         SD_CUDA(c, cudaMemsetAsync(c->alpha_line[slot].p, 0, sizeof(double) * c->D * W, c->stream));
         return SD_OK;
     }
     if (c->line_stats) SD_CUDA(c, cudaMemsetAsync(c->stats.p, 0, 4 * sizeof(unsigned long long), c->stream));
-    // pixels per thread: enough CTAs to fill the chip several times over, otherwise as much register reuse
-    // of the staged entries as possible.  SD_K2_P / SD_K2_RCP override the choice (tuning experiments).
-    static const int force_p = env_int("SD_K2_P", 0);
     static const int rcp = env_int("SD_K2_RCP", 2);
-    int P = 1;
-    if (((W + 2047) / 2048) * c->D >= 8LL * c->sm_count) P = 8;
-    else if (((W + 1023) / 1024) * c->D >= 4LL * c->sm_count) P = 4;
-    else if (((W + 511) / 512) * c->D >= 4LL * c->sm_count) P = 2;
-    if (force_p) P = force_p;
+    const int P = c->k2_P, tile = THREADS * P;
+    LineArgs a{};
+    a.L = c->L; a.N = c->N; a.p0 = c->p0; a.p1 = c->p1; a.D = c->D;
+    a.tile0 = (int)(c->p0 / tile);
+    a.n_tiles = (int)((c->N + tile - 1) / tile);
+    const int n_launch = (int)((c->p1 + tile - 1) / tile) - a.tile0;
+    a.nus = c->nus.as<double>(); a.line_idx = c->line_idx.as<int>(); a.rec = c->rec.as<LineRec>();
+    a.win_lo = c->win_lo.as<int>(); a.win_hi = c->win_hi.as<int>(); a.win_cls = c->win_cls.as<uint8_t>();
+    a.near_tiles = c->farfield ? c->near_tiles.as<unsigned>() : nullptr;
+    a.cls_list = c->cls_list.as<int>(); a.cls_off = c->cls_off.as<int>();
+    a.tile_geom = c->tile_geom.as<double>();
+    a.batch_win = c->batch_win.as<int4>();
+    a.batch_near = c->batch_near.as<unsigned>();
+    a.out = c->alpha_line[slot].as<double>();
+    a.stats = c->stats.as<unsigned long long>();
+    dim3 grid((unsigned)n_launch, (unsigned)c->D);
+    if (c->farfield) {
+        SD_TRY(sd_ensure(c, c->far_coef, sizeof(double) * c->D * n_launch * (SD_FAR_K + 1)));
+        a.far_coef = c->far_coef.as<double>();
+        k_far_coeffs<<<grid, THREADS, 0, c->stream>>>(a, tile, c->line_stats ? 1 : 0);
+        SD_TRY(sd_launch_check(c, "k_far_coeffs"));
+    }
     switch (P) {
-        case 8: return launch<8>(c, slot, c->line_stats, rcp);
-        case 4: return launch<4>(c, slot, c->line_stats, rcp);
-        case 2: return launch<2>(c, slot, c->line_stats, rcp);
-        default: return launch<1>(c, slot, c->line_stats, rcp);
+        case 8: return launch<8>(c, a, grid, c->line_stats, rcp);
+        case 4: return launch<4>(c, a, grid, c->line_stats, rcp);
+        case 2: return launch<2>(c, a, grid, c->line_stats, rcp);
+        default: return launch<1>(c, a, grid, c->line_stats, rcp);
     }
 }

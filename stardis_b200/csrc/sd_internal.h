@@ -23,6 +23,9 @@ static_assert(sizeof(LineRec) == 64, "LineRec must be 64 bytes");
 constexpr int SD_NCLS = 8;          // half-width classes
 constexpr int SD_CLS0_HW = 64;      // class 0: hw <= 64; class k: hw <= 64 * 4^k; last class: everything wider
 constexpr int SD_MAX_SOURCES = 4 + SD_MAX_TABLES;
+// far-field (Taylor) expansion of region-I wings per pixel tile: order and convergence radius
+constexpr int SD_FAR_K = 20;            // polynomial degree (21 coefficients)
+constexpr double SD_FAR_RHO_INV = 4.0;  // a (line, depth) pair is expanded only if |nu_c - pole| >= 4 h
 
 struct DevBuf {
     void *p = nullptr;
@@ -68,6 +71,13 @@ struct sd_ctx {
     DevBuf cls_off;    // int32 [D*(NCLS+1)] offsets into cls_list row d (class 0 is not listed)
     DevBuf chunk_cnt;  // int32 [D * nchunks * NCLS]
     DevBuf stats;      // uint64 [8]
+    DevBuf batch_win;  // int4 [D * ceil(L/32)]: {max lo, min hi, min lo, max hi} over 32 consecutive class-list entries
+    DevBuf batch_near; // uint32 [D * ceil(L/32)]: {min near-lo, max near-hi} of the same entries
+    DevBuf near_tiles; // uint32 [D*L]: tiles [lo16, hi16) around the line centre that must be evaluated directly
+    DevBuf tile_geom;  // double [2 * n_tiles_global]: centre frequency and half-width of every global pixel tile
+    DevBuf far_coef;   // double [D * n_tiles_shard * (SD_FAR_K + 1)]
+    int k2_P = 4;      // pixels per thread chosen for the current grid (tile = 256 * k2_P pixels)
+    bool farfield = true;
     DevBuf alpha_line[2];
     bool have_alpha[2] = {false, false};
     bool records_ready = false;
@@ -116,6 +126,7 @@ int sd_launch_check(sd_ctx *c, const char *what);
 int sd_k1_broadening(sd_ctx *c, uint32_t flags);
 int sd_k2_prepare(sd_ctx *c);
 int sd_k2_lines(sd_ctx *c, int slot);
+int sd_k2_choose_P(sd_ctx *c);
 int sd_k3_continuum(sd_ctx *c, const sd_continuum *desc, uint32_t store_mask);
 int sd_k4_raytrace(sd_ctx *c, int n_theta, const double *ray_ds, const double *weights, int inward, double scale,
                    int track);

@@ -129,6 +129,10 @@ class DeviceContext:
     def calc_alpha_line(self, slot=0):
         self._ck(self.lib.sd_calc_alpha_line(self.h, int(slot)))
 
+    def set_farfield(self, on=True):
+        """Far-field (Taylor) expansion of distant region-I wings per pixel tile; off = evaluate every pixel directly."""
+        self._ck(self.lib.sd_set_farfield(self.h, int(bool(on))))
+
     def set_line_stats(self, on=True):
         self._ck(self.lib.sd_set_line_stats(self.h, int(bool(on))))
 

@@ -196,3 +196,48 @@ def test_k4_many_angles_chunked(ctx, oracle):
     ctx.raytrace(np.diff(g["r_pp"]).reshape(-1, 1) / np.cos(th), w, track=True)
     np.testing.assert_allclose(ctx.get(L.BUF_F_NU), F, rtol=1e-9, atol=1e-300)
     np.testing.assert_allclose(ctx.get(L.BUF_I_NUS), I_nus, rtol=1e-9, atol=1e-300)
+
+
+# ------------------------------------------------------------------ K2 far-field expansion
+@pytest.mark.parametrize("P", [1, 8])
+def test_k2_far_field_expansion_matches_direct_evaluation_and_oracle(ctx, oracle, P, monkeypatch):
+    """Grid of many tiles with strong (full-grid) lines: with the far-field expansion most (line, depth, tile) triples
+    are summed as Taylor coefficients; the result must agree with the direct evaluation and with the CPU oracle, the
+    evaluation count / region histogram must still be the reference's, and a nu shard must still be bit-identical."""
+    from stardis_b200 import _lib as L
+
+    rng = np.random.default_rng(11)
+    N, Ln, D = 50000, 900, 3
+    lam = np.arange(4000.0, 4000.0 + N * 0.01, 0.01)[:N]
+    nus = 2.99792458e18 / lam
+    line_nus = np.sort(rng.uniform(nus.min(), nus.max(), Ln))
+    dws = rng.uniform(1.5e9, 5e9, (Ln, D))
+    gam = 10.0 ** rng.uniform(6.5, 10.5, (Ln, D))
+    d_nu = oracle.d_nu(nus)
+    target_hw = 10.0 ** rng.uniform(0.8, 6.5, (Ln, D))  # 6 px ... far beyond the grid
+    al = target_hw * d_nu / 20.0 / (gam + dws)
+    ref, evals, hist = oracle.calc_alan_entries(D, nus, line_nus, dws, gam, al, with_stats=True)
+    ctx.set_atmosphere(np.full(D, 5000.0))
+    results = {}
+    for far in (True, False):
+        ctx.set_farfield(far)
+        ctx.set_grid(nus)
+        ctx.set_lines(line_nus, al)
+        ctx.set_broadening(gam, dws)
+        ctx.set_line_stats(True)
+        ctx.calc_alpha_line(0)
+        results[far] = ctx.get(L.BUF_ALPHA_LINE)
+        st = ctx.line_stats()
+        ctx.set_line_stats(False)
+        assert st["evals"] == evals and np.array_equal(st["region_evals"], hist)
+        ctx.calc_alpha_line(0)  # production instantiation: bitwise equal to the counting one
+        assert np.array_equal(ctx.get(L.BUF_ALPHA_LINE), results[far])
+    np.testing.assert_allclose(results[False], ref, rtol=1e-10)
+    np.testing.assert_allclose(results[True], ref, rtol=1e-10)
+    np.testing.assert_allclose(results[True], results[False], rtol=2e-11)
+    assert not np.array_equal(results[True], results[False])  # the expansion was actually used
+    ctx.set_farfield(True)
+    p0, p1 = 12345, 30001  # not tile aligned
+    ctx.set_grid(nus, p0, p1)
+    ctx.calc_alpha_line(0)
+    assert np.array_equal(ctx.get(L.BUF_ALPHA_LINE), results[True][:, p0:p1])

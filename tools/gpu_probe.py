@@ -42,6 +42,14 @@ for rep in range(3):
     ctx.calc_alpha_line(0)
     t2 = ctx.timer_stop()
     print(f"rep {rep}: K1 {t1:.3f} ms, K2(prep+lines) {t2:.3f} ms")
+a_far = ctx.get(L.BUF_ALPHA_LINE)
+ctx.set_farfield(False)
+ctx.calc_alpha_line(0)
+ctx.timer_start(); ctx.calc_alpha_line(0); t_direct = ctx.timer_stop()
+a_dir = ctx.get(L.BUF_ALPHA_LINE)
+print(f"direct mode K2 {t_direct:.3f} ms; far-field vs direct max rel dev {np.max(np.abs(a_far - a_dir) / a_dir):.3e}")
+ctx.set_farfield(True)
+ctx.calc_alpha_line(0)
 ctx.set_line_stats(True)
 ctx.calc_alpha_line(0)
 st = ctx.line_stats()
