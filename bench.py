@@ -313,23 +313,51 @@ def run_b200_arm(args):
     stats = ctx.line_stats()
     ctx.set_line_stats(False)
     reg = torch.tensor(stats["region_evals"].astype(np.float64), device="cuda")
-    k2 = torch.tensor([phase[1]], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(reg)
-        dist.all_reduce(k2, op=dist.ReduceOp.MAX)
     region_evals = reg.cpu().numpy()
-    # the K2 phase contains the six small preparation kernels; time the Voigt kernel alone for the roofline
-    ctx.calc_alpha_line(0)
+
+    def time_k2(reps):
+        """Device time of the Voigt accumulation alone (k_far_coeffs + k_lines; records already prepared)."""
+        ctx.calc_alpha_line(0)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ms = []
+        for _ in range(reps):
+            e0.record(stream)
+            ctx.lib.sd_calc_alpha_line(ctx.h, 0)
+            e1.record(stream)
+            e1.synchronize()
+            ms.append(e0.elapsed_time(e1))
+        return float(np.mean(ms))
+
+    k2_far_ms = time_k2(max(2, args.steps))
+    a_far = torch.empty((D, W), dtype=torch.float64, device="cuda")
+    ctx.get(L.BUF_ALPHA_LINE, out=a_far)
+    # ---- the same step with the far-field expansion switched OFF: every (line, depth, pixel) triple is evaluated
+    # directly, like the reference's loop.  This is the kernel the FP64 roofline is quoted for.
+    ctx.set_farfield(False)
+    device_step()
+    barrier()
+    n_direct = max(1, args.steps // 3)
+    td0, td1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    td0.record(stream)
+    for _ in range(n_direct):
+        device_step()
+    td1.record(stream)
+    barrier()
+    t = torch.tensor([td0.elapsed_time(td1) / n_direct], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_direct = float(t.item())
+    k2_kernel_ms = time_k2(max(1, n_direct))
+    a_dir = torch.empty((D, W), dtype=torch.float64, device="cuda")
+    ctx.get(L.BUF_ALPHA_LINE, out=a_dir)
     torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    k2_ms = []
-    for _ in range(max(2, args.steps)):
-        e0.record(stream)
-        ctx.lib.sd_calc_alpha_line(ctx.h, 0)
-        e1.record(stream)
-        e1.synchronize()
-        k2_ms.append(e0.elapsed_time(e1))
-    k2_kernel_ms = float(np.mean(k2_ms))
+    far_dev = float(((a_far - a_dir).abs() / a_dir.abs().clamp_min(1e-300)).max().item())
+    del a_far, a_dir
+    ctx.set_farfield(True)
+    ctx.calc_alpha_line(0)
     dfma_peak = ctx.bench_dfma(8192)
     flops = float((stats["region_evals"] * FLOPS_PER_EVAL).sum())  # this rank's launch
     achieved_tflops = flops / (k2_kernel_ms * 1e-3) / 1e12
@@ -391,11 +419,17 @@ def run_b200_arm(args):
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": desc, "l2": "inputs larger than L2 (line records %.2f GB, outputs %.2f GB per array)"
                        % (len(sel) * D * 64 / 1e9, cells * 8 / 1e9), "partition": f"nu shards over {world} rank(s), global windows"},
-            "roofline": {"kernel": "k_lines (K2, windowed Voigt accumulation)", "bound": "fp64", "achieved": achieved_tflops,
+            "roofline": {"kernel": "k_lines, direct mode (K2: every (line, depth, pixel) Voigt evaluation done explicitly, "
+                                   "far-field expansion off)", "bound": "fp64", "achieved": achieved_tflops,
                          "peak": dfma_peak, "unit": "TFLOP/s", "frac": achieved_tflops / dfma_peak, "traffic": None,
                          "peak_source": "measured in this run: dependent-free DFMA loop on all SMs (sd_bench_dfma)",
                          "flops_per_eval": FLOPS_PER_EVAL.tolist(), "region_evals_all_ranks": region_evals.tolist(),
                          "kernel_ms": k2_kernel_ms, "gevals_per_s": float(stats["evals"] / k2_kernel_ms / 1e6)},
+            "farfield": {"what": "default mode: distant region-I wings summed as degree-20 Taylor coefficients per pixel "
+                                 "tile (k_far_coeffs) instead of per pixel; same result within max_rel_dev",
+                         "k2_ms": k2_far_ms, "k2_ms_direct": k2_kernel_ms, "k2_speedup": k2_kernel_ms / k2_far_ms,
+                         "max_rel_dev_vs_direct": far_dev, "ms_per_step_direct": ms_direct,
+                         "value_direct_mode": N / (ms_direct * 1e-3)},
             "roofline_hbm": {"kernel": "k_continuum + k_raytrace (K3+K4)", "bound": "hbm",
                              "achieved": BYTES_PER_CELL * cells / ((phase[2] + phase[3]) * 1e-3) / 1e9, "peak": hbm_peak,
                              "unit": "GB/s", "frac": BYTES_PER_CELL * cells / ((phase[2] + phase[3]) * 1e-3) / 1e9 / hbm_peak,
