@@ -101,12 +101,15 @@ __device__ __forceinline__ bool tile_is_far(double nu_c, double h, double nu_l, 
     return (dist >= SD_FAR_RHO_INV * h + a_dw) && (dist >= core) && (dw > 0.0) && (y >= 0.0) && (y < 1e300) && (h > 0.0);
 }
 
-__device__ __forceinline__ int hw_class(long long hw) {
-    // class 0: hw <= 64, class k: hw <= 64 * 4^k, last class: wider (scanned unconditionally)
+__device__ __forceinline__ int hw_class(long long hw, bool whole_grid) {
+    // class 0: hw <= 64; class k (1..5): hw <= 64 * 4^k; class 6: wider, with a window edge inside the grid; class 7:
+    // window == the whole grid.  Classes 6 and 7 are scanned unconditionally; class 7 is homogeneous (every pair covers
+    // every tile), which is what makes whole batches of it skippable by their summary.
+    if (whole_grid) return SD_NCLS - 1;
     if (hw <= SD_CLS0_HW) return 0;
     int k = 1;
     long long lim = (long long)SD_CLS0_HW * 4;
-    while (k < SD_NCLS - 1 && hw > lim) { k++; lim *= 4; }
+    while (k < SD_NCLS - 2 && hw > lim) { k++; lim *= 4; }
     return k;
 }
 
@@ -118,9 +121,7 @@ __global__ void __launch_bounds__(256) k_build_records(int64_t L, int D, int64_t
                                                        const double *__restrict__ alpha, const double *__restrict__ d_nu_p,
                                                        LineRec *__restrict__ rec, int *__restrict__ win_lo,
                                                        int *__restrict__ win_hi, uint8_t *__restrict__ win_cls,
-                                                       int tile, int n_tiles, const double *__restrict__ geom,
-                                                       unsigned *__restrict__ near_tiles,
-                                                       unsigned long long *__restrict__ stats) {
+                                                       FarGeom fg, unsigned long long *__restrict__ stats) {
     int64_t g = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     bool active = g < L * D;
     unsigned nonempty = 0, wide = 0, zero_dw = 0;
@@ -137,7 +138,7 @@ __global__ void __launch_bounds__(256) k_build_records(int64_t L, int D, int64_t
         double broad = ((gam + dw) * a) / d_nu * 20.0;
         double forced = (broad > 10.0) ? broad : 10.0;
         long long hw = (forced < 4.0e18) ? (long long)forced : (long long)4e18;
-        int cls = hw_class(hw);
+        int cls = hw_class(hw, lo == 0 && hi == N && hi > lo);
         double y = (gam / sdm::SQRT_PI_PI) / dw;
         LineRec r;
         r.nu = line_nu[l];
@@ -154,10 +155,15 @@ __global__ void __launch_bounds__(256) k_build_records(int64_t L, int D, int64_t
         win_lo[o] = (int)lo;
         win_hi[o] = (int)hi;
         win_cls[o] = (uint8_t)cls;
-        // tiles [nl, nh) around the line centre that are NOT far: only windows that can cover a whole tile matter
-        unsigned nl = 0, nh = 0xffffu;
-        if (near_tiles) {
+        // per hierarchy level: tiles [nl, nh) around the line centre that are NOT far (only windows that can cover a
+        // whole tile of that level matter; everything else keeps the default "never far")
+#pragma unroll
+        for (int k = 0; k < SD_FAR_LEVELS; k++) {
+            if (!fg.near[k]) continue;
+            unsigned nl = 0, nh = 0xffffu;
+            const int tile = fg.tile[k], n_tiles = fg.n_tiles[k];
             if (hi - lo >= tile && r.thr == r.thr) {
+                const double *__restrict__ geom = fg.geom[k];
                 int tc = (int)(line_idx[l] / tile);
                 if (tc >= n_tiles) tc = n_tiles - 1;
                 int a_ = tc, b_ = tc + 1;
@@ -166,7 +172,7 @@ __global__ void __launch_bounds__(256) k_build_records(int64_t L, int D, int64_t
                 nl = (unsigned)a_;
                 nh = (unsigned)b_;
             }
-            near_tiles[o] = nl | (nh << 16);
+            fg.near[k][o] = nl | (nh << 16);
         }
         nonempty = hi > lo;
         wide = (hi > lo) && cls > 0;
@@ -259,8 +265,8 @@ __global__ void __launch_bounds__(CHUNK) k_cls_scatter(int64_t L, const uint8_t 
 // kernel skip a whole batch that is entirely far-field for its tile (or does not overlap it) with one 20-byte read.
 __global__ void __launch_bounds__(256) k_batch_summaries(int64_t L, int D, const int *__restrict__ cls_list,
                                                          const int *__restrict__ cls_off, const int *__restrict__ win_lo,
-                                                         const int *__restrict__ win_hi, const unsigned *__restrict__ near_tiles,
-                                                         int4 *__restrict__ batch_win, unsigned *__restrict__ batch_near) {
+                                                         const int *__restrict__ win_hi, FarGeom fg,
+                                                         int4 *__restrict__ batch_win) {
     const int lane = threadIdx.x & 31;
     const int64_t nb = (L + 31) / 32;
     const int64_t b = blockIdx.x * (int64_t)(blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -269,27 +275,37 @@ __global__ void __launch_bounds__(256) k_batch_summaries(int64_t L, int D, const
     const int64_t pos = b * 32 + lane;
     const int n_listed = cls_off[d * (SD_NCLS + 1) + SD_NCLS];
     int mx_lo = -2147483647, mn_hi = 2147483647, mn_lo = 2147483647, mx_hi = -2147483647;
-    unsigned mn_nl = 0xffffu, mx_nh = 0u;
+    unsigned mn_nl[SD_FAR_LEVELS], mx_nh[SD_FAR_LEVELS];
+#pragma unroll
+    for (int k = 0; k < SD_FAR_LEVELS; k++) { mn_nl[k] = 0xffffu; mx_nh[k] = 0u; }
     if (pos < n_listed) {
         const size_t o = (size_t)d * L + cls_list[(size_t)d * L + pos];
         const int lo = win_lo[o], hi = win_hi[o];
         mx_lo = mn_lo = lo;
         mn_hi = mx_hi = hi;
-        const unsigned nr = near_tiles ? near_tiles[o] : 0xffff0000u;
-        mn_nl = nr & 0xffffu;
-        mx_nh = nr >> 16;
+#pragma unroll
+        for (int k = 0; k < SD_FAR_LEVELS; k++) {
+            const unsigned nr = fg.near[k] ? fg.near[k][o] : 0xffff0000u;
+            mn_nl[k] = nr & 0xffffu;
+            mx_nh[k] = nr >> 16;
+        }
     }
     for (int o2 = 16; o2; o2 >>= 1) {
         mx_lo = max(mx_lo, __shfl_xor_sync(0xffffffffu, mx_lo, o2));
         mn_hi = min(mn_hi, __shfl_xor_sync(0xffffffffu, mn_hi, o2));
         mn_lo = min(mn_lo, __shfl_xor_sync(0xffffffffu, mn_lo, o2));
         mx_hi = max(mx_hi, __shfl_xor_sync(0xffffffffu, mx_hi, o2));
-        mn_nl = min(mn_nl, __shfl_xor_sync(0xffffffffu, mn_nl, o2));
-        mx_nh = max(mx_nh, __shfl_xor_sync(0xffffffffu, mx_nh, o2));
+#pragma unroll
+        for (int k = 0; k < SD_FAR_LEVELS; k++) {
+            mn_nl[k] = min(mn_nl[k], __shfl_xor_sync(0xffffffffu, mn_nl[k], o2));
+            mx_nh[k] = max(mx_nh[k], __shfl_xor_sync(0xffffffffu, mx_nh[k], o2));
+        }
     }
     if (lane == 0) {
         batch_win[(size_t)d * nb + b] = make_int4(mx_lo, mn_hi, mn_lo, mx_hi);
-        batch_near[(size_t)d * nb + b] = mn_nl | (mx_nh << 16);
+#pragma unroll
+        for (int k = 0; k < SD_FAR_LEVELS; k++)
+            if (fg.batch_near[k]) fg.batch_near[k][(size_t)d * nb + b] = mn_nl[k] | (mx_nh[k] << 16);
     }
 }
 
@@ -319,14 +335,21 @@ int sd_k2_prepare(sd_ctx *c) {
     SD_TRY(sd_ensure(c, c->cls_off, sizeof(int) * D * (SD_NCLS + 1)));
     k_dnu<<<1, 1024, 0, c->stream>>>(c->N, c->nus.as<double>(), c->d_nu.as<double>());
     SD_TRY(sd_launch_check(c, "k_dnu"));
-    // pixels per thread of the line kernel (tile = 256 * P pixels) and the geometry of the global tiles
+    // pixels per thread of the line kernel (level-0 tile = 256 * P pixels) and the geometry of the tile hierarchy
     c->k2_P = sd_k2_choose_P(c);
-    const int tile = 256 * c->k2_P;
-    const int n_tiles = (int)((c->N + tile - 1) / tile);
-    SD_CHECK(c, n_tiles < 65535, SD_ERR_ARG, "grid too long for 16-bit tile indices");
-    SD_TRY(sd_ensure(c, c->tile_geom, sizeof(double) * 2 * n_tiles));
-    k_tile_geometry<<<(n_tiles + 255) / 256, 256, 0, c->stream>>>(c->N, tile, n_tiles, c->nus.as<double>(), c->tile_geom.as<double>());
-    SD_TRY(sd_launch_check(c, "k_tile_geometry"));
+    FarGeom &fg = c->far_geom;
+    for (int k = 0; k < SD_FAR_LEVELS; k++) {
+        fg.tile[k] = (256 * c->k2_P) << (SD_FAR_SHIFT * k);
+        fg.n_tiles[k] = (int)((c->N + fg.tile[k] - 1) / fg.tile[k]);
+        SD_CHECK(c, fg.n_tiles[k] < 65535, SD_ERR_ARG, "grid too long for 16-bit tile indices");
+        SD_TRY(sd_ensure(c, c->tile_geom[k], sizeof(double) * 2 * fg.n_tiles[k]));
+        fg.geom[k] = c->tile_geom[k].as<double>();
+        k_tile_geometry<<<(fg.n_tiles[k] + 255) / 256, 256, 0, c->stream>>>(c->N, fg.tile[k], fg.n_tiles[k], c->nus.as<double>(),
+                                                                          c->tile_geom[k].as<double>());
+        SD_TRY(sd_launch_check(c, "k_tile_geometry"));
+        fg.near[k] = nullptr;
+        fg.batch_near[k] = nullptr;
+    }
     if (L == 0) {
         SD_CUDA(c, cudaMemsetAsync(c->cls_off.p, 0, sizeof(int) * D * (SD_NCLS + 1), c->stream));
         c->records_ready = true;
@@ -338,7 +361,14 @@ int sd_k2_prepare(sd_ctx *c) {
     SD_TRY(sd_ensure(c, c->win_hi, sizeof(int) * n));
     SD_TRY(sd_ensure(c, c->win_cls, n));
     SD_TRY(sd_ensure(c, c->cls_list, sizeof(int) * n));
-    SD_TRY(sd_ensure(c, c->near_tiles, sizeof(unsigned) * n));
+    const int64_t nb = (L + 31) / 32;
+    if (c->farfield)
+        for (int k = 0; k < SD_FAR_LEVELS; k++) {
+            SD_TRY(sd_ensure(c, c->near_tiles[k], sizeof(unsigned) * n));
+            SD_TRY(sd_ensure(c, c->batch_near[k], sizeof(unsigned) * (size_t)D * nb));
+            fg.near[k] = c->near_tiles[k].as<unsigned>();
+            fg.batch_near[k] = c->batch_near[k].as<unsigned>();
+        }
     int nchunks = (int)((L + CHUNK - 1) / CHUNK);
     SD_TRY(sd_ensure(c, c->chunk_cnt, sizeof(int) * (size_t)D * SD_NCLS * nchunks));
     k_line_idx<<<(unsigned)((L + 255) / 256), 256, 0, c->stream>>>(L, c->N, c->nus.as<double>(), c->l_nu.as<double>(),
@@ -347,8 +377,7 @@ int sd_k2_prepare(sd_ctx *c) {
     k_build_records<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(
         L, D, c->N, c->l_nu.as<double>(), c->line_idx.as<int>(), c->gammas.as<double>(), c->gamma_cols,
         c->dws.as<double>(), c->l_alpha.as<double>(), c->d_nu.as<double>(), c->rec.as<LineRec>(), c->win_lo.as<int>(),
-        c->win_hi.as<int>(), c->win_cls.as<uint8_t>(), tile, n_tiles, c->tile_geom.as<double>(),
-        c->farfield ? c->near_tiles.as<unsigned>() : nullptr, c->stats.as<unsigned long long>());
+        c->win_hi.as<int>(), c->win_cls.as<uint8_t>(), fg, c->stats.as<unsigned long long>());
     SD_TRY(sd_launch_check(c, "k_build_records"));
     k_cls_count<<<dim3(nchunks, D), CHUNK, 0, c->stream>>>(L, c->win_cls.as<uint8_t>(), nchunks, c->chunk_cnt.as<int>());
     SD_TRY(sd_launch_check(c, "k_cls_count"));
@@ -357,12 +386,9 @@ int sd_k2_prepare(sd_ctx *c) {
     k_cls_scatter<<<dim3(nchunks, D), CHUNK, 0, c->stream>>>(L, c->win_cls.as<uint8_t>(), nchunks, c->chunk_cnt.as<int>(),
                                                            c->cls_list.as<int>());
     SD_TRY(sd_launch_check(c, "k_cls_scatter"));
-    const int64_t nb = (L + 31) / 32;
     SD_TRY(sd_ensure(c, c->batch_win, sizeof(int4) * (size_t)D * nb));
-    SD_TRY(sd_ensure(c, c->batch_near, sizeof(unsigned) * (size_t)D * nb));
     k_batch_summaries<<<dim3((unsigned)((nb + 7) / 8), D), 256, 0, c->stream>>>(
-        L, D, c->cls_list.as<int>(), c->cls_off.as<int>(), c->win_lo.as<int>(), c->win_hi.as<int>(),
-        c->farfield ? c->near_tiles.as<unsigned>() : nullptr, c->batch_win.as<int4>(), c->batch_near.as<unsigned>());
+        L, D, c->cls_list.as<int>(), c->cls_off.as<int>(), c->win_lo.as<int>(), c->win_hi.as<int>(), fg, c->batch_win.as<int4>());
     SD_TRY(sd_launch_check(c, "k_batch_summaries"));
     c->records_ready = true;
     return SD_OK;

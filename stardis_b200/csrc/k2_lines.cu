@@ -69,12 +69,12 @@ struct LineArgs {
     const LineRec *rec;
     const int *win_lo, *win_hi;
     const uint8_t *win_cls;
-    const unsigned *near_tiles;  // nullptr: far field disabled
     const int *cls_list, *cls_off;
     const int4 *batch_win;       // per 32 class-list entries: {max lo, min hi, min lo, max hi}
-    const unsigned *batch_near;  //                            {min near-lo, max near-hi}
-    const double *tile_geom;
-    double *far_coef;            // (D, n_tiles_launch, SD_FAR_K + 1)
+    FarGeom fg;                  // tile hierarchy; fg.near[0] == nullptr: far field disabled
+    double *far_coef[SD_FAR_LEVELS];   // per level: (D, n_tiles_launch[k], SD_FAR_K + 1)
+    int far_tile0[SD_FAR_LEVELS];      // first global tile of this launch, per level
+    int far_ntl[SD_FAR_LEVELS];        // tiles of this launch, per level
     double *out;                 // (D, p1 - p0)
     unsigned long long *stats;
 };
@@ -113,7 +113,7 @@ __device__ __forceinline__ void class_range(const LineArgs &a, int d, int cls, i
         return;
     }
     const int lo = a.cls_off[d * (SD_NCLS + 1) + cls], hi = a.cls_off[d * (SD_NCLS + 1) + cls + 1];
-    if (cls == SD_NCLS - 1) {
+    if (cls >= SD_NCLS - 2) {  // classes 6 (unbounded half-width) and 7 (whole grid): every pair is a candidate
         ja = lo;
         jb = hi;
         return;
@@ -138,20 +138,33 @@ __device__ __forceinline__ bool pair_is_far(int lo, int hi, unsigned near, int64
 }
 
 // ------------------------------------------------------------------------------------------------------------------
-// Far-field coefficients of one (tile, depth): C_k = -W Im(w+^(k+1) + w-^(k+1)),  w = -h / (nu_c - p),
+// Far-field coefficients of one (level-LEV tile, depth): C_k = -W Im(w+^(k+1) + w-^(k+1)),  w = -h / (nu_c - p),
 // W = K dw / (2 sqrt(pi) h);  the contribution of the pair at pixel nu is  sum_k C_k ((nu - nu_c)/h)^k.
-__global__ void __launch_bounds__(THREADS) k_far_coeffs(LineArgs a, int tile_px, int count_stats) {
+// A pair is expanded at the HIGHEST level at which it is far: level LEV takes the pairs that are far for this tile but
+// not far for the parent tile of level LEV + 1.  Warps walk the class lists in batches of 32 (one pair per lane) and
+// skip batches whose summary shows that no pair can cover the tile or that every pair is already far for the parent.
+__global__ void __launch_bounds__(THREADS) k_far_coeffs(LineArgs a, int lev, int count_stats) {
     constexpr int K1 = SD_FAR_K + 1;
     __shared__ int s_ja[SD_NCLS], s_jb[SD_NCLS];
     __shared__ double s_red[WARPS][K1];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int d = blockIdx.y;
-    const int tile = a.tile0 + blockIdx.x;
+    const int tile_px = a.fg.tile[lev];
+    const int tile = a.far_tile0[lev] + blockIdx.x;
     const int64_t t0 = (int64_t)tile * tile_px;
     const int64_t t1 = (t0 + tile_px < a.N) ? t0 + tile_px : a.N;
-    const double nu_c = a.tile_geom[2 * tile], h = a.tile_geom[2 * tile + 1];
+    const double nu_c = a.fg.geom[lev][2 * tile], h = a.fg.geom[lev][2 * tile + 1];
+    const bool has_parent = lev + 1 < SD_FAR_LEVELS;
+    const int ptile = tile >> SD_FAR_SHIFT;
+    const int64_t pt0 = has_parent ? (int64_t)ptile * a.fg.tile[has_parent ? lev + 1 : lev] : 0;
+    const int64_t pt1 = has_parent ? ((pt0 + a.fg.tile[has_parent ? lev + 1 : lev] < a.N) ? pt0 + a.fg.tile[has_parent ? lev + 1 : lev] : a.N) : 0;
+    const unsigned *__restrict__ near_k = a.fg.near[lev];
+    const unsigned *__restrict__ near_p = has_parent ? a.fg.near[lev + 1] : nullptr;
     const size_t drow = (size_t)d * a.L;
     const int *list_d = a.cls_list + drow;
+    const int64_t nb_row = (a.L + 31) / 32;
+    const int4 *__restrict__ bwin = a.batch_win + (size_t)d * nb_row;
+    const unsigned *__restrict__ bnear_p = has_parent ? a.fg.batch_near[lev + 1] + (size_t)d * nb_row : nullptr;
     {
         int ja = 0, jb = 0;
         if (warp >= 1) class_range(a, d, warp, t0, t1, ja, jb);  // class 0 windows (<= 128 px) never cover a tile
@@ -165,29 +178,51 @@ __global__ void __launch_bounds__(THREADS) k_far_coeffs(LineArgs a, int tile_px,
     const double inv_h = 1.0 / h;
     for (int cls = 1; cls < SD_NCLS; cls++) {
         const int ja = s_ja[cls], jb = s_jb[cls];
-        for (int j = ja + tid; j < jb; j += THREADS) {
-            const size_t o = drow + list_d[j];
-            const int lo = a.win_lo[o], hi = a.win_hi[o];
-            if (!pair_is_far(lo, hi, a.near_tiles[o], t0, t1, tile)) continue;
-            const LineRec r = a.rec[o];
-            const double g = r.y * r.dw;                                       // Lorentz half-width in Hz
-            const double Wn = -r.K * r.dw * (0.5 * sdm::INV_SQRT_PI) * inv_h;  // -W
-            const double adw = 0.7071067811865476 * r.dw;
-            // w = -h / (D - i g) = -h (D + i g) / (D^2 + g^2) for the two poles
-            const double D1 = nu_c - (r.nu + adw), D2 = nu_c - (r.nu - adw);
-            const double i1 = -h * sdm::rcp_fast(fma(D1, D1, g * g)), i2 = -h * sdm::rcp_fast(fma(D2, D2, g * g));
-            const double w1r = D1 * i1, w1i = g * i1, w2r = D2 * i2, w2i = g * i2;
-            double p1r = w1r, p1i = w1i, p2r = w2r, p2i = w2i;
-#pragma unroll
-            for (int k = 0; k < K1; k++) {
-                C[k] = fma(Wn, p1i + p2i, C[k]);
-                if (k + 1 < K1) {
-                    double t;
-                    t = fma(p1r, w1r, -p1i * w1i); p1i = fma(p1r, w1i, p1i * w1r); p1r = t;
-                    t = fma(p2r, w2r, -p2i * w2i); p2i = fma(p2r, w2i, p2i * w2r); p2r = t;
+        if (jb <= ja) continue;
+        const int b_first = ja >> 5, b_last = (jb - 1) >> 5;
+        for (int b0 = b_first + 32 * warp; b0 <= b_last; b0 += 32 * WARPS) {
+            bool need = false;
+            const int bb = b0 + lane;
+            if (bb <= b_last) {
+                const int4 s4 = bwin[bb];
+                need = (s4.z <= t0) && (s4.w >= t1);  // some pair may cover the tile
+                if (need && has_parent) {
+                    const unsigned nr = bnear_p[bb];
+                    const bool all_parent_far = (s4.x <= pt0) && (s4.y >= pt1) &&
+                                                (ptile < (int)(nr & 0xffffu) || ptile >= (int)(nr >> 16));
+                    need = !all_parent_far;
                 }
             }
-            n_far++;
+            unsigned open_mask = __ballot_sync(0xffffffffu, need);
+            while (open_mask) {
+                const int bsel = __ffs(open_mask) - 1;
+                open_mask &= open_mask - 1;
+                const int j = ((b0 + bsel) << 5) + lane;
+                if (j < ja || j >= jb) continue;
+                const size_t o = drow + list_d[j];
+                const int lo = a.win_lo[o], hi = a.win_hi[o];
+                if (!pair_is_far(lo, hi, near_k[o], t0, t1, tile)) continue;
+                if (has_parent && pair_is_far(lo, hi, near_p[o], pt0, pt1, ptile)) continue;
+                const LineRec r = a.rec[o];
+                const double g = r.y * r.dw;                                       // Lorentz half-width in Hz
+                const double Wn = -r.K * r.dw * (0.5 * sdm::INV_SQRT_PI) * inv_h;  // -W
+                const double adw = 0.7071067811865476 * r.dw;
+                // w = -h / (D - i g) = -h (D + i g) / (D^2 + g^2) for the two poles
+                const double D1 = nu_c - (r.nu + adw), D2 = nu_c - (r.nu - adw);
+                const double i1 = -h * sdm::rcp_fast(fma(D1, D1, g * g)), i2 = -h * sdm::rcp_fast(fma(D2, D2, g * g));
+                const double w1r = D1 * i1, w1i = g * i1, w2r = D2 * i2, w2i = g * i2;
+                double p1r = w1r, p1i = w1i, p2r = w2r, p2i = w2i;
+#pragma unroll
+                for (int k = 0; k < K1; k++) {
+                    C[k] = fma(Wn, p1i + p2i, C[k]);
+                    if (k + 1 < K1) {
+                        double t;
+                        t = fma(p1r, w1r, -p1i * w1i); p1i = fma(p1r, w1i, p1i * w1r); p1r = t;
+                        t = fma(p2r, w2r, -p2i * w2i); p2i = fma(p2r, w2i, p2i * w2r); p2r = t;
+                    }
+                }
+                n_far++;
+            }
         }
     }
     // deterministic block reduction: lanes by shuffle, warps through shared memory in fixed order
@@ -202,7 +237,7 @@ __global__ void __launch_bounds__(THREADS) k_far_coeffs(LineArgs a, int tile_px,
         double v = 0.0;
 #pragma unroll
         for (int w = 0; w < WARPS; w++) v += s_red[w][tid];
-        a.far_coef[((size_t)d * gridDim.x + blockIdx.x) * K1 + tid] = v;
+        a.far_coef[lev][((size_t)d * gridDim.x + blockIdx.x) * K1 + tid] = v;
     }
     if (count_stats) {  // every far pair stands for one region-I evaluation per tile pixel inside the shard
         for (int o2 = 16; o2; o2 >>= 1) n_far += __shfl_xor_sync(0xffffffffu, n_far, o2);
@@ -231,7 +266,8 @@ __global__ void __launch_bounds__(THREADS, MINB) k_lines(LineArgs a) {
     const size_t drow = (size_t)d * L;
     const int *list_d = a.cls_list + drow;
     const double *__restrict__ nus = a.nus;
-    const bool use_far = a.near_tiles != nullptr;
+    const unsigned *__restrict__ near0 = a.fg.near[0];
+    const bool use_far = near0 != nullptr;
 
     // pixel frequencies and accumulators live in registers for the whole kernel
     double nu_i[P], acc[P];
@@ -278,7 +314,7 @@ __global__ void __launch_bounds__(THREADS, MINB) k_lines(LineArgs a) {
 
     const int64_t nb_row = (L + 31) / 32;
     const int4 *__restrict__ bwin = a.batch_win + (size_t)d * nb_row;
-    const unsigned *__restrict__ bnear = a.batch_near + (size_t)d * nb_row;
+    const unsigned *__restrict__ bnear = use_far ? a.fg.batch_near[0] + (size_t)d * nb_row : nullptr;
     for (int cls = 0; cls < SD_NCLS && warp_has_pixels; cls++) {
         const int ja = s_ja[cls], jb = s_jb[cls];
         if (jb <= ja) continue;
@@ -320,7 +356,7 @@ __global__ void __launch_bounds__(THREADS, MINB) k_lines(LineArgs a) {
                 lo = a.win_lo[o];
                 hi = a.win_hi[o];
                 pass = (lo < we) && (hi > ws) && (hi > lo) && (cls != 0 || a.win_cls[o] == 0);
-                if (pass && use_far && cls != 0) pass = !pair_is_far(lo, hi, a.near_tiles[o], t0, t1, tile);
+                if (pass && use_far && cls != 0) pass = !pair_is_far(lo, hi, near0[o], t0, t1, tile);
             }
             if (!__any_sync(0xffffffffu, pass)) continue;
             // ---- stage: hoist the per-(line, depth) constants; far-wing entries first, mixed ones from the back
@@ -389,26 +425,30 @@ __global__ void __launch_bounds__(THREADS, MINB) k_lines(LineArgs a) {
         }
     }
 
-    // ---- far field: polynomial of the tile (Horner in t = (nu - nu_c) / h) -----------------------------------
+    // ---- far field: one polynomial per hierarchy level (Horner in t = (nu - nu_c) / h of that level's tile) -------
     if (use_far && warp_has_pixels) {
         constexpr int K1 = SD_FAR_K + 1;
-        const double nu_c = a.tile_geom[2 * tile], inv_h = 1.0 / a.tile_geom[2 * tile + 1];
-        const double *__restrict__ C = a.far_coef + ((size_t)d * gridDim.x + blockIdx.x) * K1;
-        double tt[P], poly[P];
-        const double ck = C[K1 - 1];
 #pragma unroll
-        for (int p = 0; p < P; p++) {
-            tt[p] = (nu_i[p] - nu_c) * inv_h;
-            poly[p] = ck;
+        for (int lev = 0; lev < SD_FAR_LEVELS; lev++) {
+            const int tk = tile >> (SD_FAR_SHIFT * lev);
+            const double nu_c = a.fg.geom[lev][2 * tk], inv_h = 1.0 / a.fg.geom[lev][2 * tk + 1];
+            const double *__restrict__ C = a.far_coef[lev] + ((size_t)d * a.far_ntl[lev] + (tk - a.far_tile0[lev])) * K1;
+            double tt[P], poly[P];
+            const double ck = C[K1 - 1];
+#pragma unroll
+            for (int p = 0; p < P; p++) {
+                tt[p] = (nu_i[p] - nu_c) * inv_h;
+                poly[p] = ck;
+            }
+#pragma unroll
+            for (int k = K1 - 2; k >= 0; k--) {
+                const double c = C[k];
+#pragma unroll
+                for (int p = 0; p < P; p++) poly[p] = fma(poly[p], tt[p], c);
+            }
+#pragma unroll
+            for (int p = 0; p < P; p++) acc[p] += poly[p];
         }
-#pragma unroll
-        for (int k = K1 - 2; k >= 0; k--) {
-            const double c = C[k];
-#pragma unroll
-            for (int p = 0; p < P; p++) poly[p] = fma(poly[p], tt[p], c);
-        }
-#pragma unroll
-        for (int p = 0; p < P; p++) acc[p] += poly[p];
     }
 
 #pragma unroll
@@ -456,6 +496,10 @@ int sd_k2_choose_P(sd_ctx *c) {
     static const int force_p = env_int("SD_K2_P", 0);
     if (force_p == 1 || force_p == 2 || force_p == 4 || force_p == 8) return force_p;
     const int64_t W = c->W();
+    if (c->farfield && SD_FAR_LEVELS > 1) {
+        // small level-0 tiles keep the directly evaluated near field small; the hierarchy absorbs the rest
+        return (((W + 511) / 512) * c->D >= 4LL * c->sm_count) ? 2 : 1;
+    }
     if (((W + 2047) / 2048) * c->D >= 8LL * c->sm_count) return 8;
     if (((W + 1023) / 1024) * c->D >= 4LL * c->sm_count) return 4;
     if (((W + 511) / 512) * c->D >= 4LL * c->sm_count) return 2;
@@ -479,20 +523,25 @@ int sd_k2_lines(sd_ctx *c, int slot) {
     const int n_launch = (int)((c->p1 + tile - 1) / tile) - a.tile0;
     a.nus = c->nus.as<double>(); a.line_idx = c->line_idx.as<int>(); a.rec = c->rec.as<LineRec>();
     a.win_lo = c->win_lo.as<int>(); a.win_hi = c->win_hi.as<int>(); a.win_cls = c->win_cls.as<uint8_t>();
-    a.near_tiles = c->farfield ? c->near_tiles.as<unsigned>() : nullptr;
     a.cls_list = c->cls_list.as<int>(); a.cls_off = c->cls_off.as<int>();
-    a.tile_geom = c->tile_geom.as<double>();
     a.batch_win = c->batch_win.as<int4>();
-    a.batch_near = c->batch_near.as<unsigned>();
+    a.fg = c->far_geom;
     a.out = c->alpha_line[slot].as<double>();
     a.stats = c->stats.as<unsigned long long>();
-    dim3 grid((unsigned)n_launch, (unsigned)c->D);
     if (c->farfield) {
-        SD_TRY(sd_ensure(c, c->far_coef, sizeof(double) * c->D * n_launch * (SD_FAR_K + 1)));
-        a.far_coef = c->far_coef.as<double>();
-        k_far_coeffs<<<grid, THREADS, 0, c->stream>>>(a, tile, c->line_stats ? 1 : 0);
-        SD_TRY(sd_launch_check(c, "k_far_coeffs"));
+        for (int k = SD_FAR_LEVELS - 1; k >= 0; k--) {
+            const int tk = a.fg.tile[k];
+            a.far_tile0[k] = (int)(c->p0 / tk);
+            a.far_ntl[k] = (int)((c->p1 + tk - 1) / tk) - a.far_tile0[k];
+            SD_TRY(sd_ensure(c, c->far_coef[k], sizeof(double) * c->D * a.far_ntl[k] * (SD_FAR_K + 1)));
+            a.far_coef[k] = c->far_coef[k].as<double>();
+        }
+        for (int k = SD_FAR_LEVELS - 1; k >= 0; k--) {
+            k_far_coeffs<<<dim3((unsigned)a.far_ntl[k], (unsigned)c->D), THREADS, 0, c->stream>>>(a, k, c->line_stats ? 1 : 0);
+            SD_TRY(sd_launch_check(c, "k_far_coeffs"));
+        }
     }
+    dim3 grid((unsigned)n_launch, (unsigned)c->D);
     switch (P) {
         case 8: return launch<8>(c, a, grid, c->line_stats, rcp);
         case 4: return launch<4>(c, a, grid, c->line_stats, rcp);

@@ -26,6 +26,18 @@ constexpr int SD_MAX_SOURCES = 4 + SD_MAX_TABLES;
 // far-field (Taylor) expansion of region-I wings per pixel tile: order and convergence radius
 constexpr int SD_FAR_K = 20;            // polynomial degree (21 coefficients)
 constexpr double SD_FAR_RHO_INV = 4.0;  // a (line, depth) pair is expanded only if |nu_c - pole| >= 4 h
+constexpr int SD_FAR_LEVELS = 1;        // tile hierarchy: level k tiles hold 256 * P * 8^k pixels (1 = flat; the
+                                        // multi-level code path is kept for the sorted-edge-list scheme)
+constexpr int SD_FAR_SHIFT = 3;         // log2 of the branching factor
+
+// geometry of the far-field tile hierarchy, passed by value to the kernels
+struct FarGeom {
+    int tile[SD_FAR_LEVELS];            // pixels per tile
+    int n_tiles[SD_FAR_LEVELS];         // global number of tiles
+    const double *geom[SD_FAR_LEVELS];  // {centre frequency, half-width} per tile
+    unsigned *near[SD_FAR_LEVELS];      // per (depth, line): tiles [lo16, hi16) that are NOT far; nullptr = far field off
+    unsigned *batch_near[SD_FAR_LEVELS];
+};
 
 struct DevBuf {
     void *p = nullptr;
@@ -72,10 +84,11 @@ struct sd_ctx {
     DevBuf chunk_cnt;  // int32 [D * nchunks * NCLS]
     DevBuf stats;      // uint64 [8]
     DevBuf batch_win;  // int4 [D * ceil(L/32)]: {max lo, min hi, min lo, max hi} over 32 consecutive class-list entries
-    DevBuf batch_near; // uint32 [D * ceil(L/32)]: {min near-lo, max near-hi} of the same entries
-    DevBuf near_tiles; // uint32 [D*L]: tiles [lo16, hi16) around the line centre that must be evaluated directly
-    DevBuf tile_geom;  // double [2 * n_tiles_global]: centre frequency and half-width of every global pixel tile
-    DevBuf far_coef;   // double [D * n_tiles_shard * (SD_FAR_K + 1)]
+    DevBuf batch_near[SD_FAR_LEVELS];  // uint32 [D * ceil(L/32)]: {min near-lo, max near-hi} of the same entries
+    DevBuf near_tiles[SD_FAR_LEVELS];  // uint32 [D*L]: tiles [lo16, hi16) around the line centre that are not far
+    DevBuf tile_geom[SD_FAR_LEVELS];   // double [2 * n_tiles]: centre frequency and half-width of every global tile
+    DevBuf far_coef[SD_FAR_LEVELS];    // double [D * n_tiles_shard * (SD_FAR_K + 1)]
+    FarGeom far_geom{};
     int k2_P = 4;      // pixels per thread chosen for the current grid (tile = 256 * k2_P pixels)
     bool farfield = true;
     DevBuf alpha_line[2];
