@@ -58,6 +58,10 @@ class SyntheticPlasma:
         iidx = pd.MultiIndex.from_tuples(keys, names=["atomic_number", "ion_number"])
         self.ionization_data = pd.Series(np.array([ion_rows[k] for k in keys]) * EV_ERG, index=iidx, name="ionization_energy")
         self._pandas = None
+        # optional molecular line list (plasma/molecules.py attribute surface): DataFrames + molecule -> (Ion1, Ion2)
+        self.molecule_lines_from_linelist = None
+        self.molecule_alpha_line_from_linelist = None
+        self.molecule_ion_map = None
 
     # ---- pandas views with the reference's layout (built on demand; used by the golden generator and the
     #      slow-path adapter test, never by the fast path) ---------------------------------------------------
@@ -165,6 +169,26 @@ def synthetic_line_table(rng, n_lines, nu_min, nu_max, T, strong_fraction=0.005,
             kind == 2, rng.uniform(0.5, 3.0, L), rng.integers(150, 1500, L) + rng.uniform(0.15, 0.35, L))))
     return ColumnarLines(nu=nu, atomic_number=Z, ion_number=ion, ionization_energy=e_ion, level_energy_lower=e_lo,
                          level_energy_upper=e_up, A_ul=A_ul, alpha_line=alpha, stark=stark, waals=waals)
+
+
+def attach_synthetic_molecules(plasma, T, n_lines, nu_min, nu_max, seed=0):
+    """Seeded molecular line list with the attribute layout calc_molecular_alpha_line_at_nu reads
+    (opacities_solvers/base.py:444-484, broadening.py:808-819)."""
+    rng = np.random.default_rng(seed)
+    names = np.array(["CH", "CN", "OH", "TiO", "MgH"])
+    ion_map = pd.DataFrame({"Ion1": [6, 6, 8, 22, 12], "Ion2": [1, 7, 1, 8, 1]}, index=pd.Index(names, name="molecule"))
+    nu = rng.uniform(nu_min, nu_max, n_lines)  # deliberately unsorted: the driver sorts by nu like the reference
+    mol = names[rng.integers(0, len(names), n_lines)]
+    A_ul = 10.0 ** rng.uniform(5.0, 8.0, n_lines)
+    e_lo = rng.uniform(0.0, 2.0, n_lines) * EV_ERG
+    a0 = 10.0 ** rng.uniform(-2.0, 4.0, n_lines)
+    alpha = a0[:, None] * np.exp(-e_lo[:, None] / KB_CGS * (1.0 / T[None, :] - 1.0 / T.min()))
+    plasma.molecule_lines_from_linelist = pd.DataFrame({"nu": nu, "A_ul": A_ul, "molecule": mol})
+    a = pd.DataFrame(alpha)
+    a["nu"] = nu
+    plasma.molecule_alpha_line_from_linelist = a
+    plasma.molecule_ion_map = ion_map
+    return plasma
 
 
 def create_synthetic_plasma(atmosphere, n_lines, nu_min, nu_max, seed=0, strong_fraction=0.005, vald=False,

@@ -200,3 +200,106 @@ result_options:
     out_sh = run_stardis(str(cfg), lam, shard=(30, 77), add_config_dict={"result_options.return_radiation_field": True})
     np.testing.assert_array_equal(np.asarray(out_sh.stellar_radiation_field.F_nu), F[:, 30:77])
     default_context().synchronize()
+
+
+# ------------------------------------------------------------------ the other BASELINE.json configurations
+def _oracle_total_and_flux(oracle, w, cfg, p0, p1, table_paths, flags=15):
+    """CPU oracle on the pixel shard [p0, p1) of a workload: total opacity and F_nu."""
+    from stardis_b200 import units as u
+    from stardis_b200.constants import H_CGS
+
+    model, plasma, nus = w["model"], w["plasma"], w["nus"]
+    T = u.values_of(model.temperatures)
+    lt = plasma._line_table.with_masses(model.composition.nuclide_masses).in_range(nus.min(), nus.max())
+    lines = {k: getattr(lt, k) for k in ("nu", "atomic_number", "ion_number", "ionization_energy", "level_energy_upper",
+                                         "level_energy_lower", "A_ul", "mass")}
+    n_e, n_H = plasma.electron_densities.values, plasma.ion_number_density.loc[1, 0].values
+    gam, dws = oracle.calc_broadening(lines, T, n_e, n_H, float(u.cgs_values_of(model.microturbulence)), flags)
+    total = oracle.calc_alan_entries(len(T), nus, lt.nu, dws, gam, lt.alpha_line, p0=p0, p1=p1)
+    sub = nus[p0:p1]
+    nu_cut = (float(plasma.ionization_data.loc[(1, 1)]) - plasma.excitation_energy.values) / H_CGS
+    total = total + oracle.alpha_file(sub, T, table_paths["Hminus_bf"], "Hminus_bf", plasma.h_minus_density.values)
+    total = total + oracle.alpha_file(sub, T, table_paths["Hminus_ff"], "Hminus_ff", (plasma.ion_number_density.loc[1, 0] * plasma.electron_densities).values)
+    total = total + oracle.alpha_bf(sub, nu_cut, np.ones(len(nu_cut)), plasma.level_number_density.values)
+    total = total + oracle.alpha_ff(sub, [(1, n_e * plasma.ion_number_density.loc[1, 1].values)], T)
+    total = total + oracle.alpha_rayleigh(sub, n_H, plasma.ion_number_density.loc[2, 0].values, plasma.h2_density.values, ["H", "He", "H2"])
+    total = total + oracle.alpha_electron(n_e, p1 - p0)
+    th, wts = oracle.thetas_and_weights(cfg.no_of_thetas)
+    F, _ = oracle.raytrace(T, total, sub, th, wts, dist=model.geometry.dist_to_next_depth_point)
+    return total, F
+
+
+@pytest.mark.parametrize("name", ["solar_full", "astar", "coolgiant_ir"])
+def test_full_size_grids_vs_oracle_on_shards(name, table_paths, oracle):
+    """BASELINE.json configs 2-4 at their FULL grid sizes (N = 0.55-2.1 M) with a reduced synthetic line list: the GPU
+    computes the whole grid (far-field expansion active), the CPU oracle three 256-pixel shards of it (global windows)."""
+    from stardis_b200 import units as u
+    from stardis_b200.io.config import Configuration, validate_config
+    from stardis_b200.radiation_field import RadiationField
+    from stardis_b200.radiation_field.opacities.opacities_solvers import calc_alphas
+    from stardis_b200.radiation_field.radiation_field_solvers import raytrace
+    from stardis_b200.synthetic import make_workload
+
+    w = make_workload(name, seed=2, n_lines=2500, strong_fraction=0.01)
+    cfg = Configuration(validate_config(dict(
+        stardis_config_version=1.0, atom_data="synthetic:2500", input_model=dict(type="marcs", fname="x.mod"),
+        opacity=dict(file={"Hminus_bf": table_paths["Hminus_bf"], "Hminus_ff": table_paths["Hminus_ff"]}, bf={"H_I": {}},
+                     ff={"H_I": {}}, rayleigh=["H", "He", "H2"],
+                     line=dict(broadening=["radiation", "linear_stark", "quadratic_stark", "van_der_waals"])),
+        no_of_thetas=w["no_of_thetas"])))
+    model, plasma, nus = w["model"], w["plasma"], w["nus"]
+    N = len(nus)
+    srf = RadiationField(u.Quantity(nus, u.Hz), None, model, cfg.no_of_thetas)
+    calc_alphas(plasma, model, srf, cfg.opacity, store_components=False)
+    raytrace(model, srf)
+    total = np.asarray(srf.opacities.total_alphas)
+    F = np.asarray(srf.F_nu)
+    assert total.shape == (56, N) and np.isfinite(total).all() and np.isfinite(F).all() and (F[-1] > 0).all()
+    for p0 in (0, N // 2 - 77, N - 256):
+        ref_total, ref_F = _oracle_total_and_flux(oracle, w, cfg, p0, p0 + 256, table_paths)
+        np.testing.assert_allclose(total[:, p0:p0 + 256], ref_total, rtol=RTOL_ALPHA)
+        np.testing.assert_allclose(F[:, p0:p0 + 256], ref_F, rtol=RTOL_F, atol=1e-300)
+        np.testing.assert_allclose(total[:, p0:p0 + 256], ref_total, rtol=1e-10)  # in fact far tighter
+
+
+def test_molecular_lines_vs_oracle(table_paths, oracle):
+    """include_molecules: second line table, radiation-only gammas of shape (L,1), summed constituent masses
+    (opacities_solvers/base.py:444-484, broadening.py:735-821)."""
+    from oracle.make_golden_pipeline import CASES, case_inputs
+    from stardis_b200 import units as u
+    from stardis_b200.plasma.synthetic import attach_synthetic_molecules
+    from stardis_b200.radiation_field import RadiationField
+    from stardis_b200.radiation_field.opacities.opacities_solvers import calc_alphas, calc_molecular_alpha_line_at_nu
+
+    opacity = dict(CASES["bench"])
+    opacity["line"] = dict(opacity["line"], include_molecules=True)
+    cfg, model, plasma, nus = case_inputs("bench", opacity, table_paths)
+    T = u.values_of(model.temperatures)
+    attach_synthetic_molecules(plasma, T, 250, nus.min() * 0.9995, nus.max() * 1.0005, seed=4)
+    q = u.Quantity(nus, u.Hz)
+    srf = RadiationField(q, None, model, 3)
+    calc_alphas(plasma, model, srf, cfg.opacity)
+    od = srf.opacities.opacities_dict
+    assert list(od)[-3:] == ["molecule_alpha_line_at_nu", "molecule_alpha_line_at_nu_gammas", "molecule_alpha_line_at_nu_doppler_widths"]
+    ml = plasma.molecule_lines_from_linelist.sort_values("nu")
+    ml = ml[ml.nu.between(nus.min(), nus.max())]
+    al = plasma.molecule_alpha_line_from_linelist.sort_values("nu")
+    al = al[al.nu.between(nus.min(), nus.max())].drop(labels="nu", axis=1).to_numpy()
+    ions = plasma.molecule_ion_map.loc[ml.molecule]
+    masses = (model.composition.nuclide_masses.loc[ions.Ion1].values + model.composition.nuclide_masses.loc[ions.Ion2].values)
+    vmic = float(u.cgs_values_of(model.microturbulence))
+    dws = np.array([[oracle.calc_doppler_width(n, t, m, vmic) for t in T] for n, m in zip(ml.nu.values, masses)])
+    gam = ml.A_ul.values[:, None]
+    ref = oracle.calc_alan_entries(len(T), nus, ml.nu.values, dws, gam, al)
+    assert 0 < len(ml) < 250 and np.asarray(od["molecule_alpha_line_at_nu_gammas"]).shape == (len(ml), 1)
+    np.testing.assert_allclose(np.asarray(od["molecule_alpha_line_at_nu"]), ref, rtol=1e-10, atol=1e-300)
+    np.testing.assert_allclose(np.asarray(od["molecule_alpha_line_at_nu_doppler_widths"]), dws, rtol=1e-13)
+    # total = atomic case + molecular term; atomic gammas still retrievable after the molecular pass
+    g = golden("pipeline_golden.npz")
+    np.testing.assert_allclose(np.asarray(srf.opacities.total_alphas), g["bench__total"] + ref, rtol=1e-9)
+    np.testing.assert_allclose(np.asarray(od["alpha_line_at_nu_gammas"]), g["bench__alpha_line_at_nu_gammas"], rtol=1e-12)
+    a, gm, dw = calc_molecular_alpha_line_at_nu(plasma, model, q, cfg.opacity.line)
+    np.testing.assert_array_equal(a, np.asarray(od["molecule_alpha_line_at_nu"]))
+    cfg.opacity.line.broadening.remove("radiation")  # the reference's latent AttributeError (broadening.py:802-806)
+    with pytest.raises(AttributeError):
+        calc_molecular_alpha_line_at_nu(plasma, model, q, cfg.opacity.line)
