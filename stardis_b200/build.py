@@ -15,7 +15,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "_build")
 LIB = os.path.join(HERE, "libstardis_b200.so")
-SOURCES = ["ctx.cu", "k1_broadening.cu", "k2_lines.cu", "k3_continuum.cu", "k4_raytrace.cu"]
+SOURCES = ["ctx.cu", "k1_broadening.cu", "k2_lines.cu", "k2_sort.cu", "k3_continuum.cu", "k4_raytrace.cu"]
 HEADERS = ["sd_internal.h", "sd_math.cuh", os.path.join("..", "..", "include", "stardis_b200.h")]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC",

@@ -101,11 +101,9 @@ __device__ __forceinline__ bool tile_is_far(double nu_c, double h, double nu_l, 
     return (dist >= SD_FAR_RHO_INV * h + a_dw) && (dist >= core) && (dw > 0.0) && (y >= 0.0) && (y < 1e300) && (h > 0.0);
 }
 
-__device__ __forceinline__ int hw_class(long long hw, bool whole_grid) {
-    // class 0: hw <= 64; class k (1..5): hw <= 64 * 4^k; class 6: wider, with a window edge inside the grid; class 7:
-    // window == the whole grid.  Classes 6 and 7 are scanned unconditionally; class 7 is homogeneous (every pair covers
-    // every tile), which is what makes whole batches of it skippable by their summary.
-    if (whole_grid) return SD_NCLS - 1;
+__device__ __forceinline__ int hw_class(long long hw) {
+    // class 0: hw <= 64; class k (1..5): hw <= 64 * 4^k; class 6: everything wider (walked whole by the line kernel).
+    // Class 7 (SD_FC_CLASS) is reserved for the far-capable pairs of the far-field scheme.
     if (hw <= SD_CLS0_HW) return 0;
     int k = 1;
     long long lim = (long long)SD_CLS0_HW * 4;
@@ -125,6 +123,9 @@ __global__ void __launch_bounds__(256) k_build_records(int64_t L, int D, int64_t
     int64_t g = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     bool active = g < L * D;
     unsigned nonempty = 0, wide = 0, zero_dw = 0;
+    int rad_k[SD_FAR_LEVELS];
+#pragma unroll
+    for (int k = 0; k < SD_FAR_LEVELS; k++) rad_k[k] = 0;
     if (active) {
         int64_t l = g / D;
         int d = (int)(g - l * D);
@@ -138,7 +139,7 @@ __global__ void __launch_bounds__(256) k_build_records(int64_t L, int D, int64_t
         double broad = ((gam + dw) * a) / d_nu * 20.0;
         double forced = (broad > 10.0) ? broad : 10.0;
         long long hw = (forced < 4.0e18) ? (long long)forced : (long long)4e18;
-        int cls = hw_class(hw, lo == 0 && hi == N && hi > lo);
+        int cls = hw_class(hw);
         double y = (gam / sdm::SQRT_PI_PI) / dw;
         LineRec r;
         r.nu = line_nu[l];
@@ -155,28 +156,50 @@ __global__ void __launch_bounds__(256) k_build_records(int64_t L, int D, int64_t
         win_lo[o] = (int)lo;
         win_hi[o] = (int)hi;
         win_cls[o] = (uint8_t)cls;
-        // per hierarchy level: tiles [nl, nh) around the line centre that are NOT far (only windows that can cover a
-        // whole tile of that level matter; everything else keeps the default "never far")
+        // Far-capable pair: the window holds at least one level-0 tile and all parameters are finite.  Such pairs
+        // form class 7; per hierarchy level they get the interval of tiles [nl, nh) around the line centre that are
+        // NOT far, and their window edges go to the two edge-sort key arrays.
+        const bool fc = fg.near[0] && (hi - lo >= fg.tile[0]) && (r.thr == r.thr) && (a == a) && (fabs(a) < 1e300);
+        if (fc) {
+            cls = SD_FC_CLASS;
+            win_cls[o] = (uint8_t)cls;
+        }
+        if (fg.near[0]) {
 #pragma unroll
-        for (int k = 0; k < SD_FAR_LEVELS; k++) {
-            if (!fg.near[k]) continue;
-            unsigned nl = 0, nh = 0xffffu;
-            const int tile = fg.tile[k], n_tiles = fg.n_tiles[k];
-            if (hi - lo >= tile && r.thr == r.thr) {
-                const double *__restrict__ geom = fg.geom[k];
-                int tc = (int)(line_idx[l] / tile);
-                if (tc >= n_tiles) tc = n_tiles - 1;
-                int a_ = tc, b_ = tc + 1;
-                while (a_ > 0 && !tile_is_far(geom[2 * (a_ - 1)], geom[2 * (a_ - 1) + 1], r.nu, dw, y)) a_--;
-                while (b_ < n_tiles && !tile_is_far(geom[2 * b_], geom[2 * b_ + 1], r.nu, dw, y)) b_++;
-                nl = (unsigned)a_;
-                nh = (unsigned)b_;
+            for (int k = 0; k < SD_FAR_LEVELS; k++) {
+                unsigned nl = 0, nh = 0xffffu;
+                int rad = 0;
+                const int tile = fg.tile[k], n_tiles = fg.n_tiles[k];
+                if (fc && hi - lo >= tile) {
+                    const double *__restrict__ geom = fg.geom[k];
+                    int tc = (int)(line_idx[l] / tile);
+                    if (tc >= n_tiles) tc = n_tiles - 1;
+                    int a_ = tc, b_ = tc + 1;
+                    while (a_ > 0 && !tile_is_far(geom[2 * (a_ - 1)], geom[2 * (a_ - 1) + 1], r.nu, dw, y)) a_--;
+                    while (b_ < n_tiles && !tile_is_far(geom[2 * b_], geom[2 * b_ + 1], r.nu, dw, y)) b_++;
+                    nl = (unsigned)a_;
+                    nh = (unsigned)b_;
+                    rad = max(tc - a_, b_ - 1 - tc);
+                }
+                fg.near[k][o] = nl | (nh << 16);
+                rad_k[k] = rad;
             }
-            fg.near[k][o] = nl | (nh << 16);
+            const unsigned long long dkey = (unsigned long long)d << 32;
+            fg.lo_keys[o] = dkey | (unsigned long long)((fc && lo > 0) ? lo : 0x7fffffff);
+            fg.hi_keys[o] = dkey | (unsigned long long)((fc && hi < N) ? hi : 0x7fffffff);
+            fg.lo_l[o] = (int)l;
         }
         nonempty = hi > lo;
         wide = (hi > lo) && cls > 0;
         zero_dw = (hi > lo) && (dw == 0.0);
+    }
+    if (fg.near[0]) {
+#pragma unroll
+        for (int k = 0; k < SD_FAR_LEVELS; k++) {
+            int m = rad_k[k];
+            for (int o2 = 16; o2; o2 >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o2));
+            if ((threadIdx.x & 31) == 0 && m > 0) atomicMax(&fg.near_rad[k], m);
+        }
     }
     unsigned ne_w = __popc(__ballot_sync(0xffffffffu, nonempty));
     unsigned wd_w = __popc(__ballot_sync(0xffffffffu, wide));
@@ -261,54 +284,6 @@ __global__ void __launch_bounds__(CHUNK) k_cls_scatter(int64_t L, const uint8_t 
     }
 }
 
-// Bounds over every 32 consecutive entries of a depth's class list (row positions [32 b, 32 b + 32)): lets the line
-// kernel skip a whole batch that is entirely far-field for its tile (or does not overlap it) with one 20-byte read.
-__global__ void __launch_bounds__(256) k_batch_summaries(int64_t L, int D, const int *__restrict__ cls_list,
-                                                         const int *__restrict__ cls_off, const int *__restrict__ win_lo,
-                                                         const int *__restrict__ win_hi, FarGeom fg,
-                                                         int4 *__restrict__ batch_win) {
-    const int lane = threadIdx.x & 31;
-    const int64_t nb = (L + 31) / 32;
-    const int64_t b = blockIdx.x * (int64_t)(blockDim.x >> 5) + (threadIdx.x >> 5);
-    const int d = blockIdx.y;
-    if (b >= nb) return;
-    const int64_t pos = b * 32 + lane;
-    const int n_listed = cls_off[d * (SD_NCLS + 1) + SD_NCLS];
-    int mx_lo = -2147483647, mn_hi = 2147483647, mn_lo = 2147483647, mx_hi = -2147483647;
-    unsigned mn_nl[SD_FAR_LEVELS], mx_nh[SD_FAR_LEVELS];
-#pragma unroll
-    for (int k = 0; k < SD_FAR_LEVELS; k++) { mn_nl[k] = 0xffffu; mx_nh[k] = 0u; }
-    if (pos < n_listed) {
-        const size_t o = (size_t)d * L + cls_list[(size_t)d * L + pos];
-        const int lo = win_lo[o], hi = win_hi[o];
-        mx_lo = mn_lo = lo;
-        mn_hi = mx_hi = hi;
-#pragma unroll
-        for (int k = 0; k < SD_FAR_LEVELS; k++) {
-            const unsigned nr = fg.near[k] ? fg.near[k][o] : 0xffff0000u;
-            mn_nl[k] = nr & 0xffffu;
-            mx_nh[k] = nr >> 16;
-        }
-    }
-    for (int o2 = 16; o2; o2 >>= 1) {
-        mx_lo = max(mx_lo, __shfl_xor_sync(0xffffffffu, mx_lo, o2));
-        mn_hi = min(mn_hi, __shfl_xor_sync(0xffffffffu, mn_hi, o2));
-        mn_lo = min(mn_lo, __shfl_xor_sync(0xffffffffu, mn_lo, o2));
-        mx_hi = max(mx_hi, __shfl_xor_sync(0xffffffffu, mx_hi, o2));
-#pragma unroll
-        for (int k = 0; k < SD_FAR_LEVELS; k++) {
-            mn_nl[k] = min(mn_nl[k], __shfl_xor_sync(0xffffffffu, mn_nl[k], o2));
-            mx_nh[k] = max(mx_nh[k], __shfl_xor_sync(0xffffffffu, mx_nh[k], o2));
-        }
-    }
-    if (lane == 0) {
-        batch_win[(size_t)d * nb + b] = make_int4(mx_lo, mn_hi, mn_lo, mx_hi);
-#pragma unroll
-        for (int k = 0; k < SD_FAR_LEVELS; k++)
-            if (fg.batch_near[k]) fg.batch_near[k][(size_t)d * nb + b] = mn_nl[k] | (mx_nh[k] << 16);
-    }
-}
-
 }  // namespace
 
 int sd_k1_broadening(sd_ctx *c, uint32_t flags) {
@@ -348,8 +323,10 @@ int sd_k2_prepare(sd_ctx *c) {
                                                                           c->tile_geom[k].as<double>());
         SD_TRY(sd_launch_check(c, "k_tile_geometry"));
         fg.near[k] = nullptr;
-        fg.batch_near[k] = nullptr;
     }
+    fg.near_rad = nullptr;
+    fg.lo_keys = fg.hi_keys = nullptr;
+    fg.lo_l = fg.hi_l = nullptr;
     if (L == 0) {
         SD_CUDA(c, cudaMemsetAsync(c->cls_off.p, 0, sizeof(int) * D * (SD_NCLS + 1), c->stream));
         c->records_ready = true;
@@ -361,14 +338,25 @@ int sd_k2_prepare(sd_ctx *c) {
     SD_TRY(sd_ensure(c, c->win_hi, sizeof(int) * n));
     SD_TRY(sd_ensure(c, c->win_cls, n));
     SD_TRY(sd_ensure(c, c->cls_list, sizeof(int) * n));
-    const int64_t nb = (L + 31) / 32;
-    if (c->farfield)
+    if (c->farfield) {
         for (int k = 0; k < SD_FAR_LEVELS; k++) {
             SD_TRY(sd_ensure(c, c->near_tiles[k], sizeof(unsigned) * n));
-            SD_TRY(sd_ensure(c, c->batch_near[k], sizeof(unsigned) * (size_t)D * nb));
             fg.near[k] = c->near_tiles[k].as<unsigned>();
-            fg.batch_near[k] = c->batch_near[k].as<unsigned>();
         }
+        SD_TRY(sd_ensure(c, c->near_rad, sizeof(int) * SD_FAR_LEVELS));
+        SD_CUDA(c, cudaMemsetAsync(c->near_rad.p, 0, sizeof(int) * SD_FAR_LEVELS, c->stream));
+        fg.near_rad = c->near_rad.as<int>();
+        // unsorted keys go to the temporaries (window starts) / to edge_keys[1] (window ends, sorted second)
+        SD_TRY(sd_ensure(c, c->edge_tmp_keys, sizeof(unsigned long long) * n));
+        SD_TRY(sd_ensure(c, c->edge_tmp_l, sizeof(int) * n));
+        for (int w = 0; w < 2; w++) {
+            SD_TRY(sd_ensure(c, c->edge_keys[w], sizeof(unsigned long long) * n));
+            SD_TRY(sd_ensure(c, c->edge_l[w], sizeof(int) * n));
+        }
+        fg.lo_keys = c->edge_tmp_keys.as<unsigned long long>();
+        fg.hi_keys = c->edge_keys[0].as<unsigned long long>();  // staging; overwritten by the first sort's output later
+        fg.lo_l = c->edge_tmp_l.as<int>();
+    }
     int nchunks = (int)((L + CHUNK - 1) / CHUNK);
     SD_TRY(sd_ensure(c, c->chunk_cnt, sizeof(int) * (size_t)D * SD_NCLS * nchunks));
     k_line_idx<<<(unsigned)((L + 255) / 256), 256, 0, c->stream>>>(L, c->N, c->nus.as<double>(), c->l_nu.as<double>(),
@@ -386,10 +374,15 @@ int sd_k2_prepare(sd_ctx *c) {
     k_cls_scatter<<<dim3(nchunks, D), CHUNK, 0, c->stream>>>(L, c->win_cls.as<uint8_t>(), nchunks, c->chunk_cnt.as<int>(),
                                                            c->cls_list.as<int>());
     SD_TRY(sd_launch_check(c, "k_cls_scatter"));
-    SD_TRY(sd_ensure(c, c->batch_win, sizeof(int4) * (size_t)D * nb));
-    k_batch_summaries<<<dim3((unsigned)((nb + 7) / 8), D), 256, 0, c->stream>>>(
-        L, D, c->cls_list.as<int>(), c->cls_off.as<int>(), c->win_lo.as<int>(), c->win_hi.as<int>(), fg, c->batch_win.as<int4>());
-    SD_TRY(sd_launch_check(c, "k_batch_summaries"));
+    if (c->farfield) {
+        // window ends were staged in edge_keys[0]: sort them first (into edge_keys[1]/edge_l[1]), then the starts
+        SD_TRY(sd_sort_edges(c, 1, n));
+        SD_TRY(sd_sort_edges(c, 0, n));
+        fg.lo_keys = c->edge_keys[0].as<unsigned long long>();
+        fg.lo_l = c->edge_l[0].as<int>();
+        fg.hi_keys = c->edge_keys[1].as<unsigned long long>();
+        fg.hi_l = c->edge_l[1].as<int>();
+    }
     c->records_ready = true;
     return SD_OK;
 }

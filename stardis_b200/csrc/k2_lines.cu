@@ -70,7 +70,6 @@ struct LineArgs {
     const int *win_lo, *win_hi;
     const uint8_t *win_cls;
     const int *cls_list, *cls_off;
-    const int4 *batch_win;       // per 32 class-list entries: {max lo, min hi, min lo, max hi}
     FarGeom fg;                  // tile hierarchy; fg.near[0] == nullptr: far field disabled
     double *far_coef[SD_FAR_LEVELS];   // per level: (D, n_tiles_launch[k], SD_FAR_K + 1)
     int far_tile0[SD_FAR_LEVELS];      // first global tile of this launch, per level
@@ -125,6 +124,46 @@ __device__ __forceinline__ void class_range(const LineArgs &a, int d, int cls, i
     jb = warp_first_below(key, ja, hi, clamp_i32(t0 - H + 1));
 }
 
+// first j in [a, b) with keys[j] >= X (keys ascending), b if none.  Warp-cooperative 32-ary search.
+__device__ __forceinline__ int warp_lower_bound_u64(const unsigned long long *__restrict__ keys, int a, int b,
+                                                    unsigned long long X) {
+    const int lane = threadIdx.x & 31;
+    while (b > a) {
+        int n = b - a;
+        int step = (n + 31) >> 5;
+        long long pj = (long long)a + (long long)lane * step;
+        bool pred = (pj >= b) ? true : (keys[pj] >= X);
+        unsigned m = __ballot_sync(0xffffffffu, pred);
+        int f = m ? (__ffs(m) - 1) : 32;
+        if (f == 0) return a;
+        int na = a + (f - 1) * step + 1;
+        long long nb = (f < 32) ? (long long)a + (long long)f * step : (long long)b;
+        a = na;
+        b = (int)(nb < b ? nb : b);
+    }
+    return a;
+}
+
+// Far-capable pairs (class 7, sorted by window centre) whose centre lies within `rad` level-`lev` tiles of tile `t`.
+__device__ __forceinline__ void fc_near_range(const LineArgs &a, int d, int lev, int t, int &ja, int &jb) {
+    const int lo = a.cls_off[d * (SD_NCLS + 1) + SD_FC_CLASS], hi = a.cls_off[d * (SD_NCLS + 1) + SD_FC_CLASS + 1];
+    const int *list_d = a.cls_list + (size_t)d * a.L;
+    const int *line_idx = a.line_idx;
+    const long long T = a.fg.tile[lev], rad = a.fg.near_rad[lev];
+    auto key = [&](int j) { return line_idx[list_d[j]]; };
+    ja = warp_first_below(key, lo, hi, clamp_i32(((long long)t + rad + 1) * T));  // centre <  (t + rad + 1) T
+    jb = warp_first_below(key, ja, hi, clamp_i32(((long long)t - rad) * T));      // centre <  (t - rad) T
+}
+
+// Far-capable pairs of depth d with a window start (which = 0) or end (which = 1) strictly inside (t0, t1).
+__device__ __forceinline__ void fc_edge_range(const LineArgs &a, int d, int which, int64_t t0, int64_t t1, int &ja, int &jb) {
+    const unsigned long long *keys = (which ? a.fg.hi_keys : a.fg.lo_keys);
+    const unsigned long long dk = (unsigned long long)d << 32;
+    const int lo = (int)((size_t)d * a.L), hi = lo + (int)a.L;
+    ja = warp_lower_bound_u64(keys, lo, hi, dk | (unsigned long long)(t0 + 1));
+    jb = warp_lower_bound_u64(keys, ja, hi, dk | (unsigned long long)t1);
+}
+
 __device__ __noinline__ double exact_contribution(double nu_i, double nu_l, double dw, double y, double K) {
     double x = (nu_i - nu_l) / dw;  // voigt.py:148, IEEE division
     return sdm::humlicek_re(x, y) * K;
@@ -138,14 +177,17 @@ __device__ __forceinline__ bool pair_is_far(int lo, int hi, unsigned near, int64
 }
 
 // ------------------------------------------------------------------------------------------------------------------
-// Far-field coefficients of one (level-LEV tile, depth): C_k = -W Im(w+^(k+1) + w-^(k+1)),  w = -h / (nu_c - p),
+// Far-field coefficients of one (level-`lev` tile, depth): C_k = -W Im(w+^(k+1) + w-^(k+1)),  w = -h / (nu_c - p),
 // W = K dw / (2 sqrt(pi) h);  the contribution of the pair at pixel nu is  sum_k C_k ((nu - nu_c)/h)^k.
-// A pair is expanded at the HIGHEST level at which it is far: level LEV takes the pairs that are far for this tile but
-// not far for the parent tile of level LEV + 1.  Warps walk the class lists in batches of 32 (one pair per lane) and
-// skip batches whose summary shows that no pair can cover the tile or that every pair is already far for the parent.
+// A pair is expanded at the HIGHEST level at which it is far: level `lev` takes the far-capable pairs that cover this
+// tile, are far from it, and are NOT far for the parent tile of level lev + 1.  Those are found without scanning:
+//   (A) pairs that cover the parent but have it in their near interval: a contiguous range (by window centre) of the
+//       class-7 list around the parent;
+//   (B) pairs that do not cover the parent (a window edge lies strictly inside it): two ranges of the edge-sorted lists.
+// The top level has no parent and walks the whole class-7 list.
 __global__ void __launch_bounds__(THREADS) k_far_coeffs(LineArgs a, int lev, int count_stats) {
     constexpr int K1 = SD_FAR_K + 1;
-    __shared__ int s_ja[SD_NCLS], s_jb[SD_NCLS];
+    __shared__ int s_ja[3], s_jb[3];
     __shared__ double s_red[WARPS][K1];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int d = blockIdx.y;
@@ -155,19 +197,24 @@ __global__ void __launch_bounds__(THREADS) k_far_coeffs(LineArgs a, int lev, int
     const int64_t t1 = (t0 + tile_px < a.N) ? t0 + tile_px : a.N;
     const double nu_c = a.fg.geom[lev][2 * tile], h = a.fg.geom[lev][2 * tile + 1];
     const bool has_parent = lev + 1 < SD_FAR_LEVELS;
+    const int plev = has_parent ? lev + 1 : lev;
     const int ptile = tile >> SD_FAR_SHIFT;
-    const int64_t pt0 = has_parent ? (int64_t)ptile * a.fg.tile[has_parent ? lev + 1 : lev] : 0;
-    const int64_t pt1 = has_parent ? ((pt0 + a.fg.tile[has_parent ? lev + 1 : lev] < a.N) ? pt0 + a.fg.tile[has_parent ? lev + 1 : lev] : a.N) : 0;
+    const int64_t pt0 = (int64_t)ptile * a.fg.tile[plev];
+    const int64_t pt1 = (pt0 + a.fg.tile[plev] < a.N) ? pt0 + a.fg.tile[plev] : a.N;
     const unsigned *__restrict__ near_k = a.fg.near[lev];
-    const unsigned *__restrict__ near_p = has_parent ? a.fg.near[lev + 1] : nullptr;
+    const unsigned *__restrict__ near_p = a.fg.near[plev];
     const size_t drow = (size_t)d * a.L;
     const int *list_d = a.cls_list + drow;
-    const int64_t nb_row = (a.L + 31) / 32;
-    const int4 *__restrict__ bwin = a.batch_win + (size_t)d * nb_row;
-    const unsigned *__restrict__ bnear_p = has_parent ? a.fg.batch_near[lev + 1] + (size_t)d * nb_row : nullptr;
-    {
-        int ja = 0, jb = 0;
-        if (warp >= 1) class_range(a, d, warp, t0, t1, ja, jb);  // class 0 windows (<= 128 px) never cover a tile
+    if (warp < 3) {
+        int ja, jb;
+        if (!has_parent) {
+            ja = a.cls_off[d * (SD_NCLS + 1) + SD_FC_CLASS];
+            jb = (warp == 0) ? a.cls_off[d * (SD_NCLS + 1) + SD_FC_CLASS + 1] : ja;
+        } else if (warp == 0) {
+            fc_near_range(a, d, plev, ptile, ja, jb);
+        } else {
+            fc_edge_range(a, d, warp - 1, pt0, pt1, ja, jb);
+        }
         if (lane == 0) { s_ja[warp] = ja; s_jb[warp] = jb; }
     }
     __syncthreads();
@@ -176,53 +223,41 @@ __global__ void __launch_bounds__(THREADS) k_far_coeffs(LineArgs a, int lev, int
     for (int k = 0; k < K1; k++) C[k] = 0.0;
     unsigned long long n_far = 0;
     const double inv_h = 1.0 / h;
-    for (int cls = 1; cls < SD_NCLS; cls++) {
-        const int ja = s_ja[cls], jb = s_jb[cls];
-        if (jb <= ja) continue;
-        const int b_first = ja >> 5, b_last = (jb - 1) >> 5;
-        for (int b0 = b_first + 32 * warp; b0 <= b_last; b0 += 32 * WARPS) {
-            bool need = false;
-            const int bb = b0 + lane;
-            if (bb <= b_last) {
-                const int4 s4 = bwin[bb];
-                need = (s4.z <= t0) && (s4.w >= t1);  // some pair may cover the tile
-                if (need && has_parent) {
-                    const unsigned nr = bnear_p[bb];
-                    const bool all_parent_far = (s4.x <= pt0) && (s4.y >= pt1) &&
-                                                (ptile < (int)(nr & 0xffffu) || ptile >= (int)(nr >> 16));
-                    need = !all_parent_far;
+    for (int src = 0; src < 3; src++) {
+        const int ja = s_ja[src], jb = s_jb[src];
+        for (int j = ja + tid; j < jb; j += THREADS) {
+            const int l = (src == 0) ? list_d[j] : (src == 1 ? a.fg.lo_l[j] : a.fg.hi_l[j]);
+            const size_t o = drow + l;
+            const int lo = a.win_lo[o], hi = a.win_hi[o];
+            if (!pair_is_far(lo, hi, near_k[o], t0, t1, tile)) continue;  // must cover this tile and be far from it
+            if (has_parent) {
+                const bool covers_parent = (lo <= pt0) && (hi >= pt1);
+                if (src == 0) {  // (A): covers the parent, parent inside the near interval
+                    if (!covers_parent || pair_is_far(lo, hi, near_p[o], pt0, pt1, ptile)) continue;
+                } else {         // (B): an edge strictly inside the parent; a pair with both edges inside comes via its start
+                    if (covers_parent) continue;
+                    if (src == 2 && lo > pt0 && lo < pt1) continue;
                 }
             }
-            unsigned open_mask = __ballot_sync(0xffffffffu, need);
-            while (open_mask) {
-                const int bsel = __ffs(open_mask) - 1;
-                open_mask &= open_mask - 1;
-                const int j = ((b0 + bsel) << 5) + lane;
-                if (j < ja || j >= jb) continue;
-                const size_t o = drow + list_d[j];
-                const int lo = a.win_lo[o], hi = a.win_hi[o];
-                if (!pair_is_far(lo, hi, near_k[o], t0, t1, tile)) continue;
-                if (has_parent && pair_is_far(lo, hi, near_p[o], pt0, pt1, ptile)) continue;
-                const LineRec r = a.rec[o];
-                const double g = r.y * r.dw;                                       // Lorentz half-width in Hz
-                const double Wn = -r.K * r.dw * (0.5 * sdm::INV_SQRT_PI) * inv_h;  // -W
-                const double adw = 0.7071067811865476 * r.dw;
-                // w = -h / (D - i g) = -h (D + i g) / (D^2 + g^2) for the two poles
-                const double D1 = nu_c - (r.nu + adw), D2 = nu_c - (r.nu - adw);
-                const double i1 = -h * sdm::rcp_fast(fma(D1, D1, g * g)), i2 = -h * sdm::rcp_fast(fma(D2, D2, g * g));
-                const double w1r = D1 * i1, w1i = g * i1, w2r = D2 * i2, w2i = g * i2;
-                double p1r = w1r, p1i = w1i, p2r = w2r, p2i = w2i;
+            const LineRec r = a.rec[o];
+            const double g = r.y * r.dw;                                       // Lorentz half-width in Hz
+            const double Wn = -r.K * r.dw * (0.5 * sdm::INV_SQRT_PI) * inv_h;  // -W
+            const double adw = 0.7071067811865476 * r.dw;
+            // w = -h / (D - i g) = -h (D + i g) / (D^2 + g^2) for the two poles
+            const double D1 = nu_c - (r.nu + adw), D2 = nu_c - (r.nu - adw);
+            const double i1 = -h * sdm::rcp_fast(fma(D1, D1, g * g)), i2 = -h * sdm::rcp_fast(fma(D2, D2, g * g));
+            const double w1r = D1 * i1, w1i = g * i1, w2r = D2 * i2, w2i = g * i2;
+            double p1r = w1r, p1i = w1i, p2r = w2r, p2i = w2i;
 #pragma unroll
-                for (int k = 0; k < K1; k++) {
-                    C[k] = fma(Wn, p1i + p2i, C[k]);
-                    if (k + 1 < K1) {
-                        double t;
-                        t = fma(p1r, w1r, -p1i * w1i); p1i = fma(p1r, w1i, p1i * w1r); p1r = t;
-                        t = fma(p2r, w2r, -p2i * w2i); p2i = fma(p2r, w2i, p2i * w2r); p2r = t;
-                    }
+            for (int k = 0; k < K1; k++) {
+                C[k] = fma(Wn, p1i + p2i, C[k]);
+                if (k + 1 < K1) {
+                    double t;
+                    t = fma(p1r, w1r, -p1i * w1i); p1i = fma(p1r, w1i, p1i * w1r); p1r = t;
+                    t = fma(p2r, w2r, -p2i * w2i); p2i = fma(p2r, w2i, p2i * w2r); p2r = t;
                 }
-                n_far++;
             }
+            n_far++;
         }
     }
     // deterministic block reduction: lanes by shuffle, warps through shared memory in fixed order
@@ -252,7 +287,8 @@ __global__ void __launch_bounds__(THREADS, MINB) k_lines(LineArgs a) {
     constexpr int TILE = THREADS * P;
     constexpr int SPAN = 32 * P;
     __shared__ WEntry s_ent[WARPS][32];  // every warp streams its own batches: no CTA barrier in the main loop
-    __shared__ int s_ja[SD_NCLS], s_jb[SD_NCLS];
+    constexpr int NSRC = SD_NCLS + 2;    // classes 0..6, far-capable pairs near the tile, their window starts / ends
+    __shared__ int s_ja[NSRC], s_jb[NSRC];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const unsigned lt_mask = (1u << lane) - 1u;
@@ -281,10 +317,17 @@ __global__ void __launch_bounds__(THREADS, MINB) k_lines(LineArgs a) {
     const double nu_first = nus[ws < N ? ws : N - 1];
     const double nu_last = nus[(we - 1 >= ws && we - 1 < N) ? we - 1 : (ws < N ? ws : N - 1)];
 
-    {   // candidate ranges of all classes, one warp per class
-        int ja, jb;
-        class_range(a, d, warp, t0, t1, ja, jb);
+    {   // candidate ranges of all sources, one warp per source (warps 0 and 1 take a second one)
+        int ja = 0, jb = 0;
+        if (warp < SD_FC_CLASS) class_range(a, d, warp, t0, t1, ja, jb);
+        else if (use_far) fc_near_range(a, d, 0, tile, ja, jb);
+        else { ja = a.cls_off[d * (SD_NCLS + 1) + SD_FC_CLASS]; jb = ja; }
         if (lane == 0) { s_ja[warp] = ja; s_jb[warp] = jb; }
+        if (warp < 2) {
+            ja = jb = 0;
+            if (use_far) fc_edge_range(a, d, warp, t0, t1, ja, jb);
+            if (lane == 0) { s_ja[SD_NCLS + warp] = ja; s_jb[SD_NCLS + warp] = jb; }
+        }
     }
     __syncthreads();
 
@@ -312,51 +355,29 @@ __global__ void __launch_bounds__(THREADS, MINB) k_lines(LineArgs a) {
         }
     };
 
-    const int64_t nb_row = (L + 31) / 32;
-    const int4 *__restrict__ bwin = a.batch_win + (size_t)d * nb_row;
-    const unsigned *__restrict__ bnear = use_far ? a.fg.batch_near[0] + (size_t)d * nb_row : nullptr;
-    for (int cls = 0; cls < SD_NCLS && warp_has_pixels; cls++) {
-        const int ja = s_ja[cls], jb = s_jb[cls];
-        if (jb <= ja) continue;
-        // Class 0 walks the nu-sorted line list directly.  Classes >= 1 walk the class list in batches of 32 row
-        // positions; 32 batch summaries are checked at a time (one per lane) and only batches that overlap this
-        // warp's span and are not entirely far-field for the tile are opened.
-        const int b_first = (cls == 0) ? 0 : ja >> 5, b_last = (cls == 0) ? (jb - ja - 1) >> 5 : (jb - 1) >> 5;
-        for (int b0 = b_first; b0 <= b_last; b0 += 32) {
-            unsigned open_mask = 0xffffffffu;
-            if (cls != 0) {
-                bool need = false;
-                const int bb = b0 + lane;
-                if (bb <= b_last) {
-                    const int4 s4 = bwin[bb];
-                    need = (s4.z < we) && (s4.w > ws);  // some window may overlap the span
-                    if (need && use_far) {
-                        const unsigned nr = bnear[bb];
-                        const bool all_far = (s4.x <= t0) && (s4.y >= t1) &&
-                                             (tile < (int)(nr & 0xffffu) || tile >= (int)(nr >> 16));
-                        need = !all_far;
-                    }
-                }
-                open_mask = __ballot_sync(0xffffffffu, need);
-            } else if (b0 + 32 > b_last + 1) {
-                open_mask = (b_last - b0 + 1 >= 32) ? 0xffffffffu : ((1u << (b_last - b0 + 1)) - 1u);
-            }
-            while (open_mask) {
-                const int bsel = __ffs(open_mask) - 1;
-                open_mask &= open_mask - 1;
-                const int base = (cls == 0) ? ja + ((b0 + bsel) << 5) : (b0 + bsel) << 5;
+    for (int src = 0; src < NSRC && warp_has_pixels; src++) {
+        const int ja = s_ja[src], jb = s_jb[src];
+        for (int base = ja; base < jb; base += 32) {
+            {
             // ---- test the 32 candidates of this batch against THIS WARP's span ------------------------
             const int j = base + lane;
             bool pass = false;
             size_t o = 0;
             int lo = 0, hi = 0;
-            if (j < jb && j >= ja) {
-                int l = (cls == 0) ? j : list_d[j];
+            if (j < jb) {
+                int l;
+                if (src == 0) l = j;                                   // class 0: the nu-sorted line list itself
+                else if (src <= SD_FC_CLASS) l = list_d[j];            // class lists (7 = far-capable pairs near the tile)
+                else l = (src == SD_NCLS) ? a.fg.lo_l[j] : a.fg.hi_l[j];  // far-capable pairs with an edge inside the tile
                 o = drow + l;
                 lo = a.win_lo[o];
                 hi = a.win_hi[o];
-                pass = (lo < we) && (hi > ws) && (hi > lo) && (cls != 0 || a.win_cls[o] == 0);
-                if (pass && use_far && cls != 0) pass = !pair_is_far(lo, hi, near0[o], t0, t1, tile);
+                pass = (lo < we) && (hi > ws) && (hi > lo);
+                if (src == 0) pass = pass && (a.win_cls[o] == 0);
+                else if (src == SD_FC_CLASS) {
+                    // covering pairs only (the others come through the edge lists); skip those expanded by k_far_coeffs
+                    pass = pass && (lo <= t0) && (hi >= t1) && !pair_is_far(lo, hi, near0[o], t0, t1, tile);
+                }
             }
             if (!__any_sync(0xffffffffu, pass)) continue;
             // ---- stage: hoist the per-(line, depth) constants; far-wing entries first, mixed ones from the back
@@ -421,7 +442,7 @@ __global__ void __launch_bounds__(THREADS, MINB) k_lines(LineArgs a) {
                 }
             }
             __syncwarp();
-            }  // open batches
+            }
         }
     }
 
@@ -524,7 +545,6 @@ int sd_k2_lines(sd_ctx *c, int slot) {
     a.nus = c->nus.as<double>(); a.line_idx = c->line_idx.as<int>(); a.rec = c->rec.as<LineRec>();
     a.win_lo = c->win_lo.as<int>(); a.win_hi = c->win_hi.as<int>(); a.win_cls = c->win_cls.as<uint8_t>();
     a.cls_list = c->cls_list.as<int>(); a.cls_off = c->cls_off.as<int>();
-    a.batch_win = c->batch_win.as<int4>();
     a.fg = c->far_geom;
     a.out = c->alpha_line[slot].as<double>();
     a.stats = c->stats.as<unsigned long long>();

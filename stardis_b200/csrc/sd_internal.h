@@ -26,17 +26,21 @@ constexpr int SD_MAX_SOURCES = 4 + SD_MAX_TABLES;
 // far-field (Taylor) expansion of region-I wings per pixel tile: order and convergence radius
 constexpr int SD_FAR_K = 20;            // polynomial degree (21 coefficients)
 constexpr double SD_FAR_RHO_INV = 4.0;  // a (line, depth) pair is expanded only if |nu_c - pole| >= 4 h
-constexpr int SD_FAR_LEVELS = 1;        // tile hierarchy: level k tiles hold 256 * P * 8^k pixels (1 = flat; the
-                                        // multi-level code path is kept for the sorted-edge-list scheme)
+constexpr int SD_FAR_LEVELS = 3;        // tile hierarchy: level k tiles hold 256 * P * 8^k pixels
 constexpr int SD_FAR_SHIFT = 3;         // log2 of the branching factor
+constexpr int SD_FC_CLASS = SD_NCLS - 1;  // class of the "far-capable" pairs (window >= one level-0 tile, finite parameters)
 
-// geometry of the far-field tile hierarchy, passed by value to the kernels
+// geometry of the far-field tile hierarchy and the per-pair tables that drive it, passed by value to the kernels
 struct FarGeom {
     int tile[SD_FAR_LEVELS];            // pixels per tile
     int n_tiles[SD_FAR_LEVELS];         // global number of tiles
     const double *geom[SD_FAR_LEVELS];  // {centre frequency, half-width} per tile
     unsigned *near[SD_FAR_LEVELS];      // per (depth, line): tiles [lo16, hi16) that are NOT far; nullptr = far field off
-    unsigned *batch_near[SD_FAR_LEVELS];
+    int *near_rad;                      // [SD_FAR_LEVELS] largest half-extent (in tiles) of any near interval
+    // far-capable pairs sorted by the position of their window edges (per depth: entries [d L, (d+1) L)); keys are
+    // (depth << 32 | pixel), pixel = 0x7fffffff when the pair has no such edge inside the grid
+    unsigned long long *lo_keys, *hi_keys;
+    int *lo_l, *hi_l;
 };
 
 struct DevBuf {
@@ -83,8 +87,9 @@ struct sd_ctx {
     DevBuf cls_off;    // int32 [D*(NCLS+1)] offsets into cls_list row d (class 0 is not listed)
     DevBuf chunk_cnt;  // int32 [D * nchunks * NCLS]
     DevBuf stats;      // uint64 [8]
-    DevBuf batch_win;  // int4 [D * ceil(L/32)]: {max lo, min hi, min lo, max hi} over 32 consecutive class-list entries
-    DevBuf batch_near[SD_FAR_LEVELS];  // uint32 [D * ceil(L/32)]: {min near-lo, max near-hi} of the same entries
+    DevBuf near_rad;                   // int [SD_FAR_LEVELS]
+    DevBuf edge_keys[2], edge_l[2];    // sorted (depth, edge pixel) keys / line indices: [0] window starts, [1] window ends
+    DevBuf edge_tmp_keys, edge_tmp_l, edge_sort_tmp;
     DevBuf near_tiles[SD_FAR_LEVELS];  // uint32 [D*L]: tiles [lo16, hi16) around the line centre that are not far
     DevBuf tile_geom[SD_FAR_LEVELS];   // double [2 * n_tiles]: centre frequency and half-width of every global tile
     DevBuf far_coef[SD_FAR_LEVELS];    // double [D * n_tiles_shard * (SD_FAR_K + 1)]
@@ -140,6 +145,7 @@ int sd_k1_broadening(sd_ctx *c, uint32_t flags);
 int sd_k2_prepare(sd_ctx *c);
 int sd_k2_lines(sd_ctx *c, int slot);
 int sd_k2_choose_P(sd_ctx *c);
+int sd_sort_edges(sd_ctx *c, int which, int64_t n);  // k2_sort.cu (CUB radix sort of the edge keys)
 int sd_k3_continuum(sd_ctx *c, const sd_continuum *desc, uint32_t store_mask);
 int sd_k4_raytrace(sd_ctx *c, int n_theta, const double *ray_ds, const double *weights, int inward, double scale,
                    int track);
