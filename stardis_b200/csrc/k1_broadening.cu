@@ -314,7 +314,7 @@ int sd_k2_prepare(sd_ctx *c) {
     c->k2_P = sd_k2_choose_P(c);
     FarGeom &fg = c->far_geom;
     for (int k = 0; k < SD_FAR_LEVELS; k++) {
-        fg.tile[k] = (256 * c->k2_P) << (SD_FAR_SHIFT * k);
+        fg.tile[k] = (32 * c->k2_NW * c->k2_P) << (SD_FAR_SHIFT * k);
         fg.n_tiles[k] = (int)((c->N + fg.tile[k] - 1) / fg.tile[k]);
         SD_CHECK(c, fg.n_tiles[k] < 65535, SD_ERR_ARG, "grid too long for 16-bit tile indices");
         SD_TRY(sd_ensure(c, c->tile_geom[k], sizeof(double) * 2 * fg.n_tiles[k]));

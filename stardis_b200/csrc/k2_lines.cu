@@ -41,7 +41,6 @@ namespace {
 
 constexpr int THREADS = 256;
 constexpr int WARPS = THREADS / 32;
-static_assert(WARPS == SD_NCLS, "one warp per half-width class in the range search");
 
 struct __align__(16) WEntry {
     // far-wing path (48 B)
@@ -282,11 +281,11 @@ __global__ void __launch_bounds__(THREADS) k_far_coeffs(LineArgs a, int lev, int
 }
 
 // ------------------------------------------------------------------------------------------------------------------
-template <int P, bool STATS, int RCP, int MINB>
-__global__ void __launch_bounds__(THREADS, MINB) k_lines(LineArgs a) {
-    constexpr int TILE = THREADS * P;
+template <int P, int NW, bool STATS, int RCP, int MINB>
+__global__ void __launch_bounds__(32 * NW, MINB) k_lines(LineArgs a) {
+    constexpr int TILE = 32 * NW * P;
     constexpr int SPAN = 32 * P;
-    __shared__ WEntry s_ent[WARPS][32];  // every warp streams its own batches: no CTA barrier in the main loop
+    __shared__ WEntry s_ent[NW][32];  // every warp streams its own batches: no CTA barrier in the main loop
     constexpr int NSRC = SD_NCLS + 2;    // classes 0..6, far-capable pairs near the tile, their window starts / ends
     __shared__ int s_ja[NSRC], s_jb[NSRC];
 
@@ -317,17 +316,14 @@ __global__ void __launch_bounds__(THREADS, MINB) k_lines(LineArgs a) {
     const double nu_first = nus[ws < N ? ws : N - 1];
     const double nu_last = nus[(we - 1 >= ws && we - 1 < N) ? we - 1 : (ws < N ? ws : N - 1)];
 
-    {   // candidate ranges of all sources, one warp per source (warps 0 and 1 take a second one)
+    // candidate ranges of all sources, distributed over the warps of the CTA
+    for (int src = warp; src < NSRC; src += NW) {
         int ja = 0, jb = 0;
-        if (warp < SD_FC_CLASS) class_range(a, d, warp, t0, t1, ja, jb);
-        else if (use_far) fc_near_range(a, d, 0, tile, ja, jb);
-        else { ja = a.cls_off[d * (SD_NCLS + 1) + SD_FC_CLASS]; jb = ja; }
-        if (lane == 0) { s_ja[warp] = ja; s_jb[warp] = jb; }
-        if (warp < 2) {
-            ja = jb = 0;
-            if (use_far) fc_edge_range(a, d, warp, t0, t1, ja, jb);
-            if (lane == 0) { s_ja[SD_NCLS + warp] = ja; s_jb[SD_NCLS + warp] = jb; }
-        }
+        if (src < SD_FC_CLASS) class_range(a, d, src, t0, t1, ja, jb);
+        else if (src == SD_FC_CLASS) {
+            if (use_far) fc_near_range(a, d, 0, tile, ja, jb);
+        } else if (use_far) fc_edge_range(a, d, src - SD_NCLS, t0, t1, ja, jb);
+        if (lane == 0) { s_ja[src] = ja; s_jb[src] = jb; }
     }
     __syncthreads();
 
@@ -498,14 +494,13 @@ int env_int(const char *name, int dflt) {
     return v ? atoi(v) : dflt;
 }
 
-template <int P>
+template <int P, int NW>
 int launch(sd_ctx *c, const LineArgs &a, dim3 grid, bool stats, int rcp) {
-    static const int minb = env_int("SD_K2_MINB", 2);
+    constexpr int MINB = (NW == 8) ? 2 : (NW == 2 ? 8 : 16);  // <= 128 registers per thread in every configuration
     // the counting instantiation uses the production arithmetic (Newton reciprocal) so that both are bitwise equal
-    if (stats) k_lines<P, true, 2, 2><<<grid, THREADS, 0, c->stream>>>(a);
-    else if (rcp == 3) k_lines<P, false, 3, 2><<<grid, THREADS, 0, c->stream>>>(a);
-    else if (minb == 3) k_lines<P, false, 2, 3><<<grid, THREADS, 0, c->stream>>>(a);
-    else k_lines<P, false, 2, 2><<<grid, THREADS, 0, c->stream>>>(a);
+    if (stats) k_lines<P, NW, true, 2, MINB><<<grid, 32 * NW, 0, c->stream>>>(a);
+    else if (rcp == 3) k_lines<P, NW, false, 3, MINB><<<grid, 32 * NW, 0, c->stream>>>(a);
+    else k_lines<P, NW, false, 2, MINB><<<grid, 32 * NW, 0, c->stream>>>(a);
     return sd_launch_check(c, "k_lines");
 }
 
@@ -515,16 +510,23 @@ int launch(sd_ctx *c, const LineArgs &a, dim3 grid, bool stats, int rcp) {
 // entries as possible.  SD_K2_P overrides the choice (tuning experiments).
 int sd_k2_choose_P(sd_ctx *c) {
     static const int force_p = env_int("SD_K2_P", 0);
-    if (force_p == 1 || force_p == 2 || force_p == 4 || force_p == 8) return force_p;
+    static const int force_nw = env_int("SD_K2_NW", 0);
     const int64_t W = c->W();
-    if (c->farfield && SD_FAR_LEVELS > 1) {
-        // small level-0 tiles keep the directly evaluated near field small; the hierarchy absorbs the rest
-        return (((W + 511) / 512) * c->D >= 4LL * c->sm_count) ? 2 : 1;
-    }
-    if (((W + 2047) / 2048) * c->D >= 8LL * c->sm_count) return 8;
-    if (((W + 1023) / 1024) * c->D >= 4LL * c->sm_count) return 4;
-    if (((W + 511) / 512) * c->D >= 4LL * c->sm_count) return 2;
-    return 1;
+    int P, NW = 8;
+    if (c->farfield) {
+        // Small level-0 tiles keep the directly evaluated near field small (the hierarchy absorbs the rest), wide
+        // per-warp spans keep the per-pair staging amortised: 2 warps x 256 pixels (1 warp on small grids).
+        P = 8;
+        NW = (((W + 511) / 512) * c->D >= 2LL * c->sm_count) ? 2 : 1;
+    } else if (((W + 2047) / 2048) * c->D >= 8LL * c->sm_count) P = 8;
+    else if (((W + 1023) / 1024) * c->D >= 4LL * c->sm_count) P = 4;
+    else if (((W + 511) / 512) * c->D >= 4LL * c->sm_count) P = 2;
+    else P = 1;
+    if (force_p == 1 || force_p == 2 || force_p == 4 || force_p == 8) P = force_p;
+    if (force_nw == 1 || force_nw == 2 || force_nw == 8) NW = force_nw;
+    if (NW != 8 && P != 8) P = 8;  // only P = 8 is instantiated for the narrow CTAs
+    c->k2_NW = NW;
+    return P;
 }
 
 int sd_k2_lines(sd_ctx *c, int slot) {
@@ -536,7 +538,7 @@ int sd_k2_lines(sd_ctx *c, int slot) {
     }
     if (c->line_stats) SD_CUDA(c, cudaMemsetAsync(c->stats.p, 0, 4 * sizeof(unsigned long long), c->stream));
     static const int rcp = env_int("SD_K2_RCP", 2);
-    const int P = c->k2_P, tile = THREADS * P;
+    const int P = c->k2_P, NW = c->k2_NW, tile = 32 * NW * P;
     LineArgs a{};
     a.L = c->L; a.N = c->N; a.p0 = c->p0; a.p1 = c->p1; a.D = c->D;
     a.tile0 = (int)(c->p0 / tile);
@@ -562,10 +564,12 @@ int sd_k2_lines(sd_ctx *c, int slot) {
         }
     }
     dim3 grid((unsigned)n_launch, (unsigned)c->D);
+    if (NW == 2) return launch<8, 2>(c, a, grid, c->line_stats, rcp);
+    if (NW == 1) return launch<8, 1>(c, a, grid, c->line_stats, rcp);
     switch (P) {
-        case 8: return launch<8>(c, a, grid, c->line_stats, rcp);
-        case 4: return launch<4>(c, a, grid, c->line_stats, rcp);
-        case 2: return launch<2>(c, a, grid, c->line_stats, rcp);
-        default: return launch<1>(c, a, grid, c->line_stats, rcp);
+        case 8: return launch<8, 8>(c, a, grid, c->line_stats, rcp);
+        case 4: return launch<4, 8>(c, a, grid, c->line_stats, rcp);
+        case 2: return launch<2, 8>(c, a, grid, c->line_stats, rcp);
+        default: return launch<1, 8>(c, a, grid, c->line_stats, rcp);
     }
 }

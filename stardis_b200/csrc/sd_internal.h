@@ -94,7 +94,8 @@ struct sd_ctx {
     DevBuf tile_geom[SD_FAR_LEVELS];   // double [2 * n_tiles]: centre frequency and half-width of every global tile
     DevBuf far_coef[SD_FAR_LEVELS];    // double [D * n_tiles_shard * (SD_FAR_K + 1)]
     FarGeom far_geom{};
-    int k2_P = 4;      // pixels per thread chosen for the current grid (tile = 256 * k2_P pixels)
+    int k2_P = 4;      // pixels per thread chosen for the current grid
+    int k2_NW = 8;     // warps per CTA of the line kernel (level-0 tile = 32 * k2_NW * k2_P pixels)
     bool farfield = true;
     DevBuf alpha_line[2];
     bool have_alpha[2] = {false, false};
