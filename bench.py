@@ -280,11 +280,11 @@ def run_b200_arm(args):
             allgather_spectrum(d_spec, (p0, p1), N)
         if record: ev[5].record(stream)
 
+    sampler = ClockSampler(local_rank)  # sampled from the warm-up on: the timed region itself may last < 1 s
+    sampler.start()
     for _ in range(args.warmup):
         device_step()
     barrier()
-    sampler = ClockSampler(local_rank)
-    sampler.start()
     launches0 = ctx.launch_count()
     phase = np.zeros(5)
     t_start = torch.cuda.Event(enable_timing=True)
