@@ -286,6 +286,7 @@ __global__ void __launch_bounds__(32 * NW, MINB) k_lines(LineArgs a) {
     constexpr int TILE = 32 * NW * P;
     constexpr int SPAN = 32 * P;
     __shared__ WEntry s_ent[NW][32];  // every warp streams its own batches: no CTA barrier in the main loop
+    __shared__ double s_acc[NW][SPAN];  // accumulators of the pixel-parallel mixed path
     constexpr int NSRC = SD_NCLS + 2;    // classes 0..6, far-capable pairs near the tile, their window starts / ends
     __shared__ int s_ja[NSRC], s_jb[NSRC];
 
@@ -311,6 +312,10 @@ __global__ void __launch_bounds__(32 * NW, MINB) k_lines(LineArgs a) {
         int64_t pix = ws + p * 32 + lane;
         nu_i[p] = nus[pix < N ? pix : N - 1];
         acc[p] = 0.0;
+    }
+#pragma unroll
+    for (int p = 0; p < P; p++) {
+        s_acc[warp][p * 32 + lane] = 0.0;
     }
     // frequencies at the two ends of this warp's span (x is monotone in the pixel index)
     const double nu_first = nus[ws < N ? ws : N - 1];
@@ -413,27 +418,57 @@ __global__ void __launch_bounds__(32 * NW, MINB) k_lines(LineArgs a) {
                 far_eval(w.xl, w.inv_dw, w.b, w.c, w.Kc, w.Kf);
             }
             if (STATS) h0 += (unsigned long long)n_far * nvalid;
-            // ---- mixed entries: window edge inside the span and/or pixels near the line core --------------
+            // ---- mixed entries: window edge inside the span and/or pixels near the line core.  Lanes take CONSECUTIVE
+            // pixels of the in-window part of the span (a 20-pixel window keeps 20 lanes busy in one pass); entries are
+            // processed one after the other and a pass touches distinct pixels, so the shared accumulators need no
+            // atomics and the summation order stays fixed.
             for (int m = 0; m < n_mix; m++) {
                 const WEntry &e2 = my[31 - m];
-                const int lo2 = e2.lo, hi2 = e2.hi;
+                const int64_t pa = e2.lo > ws ? e2.lo : ws, pb = e2.hi < we ? e2.hi : we;
                 const double thr = e2.thr, xl = e2.xl, inv_dw = e2.inv_dw, eb = e2.b, ec = e2.c, Kc = e2.Kc, Kf = e2.Kf;
+                if (pb - pa <= 64) {
+                    for (int64_t c0 = pa; c0 < pb; c0 += 32) {
+                        const int64_t pix = c0 + lane;
+                        if (pix < pb) {
+                            const int k = (int)(pix - ws);
+                            const double nu = nus[pix];
+                            double x = fma(nu, inv_dw, -xl);
+                            double q = x * x;
+                            double v;
+                            if (q > thr) {
+                                double den = fma(q, q + eb, ec);
+                                double num = fma(Kf, q, Kc);
+                                v = num * (RCP == 2 ? sdm::rcp_fast2(den) : sdm::rcp_fast(den));
+                            } else {
+                                v = exact_contribution(nu, e2.nu, e2.dw, e2.y, e2.K);
+                            }
+                            s_acc[warp][k] += v;
+                            if (STATS && pix >= p0 && pix < p1) {
+                                int r = sdm::humlicek_region((nu - e2.nu) / e2.dw, e2.y);
+                                h0 += (r == 0); h1 += (r == 1); h2 += (r == 2); h3 += (r == 3);
+                            }
+                        }
+                    }
+                } else {
+                    // long overlap (a near-field pair whose core or window edge lies in this span): register slots
+                    const int lo2 = e2.lo, hi2 = e2.hi;
 #pragma unroll
-                for (int p = 0; p < P; p++) {
-                    int64_t pix = ws + p * 32 + lane;
-                    bool inwin = (pix >= lo2) && (pix < hi2) && (pix < t1);
-                    if (!__any_sync(0xffffffffu, inwin)) continue;
-                    double x = fma(nu_i[p], inv_dw, -xl);
-                    double q = x * x;
-                    bool fast = inwin && (q > thr);
-                    double den = fma(q, q + eb, ec);
-                    double num = fma(Kf, q, Kc);
-                    double v = num * (RCP == 2 ? sdm::rcp_fast2(den) : sdm::rcp_fast(den));
-                    if (fast) acc[p] += v;
-                    if (inwin && !fast) acc[p] += exact_contribution(nu_i[p], e2.nu, e2.dw, e2.y, e2.K);
-                    if (STATS && inwin && pix >= p0 && pix < p1) {
-                        int r = sdm::humlicek_region((nu_i[p] - e2.nu) / e2.dw, e2.y);
-                        h0 += (r == 0); h1 += (r == 1); h2 += (r == 2); h3 += (r == 3);
+                    for (int p = 0; p < P; p++) {
+                        int64_t pix = ws + p * 32 + lane;
+                        bool inwin = (pix >= lo2) && (pix < hi2) && (pix < t1);
+                        if (!__any_sync(0xffffffffu, inwin)) continue;
+                        double x = fma(nu_i[p], inv_dw, -xl);
+                        double q = x * x;
+                        bool fast = inwin && (q > thr);
+                        double den = fma(q, q + eb, ec);
+                        double num = fma(Kf, q, Kc);
+                        double v = num * (RCP == 2 ? sdm::rcp_fast2(den) : sdm::rcp_fast(den));
+                        if (fast) acc[p] += v;
+                        if (inwin && !fast) acc[p] += exact_contribution(nu_i[p], e2.nu, e2.dw, e2.y, e2.K);
+                        if (STATS && inwin && pix >= p0 && pix < p1) {
+                            int r = sdm::humlicek_region((nu_i[p] - e2.nu) / e2.dw, e2.y);
+                            h0 += (r == 0); h1 += (r == 1); h2 += (r == 2); h3 += (r == 3);
+                        }
                     }
                 }
             }
@@ -441,6 +476,10 @@ __global__ void __launch_bounds__(32 * NW, MINB) k_lines(LineArgs a) {
             }
         }
     }
+
+    __syncwarp();
+#pragma unroll
+    for (int p = 0; p < P; p++) acc[p] += s_acc[warp][p * 32 + lane];
 
     // ---- far field: one polynomial per hierarchy level (Horner in t = (nu - nu_c) / h of that level's tile) -------
     if (use_far && warp_has_pixels) {
