@@ -36,16 +36,20 @@ struct RayArgs {
     double *I_nus;         // (D, W, th_total) or nullptr
 };
 
-// One step of the short-characteristics recurrence (base.py:209-249 / :151-198): returns the new intensity.
-__device__ __forceinline__ double sc_step(double I_prev, double tau_k, double tau_n, double S_mid, double S_far,
-                                          double S_near) {
-    // outward form: I_{k+1} from I_k with tau_k (this gap), tau_n (next gap), S_mid = S_{k+1}, S_far = S_{k+2},
-    // S_near = S_k.  The inward sweep uses the same expression with mirrored arguments.
+// One step of the short-characteristics recurrence (base.py:209-249 / :151-198) with the five divisions of the
+// reference replaced by two reciprocals, one of which (1/tau of the gap just crossed) is carried over to the next step:
+//   second + third = [ dA r_n (w1 tau_k - w2) - dB r_k (w1 tau_n + w2) ] / (tau_k + tau_n),
+//   dA = S_mid - S_far, dB = S_mid - S_near, r = 1/tau.
+// Outward: tau_k = this gap, tau_n = next gap, S_mid = S_{k+1}, S_far = S_{k+2}, S_near = S_k; the inward sweep uses
+// the same expression with mirrored arguments.  A zero tau_n gives NaN like the reference's 0-division does.
+__device__ __forceinline__ double sc_step(double I_prev, double tau_k, double r_k, double tau_n, double r_n, double S_mid,
+                                          double dA, double dB) {
     double w0, w1, w2;
     sdm::rt_weights(tau_k, w0, w1, w2);
-    double second = w1 * ((S_mid - S_far) * (tau_k / tau_n) - (S_mid - S_near) * (tau_n / tau_k)) / (tau_k + tau_n);
-    double third = w2 * (((S_far - S_mid) / tau_n) + ((S_near - S_mid) / tau_k)) / (tau_k + tau_n);
-    return (1.0 - w0) * I_prev + w0 * S_mid + second + third;
+    const double rs = sdm::rcp_fast(tau_k + tau_n);
+    const double u = fma(w1, tau_k, -w2), v = fma(w1, tau_n, w2);
+    const double corr = fma(dA * r_n, u, -(dB * r_k) * v) * rs;
+    return fma(1.0 - w0, I_prev, fma(w0, S_mid, corr));
 }
 
 template <int TH>
@@ -71,7 +75,7 @@ __global__ void __launch_bounds__(128) k_raytrace(RayArgs a) {
     const bool last = a.scale != 0.0;  // scale == 0 marks "not the last launch"
     const double scale = last ? a.scale : 1.0;
 
-    double I[TH];
+    double I[TH], tau_c[TH], r_c[TH];  // intensity, optical depth of the current gap and its reciprocal, per angle
 #pragma unroll
     for (int t = 0; t < TH; t++) I[t] = 0.0;
 
@@ -94,11 +98,14 @@ __global__ void __launch_bounds__(128) k_raytrace(RayArgs a) {
         const double sa_last = sqrt(al[(size_t)(D - 1) * W]), sa_last2 = sqrt(al[(size_t)(D - 2) * W]);
         const double mean_wrap = sa_last * sa_last2;  // mean opacity of gap G-1
         const double S_wrap = sdm::planck(nu, s_T[D - 1]);
-        // rolling: mean_k (gap k), mean_km (gap k-1); S_{k+1}, S_k, S_{k-1}
-        double sa_kp1 = sa_last, sa_k = sa_last2;
+        double sa_k = sa_last2;
         double S_kp1 = S_wrap, S_k = sdm::planck(nu, s_T[D - 2]);
+#pragma unroll
+        for (int t = 0; t < TH; t++) {
+            tau_c[t] = mean_wrap * s_ds[(G - 1) * TH + t];
+            r_c[t] = sdm::rcp_fast(tau_c[t]);
+        }
         for (int k = G - 1; k >= 0; k--) {
-            double mean_k = sa_kp1 * sa_k;
             double sa_km1 = 0.0, S_km1, mean_km;
             if (k >= 1) {
                 sa_km1 = sqrt(al[(size_t)(k - 1) * W]);
@@ -109,45 +116,59 @@ __global__ void __launch_bounds__(128) k_raytrace(RayArgs a) {
                 mean_km = mean_wrap;
             }
             const int km = (k >= 1) ? k - 1 : G - 1;
+            const double dA = S_k - S_km1, dB = S_k - S_kp1;
 #pragma unroll
             for (int t = 0; t < TH; t++) {
-                double tau_k = mean_k * s_ds[k * TH + t];
-                double tau_m = mean_km * s_ds[km * TH + t];
-                if (!(tau_k == 0.0 || tau_m == 0.0))
-                    I[t] = sc_step(I[t], tau_k, tau_m, S_k, S_km1, S_kp1);
+                const double tau_k = tau_c[t], r_k = r_c[t];
+                const double tau_m = mean_km * s_ds[km * TH + t];
+                const double r_m = sdm::rcp_fast(tau_m);
+                if (!(tau_k == 0.0 || tau_m == 0.0)) I[t] = sc_step(I[t], tau_k, r_k, tau_m, r_m, S_k, dA, dB);
+                tau_c[t] = tau_m;
+                r_c[t] = r_m;
             }
-            sa_kp1 = sa_k; sa_k = sa_km1;
+            sa_k = sa_km1;
             S_kp1 = S_k; S_k = S_km1;
         }
     }
     emit(0);
 
     // outward sweep, base.py:200-266
-    double sa0 = sqrt(al[0]), sa1 = sqrt(al[(size_t)W]);
+    double sa1 = sqrt(al[(size_t)W]);
     double S0 = sdm::planck(nu, s_T[0]), S1 = sdm::planck(nu, s_T[1]);
-    double mean0 = sa0 * sa1;
-    for (int k = 0; k < G - 1; k++) {
-        double sa2 = sqrt(al[(size_t)(k + 2) * W]);
-        double S2 = sdm::planck(nu, s_T[k + 2]);
-        double mean1 = sa1 * sa2;
+    {
+        const double mean0 = sqrt(al[0]) * sa1;
 #pragma unroll
         for (int t = 0; t < TH; t++) {
-            double tau_k = mean0 * s_ds[k * TH + t];
-            double tau_n = mean1 * s_ds[(k + 1) * TH + t];
-            if (tau_k != 0.0) I[t] = sc_step(I[t], tau_k, tau_n, S1, S2, S0);
+            tau_c[t] = mean0 * s_ds[t];
+            r_c[t] = sdm::rcp_fast(tau_c[t]);
+        }
+    }
+    for (int k = 0; k < G - 1; k++) {
+        const double sa2 = sqrt(al[(size_t)(k + 2) * W]);
+        const double S2 = sdm::planck(nu, s_T[k + 2]);
+        const double mean1 = sa1 * sa2;
+        const double dA = S1 - S2, dB = S1 - S0;
+#pragma unroll
+        for (int t = 0; t < TH; t++) {
+            const double tau_k = tau_c[t], r_k = r_c[t];
+            const double tau_n = mean1 * s_ds[(k + 1) * TH + t];
+            const double r_n = sdm::rcp_fast(tau_n);
+            if (tau_k != 0.0) I[t] = sc_step(I[t], tau_k, r_k, tau_n, r_n, S1, dA, dB);
+            tau_c[t] = tau_n;
+            r_c[t] = r_n;
         }
         emit(k + 1);
-        sa1 = sa2; mean0 = mean1;
+        sa1 = sa2;
         S0 = S1; S1 = S2;
     }
-    {  // final jump, base.py:253-266 (after the loop: S0 = S_{D-2}, S1 = S_{D-1}, mean0 = gap G-1)
+    {  // final jump, base.py:253-266 (after the loop: S0 = S_{D-2}, S1 = S_{D-1}, tau_c = gap G-1)
 #pragma unroll
         for (int t = 0; t < TH; t++) {
-            double tau = mean0 * s_ds[(G - 1) * TH + t];
+            const double tau = tau_c[t];
             if (tau != 0.0) {
                 double w0, w1, w2;
                 sdm::rt_weights(tau, w0, w1, w2);
-                double third = w2 * (S0 - S1) / (tau * tau);
+                const double third = w2 * (S0 - S1) * (r_c[t] * r_c[t]);
                 I[t] = (1.0 - w0) * I[t] + w0 * S1 + third;
             }
         }
