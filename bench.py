@@ -210,7 +210,7 @@ def run_b200_arm(args):
     from stardis_b200 import _lib as L
     from stardis_b200 import units as u
     from stardis_b200.device import DeviceContext
-    from stardis_b200.distributed import allgather_spectrum, shard_bounds
+    from stardis_b200.distributed import allgather_spectrum, line_balanced_bounds
     from stardis_b200.radiation_field import RadiationField
     from stardis_b200.radiation_field.opacities.opacities_solvers import base as ob
     from stardis_b200.radiation_field.opacities.opacities_solvers.broadening import set_device_atmosphere, upload_lines_and_broaden
@@ -228,8 +228,6 @@ def run_b200_arm(args):
     w, cfg, desc = build_workload(args)
     model, plasma, nus = w["model"], w["plasma"], w["nus"]
     N, D = len(nus), model.no_of_depth_points
-    p0, p1 = shard_bounds(N, rank, world)
-    W = p1 - p0
     stream = torch.cuda.Stream()  # all kernels, copies and timing events of this benchmark live on this stream
     torch.cuda.set_stream(stream)
     ctx = DeviceContext(local_rank, stream=stream)
@@ -243,6 +241,11 @@ def run_b200_arm(args):
     line_cfg = cfg.opacity.line
     nus_q = u.Quantity(nus, u.Hz)
     lines = ob.select_lines(plasma, model, nus_q, line_cfg)
+    # cost-balanced contiguous nu ranges (pixels + 4 x lines inside): the blue end of the grid holds ~10x more lines per
+    # pixel than the red end, so equal-width ranges would leave rank 0 with several times the line-core work
+    bounds = line_balanced_bounds(nus, lines.nu, world)
+    p0, p1 = bounds[rank]
+    W = p1 - p0
     flags = ob._line_flags(line_cfg)
     tables, _ = ob.file_tables(plasma, model, cfg.opacity.file)
     bf_cut, bf_prefix = ob.bf_descriptor(plasma, cfg.opacity.bf)
@@ -277,7 +280,7 @@ def run_b200_arm(args):
         if record: ev[4].record(stream)
         ctx.get_row(L.BUF_F_NU, -1, out=d_spec)
         if world > 1:
-            allgather_spectrum(d_spec, (p0, p1), N)
+            allgather_spectrum(d_spec, (p0, p1), N, bounds=bounds)
         if record: ev[5].record(stream)
 
     sampler = ClockSampler(local_rank)  # sampled from the warm-up on: the timed region itself may last < 1 s
@@ -381,14 +384,15 @@ def run_b200_arm(args):
     d2h = int(W * 8)
 
     def api_step():
-        srf = RadiationField(nus_host, None, model, cfg.no_of_thetas, device_context=ctx, shard=(p0, p1) if world > 1 else None)
+        srf = RadiationField(nus_host, None, model, cfg.no_of_thetas, device_context=ctx, shard=(p0, p1) if world > 1 else None,
+                             shard_bounds=bounds)
         ob.calc_alphas(plasma, model, srf, cfg.opacity, store_components=False)
         raytrace(model, srf)
         ctx.get_row(L.BUF_F_NU, -1, out=h_spec)
         ctx.synchronize()
         spec = h_spec
         if world > 1:
-            spec = allgather_spectrum(h_spec.numpy(), (p0, p1), N, device="cuda")
+            spec = allgather_spectrum(h_spec.numpy(), (p0, p1), N, device="cuda", bounds=bounds)
         return spec
 
     api_step()
@@ -418,7 +422,8 @@ def run_b200_arm(args):
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": desc, "l2": "inputs larger than L2 (line records %.2f GB, outputs %.2f GB per array)"
-                       % (len(sel) * D * 64 / 1e9, cells * 8 / 1e9), "partition": f"nu shards over {world} rank(s), global windows"},
+                       % (len(sel) * D * 64 / 1e9, cells * 8 / 1e9), "partition": f"{world} contiguous nu range(s), global windows, cut at equal (pixels + 4 x lines inside)",
+                       "ranges": [list(b) for b in bounds]},
             "roofline": {"kernel": "k_lines, direct mode (K2: every (line, depth, pixel) Voigt evaluation done explicitly, "
                                    "far-field expansion off)", "bound": "fp64", "achieved": achieved_tflops,
                          "peak": dfma_peak, "unit": "TFLOP/s", "frac": achieved_tflops / dfma_peak, "traffic": None,

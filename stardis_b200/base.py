@@ -20,7 +20,8 @@ def run_stardis(config_fname, tracing_lambdas_or_nus, add_config_dict=None, devi
     ``config_fname``: YAML configuration; ``tracing_lambdas_or_nus``: wavelengths or frequencies with units
     (``stardis_b200.units`` or astropy); ``add_config_dict``: dotted-key overrides.  Returns ``STARDISOutput``.
     Opacities and the formal solution run on the GPU; ``device_context`` / ``shard`` select the device and, for
-    multi-GPU runs, the pixel range of the global grid this rank evaluates."""
+    multi-GPU runs, the pixel range of the global grid this rank evaluates (``shard="auto"``: this rank's range of
+    the cost-balanced partition, see ``distributed.line_balanced_bounds``)."""
     tracing_nus = u.to_hz(tracing_lambdas_or_nus)
     config, adata, stellar_model = parse_config_to_model(config_fname, add_config_dict)
     set_num_threads(config.n_threads)
@@ -87,7 +88,8 @@ class STARDISOutput:
             from .distributed import allgather_spectrum, dist_info
 
             if dist_info()[0] is not None:
-                emergent = allgather_spectrum(emergent, shard, len(nus))
+                emergent = allgather_spectrum(emergent, shard, len(nus),
+                                              bounds=getattr(stellar_radiation_field, "shard_bounds", None))
             else:  # single process evaluating one shard: the spectrum covers pixels [p0, p1) only
                 self.shard = (int(shard[0]), int(shard[1]))
                 nus, lambdas = nus[shard[0]:shard[1]], lambdas[shard[0]:shard[1]]

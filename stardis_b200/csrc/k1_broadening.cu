@@ -117,8 +117,8 @@ __global__ void __launch_bounds__(256) k_build_records(int64_t L, int D, int64_t
                                                        const int *__restrict__ line_idx, const double *__restrict__ gammas,
                                                        int gamma_cols, const double *__restrict__ dws,
                                                        const double *__restrict__ alpha, const double *__restrict__ d_nu_p,
-                                                       LineRec *__restrict__ rec, int *__restrict__ win_lo,
-                                                       int *__restrict__ win_hi, uint8_t *__restrict__ win_cls,
+                                                       LineRec *__restrict__ rec, PairWin *__restrict__ win,
+                                                       uint8_t *__restrict__ win_cls,
                                                        FarGeom fg, unsigned long long *__restrict__ stats) {
     int64_t g = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     bool active = g < L * D;
@@ -153,18 +153,19 @@ __global__ void __launch_bounds__(256) k_build_records(int64_t L, int D, int64_t
         r.pad0 = r.pad1 = 0.0;
         size_t o = (size_t)d * L + l;
         rec[o] = r;
-        win_lo[o] = (int)lo;
-        win_hi[o] = (int)hi;
-        win_cls[o] = (uint8_t)cls;
+        PairWin pw;
+        pw.lo = (int)lo;
+        pw.hi = (int)hi;
+        pw.near[0] = pw.near[1] = pw.near[2] = 0xffff0000u;
+        pw.pad0 = pw.pad1 = 0;
         // Far-capable pair: the window holds at least one level-0 tile and all parameters are finite.  Such pairs
         // form class 7; per hierarchy level they get the interval of tiles [nl, nh) around the line centre that are
         // NOT far, and their window edges go to the two edge-sort key arrays.
-        const bool fc = fg.near[0] && (hi - lo >= fg.tile[0]) && (r.thr == r.thr) && (a == a) && (fabs(a) < 1e300);
-        if (fc) {
-            cls = SD_FC_CLASS;
-            win_cls[o] = (uint8_t)cls;
-        }
-        if (fg.near[0]) {
+        const bool fc = fg.enabled && (hi - lo >= fg.tile[0]) && (r.thr == r.thr) && (a == a) && (fabs(a) < 1e300);
+        if (fc) cls = SD_FC_CLASS;
+        win_cls[o] = (uint8_t)cls;
+        pw.cls = cls;
+        if (fg.enabled) {
 #pragma unroll
             for (int k = 0; k < SD_FAR_LEVELS; k++) {
                 unsigned nl = 0, nh = 0xffffu;
@@ -181,7 +182,7 @@ __global__ void __launch_bounds__(256) k_build_records(int64_t L, int D, int64_t
                     nh = (unsigned)b_;
                     rad = max(tc - a_, b_ - 1 - tc);
                 }
-                fg.near[k][o] = nl | (nh << 16);
+                pw.near[k] = nl | (nh << 16);
                 rad_k[k] = rad;
             }
             const unsigned long long dkey = (unsigned long long)d << 32;
@@ -189,11 +190,12 @@ __global__ void __launch_bounds__(256) k_build_records(int64_t L, int D, int64_t
             fg.hi_keys[o] = dkey | (unsigned long long)((fc && hi < N) ? hi : 0x7fffffff);
             fg.lo_l[o] = (int)l;
         }
+        win[o] = pw;
         nonempty = hi > lo;
         wide = (hi > lo) && cls > 0;
         zero_dw = (hi > lo) && (dw == 0.0);
     }
-    if (fg.near[0]) {
+    if (fg.enabled) {
 #pragma unroll
         for (int k = 0; k < SD_FAR_LEVELS; k++) {
             int m = rad_k[k];
@@ -322,9 +324,9 @@ int sd_k2_prepare(sd_ctx *c) {
         k_tile_geometry<<<(fg.n_tiles[k] + 255) / 256, 256, 0, c->stream>>>(c->N, fg.tile[k], fg.n_tiles[k], c->nus.as<double>(),
                                                                           c->tile_geom[k].as<double>());
         SD_TRY(sd_launch_check(c, "k_tile_geometry"));
-        fg.near[k] = nullptr;
     }
     fg.near_rad = nullptr;
+    fg.enabled = 0;
     fg.lo_keys = fg.hi_keys = nullptr;
     fg.lo_l = fg.hi_l = nullptr;
     if (L == 0) {
@@ -334,15 +336,11 @@ int sd_k2_prepare(sd_ctx *c) {
     }
     SD_TRY(sd_ensure(c, c->line_idx, sizeof(int) * L));
     SD_TRY(sd_ensure(c, c->rec, sizeof(LineRec) * n));
-    SD_TRY(sd_ensure(c, c->win_lo, sizeof(int) * n));
-    SD_TRY(sd_ensure(c, c->win_hi, sizeof(int) * n));
+    SD_TRY(sd_ensure(c, c->win, sizeof(PairWin) * n));
     SD_TRY(sd_ensure(c, c->win_cls, n));
     SD_TRY(sd_ensure(c, c->cls_list, sizeof(int) * n));
     if (c->farfield) {
-        for (int k = 0; k < SD_FAR_LEVELS; k++) {
-            SD_TRY(sd_ensure(c, c->near_tiles[k], sizeof(unsigned) * n));
-            fg.near[k] = c->near_tiles[k].as<unsigned>();
-        }
+        fg.enabled = 1;
         SD_TRY(sd_ensure(c, c->near_rad, sizeof(int) * SD_FAR_LEVELS));
         SD_CUDA(c, cudaMemsetAsync(c->near_rad.p, 0, sizeof(int) * SD_FAR_LEVELS, c->stream));
         fg.near_rad = c->near_rad.as<int>();
@@ -364,8 +362,8 @@ int sd_k2_prepare(sd_ctx *c) {
     SD_TRY(sd_launch_check(c, "k_line_idx"));
     k_build_records<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(
         L, D, c->N, c->l_nu.as<double>(), c->line_idx.as<int>(), c->gammas.as<double>(), c->gamma_cols,
-        c->dws.as<double>(), c->l_alpha.as<double>(), c->d_nu.as<double>(), c->rec.as<LineRec>(), c->win_lo.as<int>(),
-        c->win_hi.as<int>(), c->win_cls.as<uint8_t>(), fg, c->stats.as<unsigned long long>());
+        c->dws.as<double>(), c->l_alpha.as<double>(), c->d_nu.as<double>(), c->rec.as<LineRec>(), c->win.as<PairWin>(),
+        c->win_cls.as<uint8_t>(), fg, c->stats.as<unsigned long long>());
     SD_TRY(sd_launch_check(c, "k_build_records"));
     k_cls_count<<<dim3(nchunks, D), CHUNK, 0, c->stream>>>(L, c->win_cls.as<uint8_t>(), nchunks, c->chunk_cnt.as<int>());
     SD_TRY(sd_launch_check(c, "k_cls_count"));

@@ -41,6 +41,10 @@ namespace {
 
 constexpr int THREADS = 256;
 constexpr int WARPS = THREADS / 32;
+constexpr int FAR_R = 8;                    // candidates per lane and scan round of k_far_coeffs
+constexpr int FAR_QCAP = 32 * (FAR_R + 1);  // per-warp queue: a carried remainder (< 32 pairs) plus one scan round
+struct __align__(16) FarRec { double nu, dw, y, K; };  // = the first 32 bytes of LineRec
+constexpr size_t FAR_SMEM = (size_t)WARPS * FAR_QCAP * sizeof(FarRec);
 
 struct __align__(16) WEntry {
     // far-wing path (48 B)
@@ -66,8 +70,7 @@ struct LineArgs {
     const double *nus;
     const int *line_idx;
     const LineRec *rec;
-    const int *win_lo, *win_hi;
-    const uint8_t *win_cls;
+    const PairWin *win;   // (depth, line) window records
     const int *cls_list, *cls_off;
     FarGeom fg;                  // tile hierarchy; fg.near[0] == nullptr: far field disabled
     double *far_coef[SD_FAR_LEVELS];   // per level: (D, n_tiles_launch[k], SD_FAR_K + 1)
@@ -163,6 +166,19 @@ __device__ __forceinline__ void fc_edge_range(const LineArgs &a, int d, int whic
     jb = warp_lower_bound_u64(keys, ja, hi, dk | (unsigned long long)t1);
 }
 
+// one 32-byte gather (two 16-byte loads of the same sector)
+__device__ __forceinline__ PairWin load_win(const PairWin *__restrict__ w) {
+    const int4 a = __ldg(reinterpret_cast<const int4 *>(w)), b = __ldg(reinterpret_cast<const int4 *>(w) + 1);
+    PairWin r;
+    r.lo = a.x; r.hi = a.y; r.near[0] = (unsigned)a.z; r.near[1] = (unsigned)a.w;
+    r.near[2] = (unsigned)b.x; r.cls = b.y; r.pad0 = 0; r.pad1 = 0;
+    return r;
+}
+
+__device__ __forceinline__ unsigned near_of(const PairWin &w, int lev) {  // no dynamically indexed registers
+    return lev == 0 ? w.near[0] : (lev == 1 ? w.near[1] : w.near[2]);
+}
+
 __device__ __noinline__ double exact_contribution(double nu_i, double nu_l, double dw, double y, double K) {
     double x = (nu_i - nu_l) / dw;  // voigt.py:148, IEEE division
     return sdm::humlicek_re(x, y) * K;
@@ -184,14 +200,18 @@ __device__ __forceinline__ bool pair_is_far(int lo, int hi, unsigned near, int64
 //       class-7 list around the parent;
 //   (B) pairs that do not cover the parent (a window edge lies strictly inside it): two ranges of the edge-sorted lists.
 // The top level has no parent and walks the whole class-7 list.
-__global__ void __launch_bounds__(THREADS) k_far_coeffs(LineArgs a, int lev, int count_stats) {
+// The top level is launched with `nsplit` CTAs per (tile, depth), each taking a fixed slice of the class-7 list (the
+// slices do not depend on the shard, so the summation order -- and the result, bit for bit -- is the same for every
+// partition of the grid); k_far_reduce adds the partial sums in slice order.
+__global__ void __launch_bounds__(THREADS) k_far_coeffs(LineArgs a, int lev, int count_stats, int nsplit, double *part) {
     constexpr int K1 = SD_FAR_K + 1;
     __shared__ int s_ja[3], s_jb[3];
     __shared__ double s_red[WARPS][K1];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int d = blockIdx.y;
     const int tile_px = a.fg.tile[lev];
-    const int tile = a.far_tile0[lev] + blockIdx.x;
+    const int tile_local = blockIdx.x / nsplit, split = blockIdx.x - tile_local * nsplit;
+    const int tile = a.far_tile0[lev] + tile_local;
     const int64_t t0 = (int64_t)tile * tile_px;
     const int64_t t1 = (t0 + tile_px < a.N) ? t0 + tile_px : a.N;
     const double nu_c = a.fg.geom[lev][2 * tile], h = a.fg.geom[lev][2 * tile + 1];
@@ -200,15 +220,15 @@ __global__ void __launch_bounds__(THREADS) k_far_coeffs(LineArgs a, int lev, int
     const int ptile = tile >> SD_FAR_SHIFT;
     const int64_t pt0 = (int64_t)ptile * a.fg.tile[plev];
     const int64_t pt1 = (pt0 + a.fg.tile[plev] < a.N) ? pt0 + a.fg.tile[plev] : a.N;
-    const unsigned *__restrict__ near_k = a.fg.near[lev];
-    const unsigned *__restrict__ near_p = a.fg.near[plev];
     const size_t drow = (size_t)d * a.L;
     const int *list_d = a.cls_list + drow;
     if (warp < 3) {
         int ja, jb;
         if (!has_parent) {
-            ja = a.cls_off[d * (SD_NCLS + 1) + SD_FC_CLASS];
-            jb = (warp == 0) ? a.cls_off[d * (SD_NCLS + 1) + SD_FC_CLASS + 1] : ja;
+            const int c0 = a.cls_off[d * (SD_NCLS + 1) + SD_FC_CLASS], c1 = a.cls_off[d * (SD_NCLS + 1) + SD_FC_CLASS + 1];
+            const int len = (c1 - c0 + nsplit - 1) / nsplit;
+            ja = min(c0 + split * len, c1);
+            jb = (warp == 0) ? min(ja + len, c1) : ja;
         } else if (warp == 0) {
             fc_near_range(a, d, plev, ptile, ja, jb);
         } else {
@@ -222,43 +242,111 @@ __global__ void __launch_bounds__(THREADS) k_far_coeffs(LineArgs a, int lev, int
     for (int k = 0; k < K1; k++) C[k] = 0.0;
     unsigned long long n_far = 0;
     const double inv_h = 1.0 / h;
-    for (int src = 0; src < 3; src++) {
-        const int ja = s_ja[src], jb = s_jb[src];
-        for (int j = ja + tid; j < jb; j += THREADS) {
-            const int l = (src == 0) ? list_d[j] : (src == 1 ? a.fg.lo_l[j] : a.fg.hi_l[j]);
-            const size_t o = drow + l;
-            const int lo = a.win_lo[o], hi = a.win_hi[o];
-            if (!pair_is_far(lo, hi, near_k[o], t0, t1, tile)) continue;  // must cover this tile and be far from it
-            if (has_parent) {
-                const bool covers_parent = (lo <= pt0) && (hi >= pt1);
-                if (src == 0) {  // (A): covers the parent, parent inside the near interval
-                    if (!covers_parent || pair_is_far(lo, hi, near_p[o], pt0, pt1, ptile)) continue;
-                } else {         // (B): an edge strictly inside the parent; a pair with both edges inside comes via its start
-                    if (covers_parent) continue;
-                    if (src == 2 && lo > pt0 && lo < pt1) continue;
-                }
-            }
-            const LineRec r = a.rec[o];
-            const double g = r.y * r.dw;                                       // Lorentz half-width in Hz
-            const double Wn = -r.K * r.dw * (0.5 * sdm::INV_SQRT_PI) * inv_h;  // -W
+    const unsigned lt_mask = (1u << lane) - 1u;
+
+    // One accepted pair: 21 Taylor coefficients of its two poles about the tile centre.  Called with a dense batch of
+    // pairs (one per thread); `have` is false only in the last, partial batch.
+    auto expand = [&](bool have, const FarRec &r) {
+        double Wn = 0.0, w1r = 0.0, w1i = 0.0, w2r = 0.0, w2i = 0.0;
+        int nterms = 0;
+        if (have) {
+            const double g = r.y * r.dw;                                // Lorentz half-width in Hz
+            Wn = -r.K * r.dw * (0.5 * sdm::INV_SQRT_PI) * inv_h;        // -W
             const double adw = 0.7071067811865476 * r.dw;
             // w = -h / (D - i g) = -h (D + i g) / (D^2 + g^2) for the two poles
             const double D1 = nu_c - (r.nu + adw), D2 = nu_c - (r.nu - adw);
-            const double i1 = -h * sdm::rcp_fast(fma(D1, D1, g * g)), i2 = -h * sdm::rcp_fast(fma(D2, D2, g * g));
-            const double w1r = D1 * i1, w1i = g * i1, w2r = D2 * i2, w2i = g * i2;
-            double p1r = w1r, p1i = w1i, p2r = w2r, p2i = w2i;
-#pragma unroll
-            for (int k = 0; k < K1; k++) {
-                C[k] = fma(Wn, p1i + p2i, C[k]);
-                if (k + 1 < K1) {
-                    double t;
-                    t = fma(p1r, w1r, -p1i * w1i); p1i = fma(p1r, w1i, p1i * w1r); p1r = t;
-                    t = fma(p2r, w2r, -p2i * w2i); p2i = fma(p2r, w2i, p2i * w2r); p2r = t;
-                }
-            }
+            const double q1 = sdm::rcp_fast(fma(D1, D1, g * g)), q2 = sdm::rcp_fast(fma(D2, D2, g * g));
+            const double i1 = -h * q1, i2 = -h * q2;
+            w1r = D1 * i1; w1i = g * i1; w2r = D2 * i2; w2i = g * i2;
+            // terms needed: (n + 1) rho^n <= 22 * 4^-21 (the bound of the full series at the far criterion rho = 1/4)
+            // <=>  n >= ~42 / log2(1 / rho);  rho^2 = h^2 max(q1, q2)
+            const float lg = -0.5f * __log2f((float)(h * h * fmax(q1, q2)));
+            nterms = (lg > 2.0f) ? min(K1, (int)(42.0f / lg + 1.01f)) : K1;
             n_far++;
         }
+        // queue neighbours are neighbours in frequency, at similar distances from the tile: warp-uniform series length
+        const int nt = __reduce_max_sync(0xffffffffu, nterms);
+        double p1r = w1r, p1i = w1i, p2r = w2r, p2i = w2i;
+#pragma unroll
+        for (int k = 0; k < K1; k++) {
+            if (k >= nt) break;
+            C[k] = fma(Wn, p1i + p2i, C[k]);
+            if (k + 1 < K1) {
+                double t;
+                t = fma(p1r, w1r, -p1i * w1i); p1i = fma(p1r, w1i, p1i * w1r); p1r = t;
+                t = fma(p2r, w2r, -p2i * w2i); p2i = fma(p2r, w2i, p2i * w2r); p2r = t;
+            }
+        }
+    };
+
+    // Every warp works on its own, in rounds of FAR_R x 32 consecutive candidates:
+    //   scan     FAR_R independent 32-byte gathers per lane (PairWin), acceptance test, ballot compaction of the
+    //            accepted line numbers into the warp's queue, in list order;
+    //   stage    the 32 bytes of LineRec the expansion needs are copied to shared memory with cp.async for ALL newly
+    //            queued pairs at once (one memory latency per round, not one per batch);
+    //   expand   full batches of 32 queued pairs, one per lane, all lanes busy; the remainder is carried over.
+    // There is no CTA barrier in the loop, so the warps of an SM drift apart and the gathers of one overlap the
+    // arithmetic of the others.  Candidate -> warp assignment and queue order are functions of the candidate lists only:
+    // the summation order is fixed.
+    extern __shared__ __align__(16) unsigned char far_smem[];
+    FarRec *const q = reinterpret_cast<FarRec *>(far_smem) + (size_t)warp * FAR_QCAP;
+    int qn = 0;  // queue length of this warp
+    for (int src = 0; src < 3; src++) {
+        const int ja = s_ja[src], jb = s_jb[src];
+        for (int base = ja + warp * (32 * FAR_R); base < jb; base += THREADS * FAR_R) {
+            int l_r[FAR_R];
+            unsigned m_r[FAR_R];
+#pragma unroll
+            for (int r = 0; r < FAR_R; r++) {
+                const int j = base + r * 32 + lane;
+                l_r[r] = (j < jb) ? ((src == 0) ? list_d[j] : (src == 1 ? a.fg.lo_l[j] : a.fg.hi_l[j])) : -1;
+            }
+#pragma unroll
+            for (int r = 0; r < FAR_R; r++) {
+                bool ok = l_r[r] >= 0;
+                if (ok) {
+                    const PairWin pw = load_win(a.win + drow + l_r[r]);
+                    const int lo = pw.lo, hi = pw.hi;
+                    ok = pair_is_far(lo, hi, near_of(pw, lev), t0, t1, tile);  // must cover this tile and be far from it
+                    if (has_parent) {
+                        const bool covers_parent = (lo <= pt0) && (hi >= pt1);
+                        if (src == 0) {  // (A): covers the parent, parent inside the near interval
+                            ok = ok && covers_parent && !pair_is_far(lo, hi, near_of(pw, plev), pt0, pt1, ptile);
+                        } else {         // (B): an edge strictly inside the parent; both edges inside: via its start
+                            ok = ok && !covers_parent && !(src == 2 && lo > pt0 && lo < pt1);
+                        }
+                    }
+                }
+                m_r[r] = __ballot_sync(0xffffffffu, ok);
+            }
+#pragma unroll
+            for (int r = 0; r < FAR_R; r++) {
+                if ((m_r[r] >> lane) & 1u) {
+                    const unsigned dst = (unsigned)__cvta_generic_to_shared(q + qn + __popc(m_r[r] & lt_mask));
+                    const LineRec *srcp = a.rec + drow + l_r[r];
+                    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(srcp) : "memory");
+                    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst + 16u),
+                                 "l"(reinterpret_cast<const char *>(srcp) + 16) : "memory");
+                }
+                qn += __popc(m_r[r]);
+            }
+            asm volatile("cp.async.commit_group;" ::: "memory");
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+            __syncwarp();
+            int b = 0;
+            for (; b + 32 <= qn; b += 32) expand(true, q[b + lane]);
+            if (b > 0) {  // move the remainder (< 32 entries) to the front
+                const int rem = qn - b;
+                FarRec v;
+                if (lane < rem) v = q[b + lane];
+                __syncwarp();
+                if (lane < rem) q[lane] = v;
+                qn = rem;
+                __syncwarp();
+            }
+        }
     }
+    if (qn > 0) expand(lane < qn, q[lane < qn ? lane : 0]);
     // deterministic block reduction: lanes by shuffle, warps through shared memory in fixed order
 #pragma unroll
     for (int k = 0; k < K1; k++) {
@@ -271,13 +359,25 @@ __global__ void __launch_bounds__(THREADS) k_far_coeffs(LineArgs a, int lev, int
         double v = 0.0;
 #pragma unroll
         for (int w = 0; w < WARPS; w++) v += s_red[w][tid];
-        a.far_coef[lev][((size_t)d * gridDim.x + blockIdx.x) * K1 + tid] = v;
+        if (nsplit > 1) part[((size_t)d * gridDim.x + blockIdx.x) * K1 + tid] = v;
+        else a.far_coef[lev][((size_t)d * gridDim.x + blockIdx.x) * K1 + tid] = v;
     }
     if (count_stats) {  // every far pair stands for one region-I evaluation per tile pixel inside the shard
         for (int o2 = 16; o2; o2 >>= 1) n_far += __shfl_xor_sync(0xffffffffu, n_far, o2);
         const int64_t e0 = t0 > a.p0 ? t0 : a.p0, e1 = t1 < a.p1 ? t1 : a.p1;
         if (lane == 0 && n_far && e1 > e0) atomicAdd(&a.stats[0], n_far * (unsigned long long)(e1 - e0));
     }
+}
+
+// sum of the nsplit partial coefficient sets of the top level, in slice order
+__global__ void k_far_reduce(int n, int nsplit, const double *__restrict__ part, double *__restrict__ coef) {
+    constexpr int K1 = SD_FAR_K + 1;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;  // (depth, tile) * K1 + k
+    if (i >= n) return;
+    const int td = i / K1, k = i - td * K1;
+    double v = 0.0;
+    for (int s2 = 0; s2 < nsplit; s2++) v += part[((size_t)td * nsplit + s2) * K1 + k];
+    coef[i] = v;
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -302,8 +402,7 @@ __global__ void __launch_bounds__(32 * NW, MINB) k_lines(LineArgs a) {
     const size_t drow = (size_t)d * L;
     const int *list_d = a.cls_list + drow;
     const double *__restrict__ nus = a.nus;
-    const unsigned *__restrict__ near0 = a.fg.near[0];
-    const bool use_far = near0 != nullptr;
+    const bool use_far = a.fg.enabled != 0;
 
     // pixel frequencies and accumulators live in registers for the whole kernel
     double nu_i[P], acc[P];
@@ -371,13 +470,14 @@ __global__ void __launch_bounds__(32 * NW, MINB) k_lines(LineArgs a) {
                 else if (src <= SD_FC_CLASS) l = list_d[j];            // class lists (7 = far-capable pairs near the tile)
                 else l = (src == SD_NCLS) ? a.fg.lo_l[j] : a.fg.hi_l[j];  // far-capable pairs with an edge inside the tile
                 o = drow + l;
-                lo = a.win_lo[o];
-                hi = a.win_hi[o];
+                const PairWin pw = load_win(a.win + o);
+                lo = pw.lo;
+                hi = pw.hi;
                 pass = (lo < we) && (hi > ws) && (hi > lo);
-                if (src == 0) pass = pass && (a.win_cls[o] == 0);
+                if (src == 0) pass = pass && (pw.cls == 0);
                 else if (src == SD_FC_CLASS) {
                     // covering pairs only (the others come through the edge lists); skip those expanded by k_far_coeffs
-                    pass = pass && (lo <= t0) && (hi >= t1) && !pair_is_far(lo, hi, near0[o], t0, t1, tile);
+                    pass = pass && (lo <= t0) && (hi >= t1) && !pair_is_far(lo, hi, pw.near[0], t0, t1, tile);
                 }
             }
             if (!__any_sync(0xffffffffu, pass)) continue;
@@ -584,7 +684,7 @@ int sd_k2_lines(sd_ctx *c, int slot) {
     a.n_tiles = (int)((c->N + tile - 1) / tile);
     const int n_launch = (int)((c->p1 + tile - 1) / tile) - a.tile0;
     a.nus = c->nus.as<double>(); a.line_idx = c->line_idx.as<int>(); a.rec = c->rec.as<LineRec>();
-    a.win_lo = c->win_lo.as<int>(); a.win_hi = c->win_hi.as<int>(); a.win_cls = c->win_cls.as<uint8_t>();
+    a.win = c->win.as<PairWin>();
     a.cls_list = c->cls_list.as<int>(); a.cls_off = c->cls_off.as<int>();
     a.fg = c->far_geom;
     a.out = c->alpha_line[slot].as<double>();
@@ -597,9 +697,22 @@ int sd_k2_lines(sd_ctx *c, int slot) {
             SD_TRY(sd_ensure(c, c->far_coef[k], sizeof(double) * c->D * a.far_ntl[k] * (SD_FAR_K + 1)));
             a.far_coef[k] = c->far_coef[k].as<double>();
         }
+        constexpr int TOP_SPLIT = 8;
+        if (!c->far_attr_set) {  // per device: > 48 KB of dynamic shared memory needs the opt-in
+            SD_CUDA(c, cudaFuncSetAttribute(k_far_coeffs, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FAR_SMEM));
+            c->far_attr_set = true;
+        }
+        SD_TRY(sd_ensure(c, c->far_part, sizeof(double) * c->D * a.far_ntl[SD_FAR_LEVELS - 1] * TOP_SPLIT * (SD_FAR_K + 1)));
         for (int k = SD_FAR_LEVELS - 1; k >= 0; k--) {
-            k_far_coeffs<<<dim3((unsigned)a.far_ntl[k], (unsigned)c->D), THREADS, 0, c->stream>>>(a, k, c->line_stats ? 1 : 0);
+            const int nsplit = (k == SD_FAR_LEVELS - 1) ? TOP_SPLIT : 1;
+            k_far_coeffs<<<dim3((unsigned)(a.far_ntl[k] * nsplit), (unsigned)c->D), THREADS, FAR_SMEM, c->stream>>>(
+                a, k, c->line_stats ? 1 : 0, nsplit, c->far_part.as<double>());
             SD_TRY(sd_launch_check(c, "k_far_coeffs"));
+            if (nsplit > 1) {
+                const int n = c->D * a.far_ntl[k] * (SD_FAR_K + 1);
+                k_far_reduce<<<(n + 255) / 256, 256, 0, c->stream>>>(n, nsplit, c->far_part.as<double>(), a.far_coef[k]);
+                SD_TRY(sd_launch_check(c, "k_far_reduce"));
+            }
         }
     }
     dim3 grid((unsigned)n_launch, (unsigned)c->D);

@@ -10,15 +10,26 @@
 
 // ---- K2 line-record layout (device global memory, depth-major: rec[d * L + l]) ----------------------
 struct __align__(16) LineRec {
+    // first 32 bytes: everything the far-field expansion needs (staged with two 16-byte async copies)
     double nu;      // line frequency
-    double inv_dw;  // 1 / doppler width
     double dw;      // doppler width (exact division in the near-core path)
     double y;       // (gamma / (sqrt(pi) pi)) / dw            voigt.py:148
     double K;       // alpha_line / (sqrt(pi) dw)              voigt.py:149, base.py:627
+    double inv_dw;  // 1 / doppler width
     double thr;     // x^2 above which the pixel is certainly Humlicek region I (or -1: always)
     double pad0, pad1;
 };
 static_assert(sizeof(LineRec) == 64, "LineRec must be 64 bytes");
+
+// ---- per-(depth, line) window record: everything the candidate tests of k_lines / k_far_coeffs need, in ONE 32-byte
+// sector (one gather per candidate instead of one per array)
+struct __align__(16) PairWin {
+    int lo, hi;         // window [lo, hi) in global pixels (base.py:563-592 semantics, see sdm::line_window)
+    unsigned near[3];   // per hierarchy level: tiles [lo16, hi16) around the line centre that are NOT far
+    int cls;            // half-width class (0..6) or SD_FC_CLASS
+    int pad0, pad1;
+};
+static_assert(sizeof(PairWin) == 32, "PairWin must be 32 bytes");
 
 constexpr int SD_NCLS = 8;          // half-width classes
 constexpr int SD_CLS0_HW = 64;      // class 0: hw <= 64; class k: hw <= 64 * 4^k; last class: everything wider
@@ -28,6 +39,7 @@ constexpr int SD_FAR_K = 20;            // polynomial degree (21 coefficients)
 constexpr double SD_FAR_RHO_INV = 4.0;  // a (line, depth) pair is expanded only if |nu_c - pole| >= 4 h
 constexpr int SD_FAR_LEVELS = 3;        // tile hierarchy: level k tiles hold 256 * P * 8^k pixels
 constexpr int SD_FAR_SHIFT = 3;         // log2 of the branching factor
+static_assert(SD_FAR_LEVELS == 3, "PairWin::near holds three levels");
 constexpr int SD_FC_CLASS = SD_NCLS - 1;  // class of the "far-capable" pairs (window >= one level-0 tile, finite parameters)
 
 // geometry of the far-field tile hierarchy and the per-pair tables that drive it, passed by value to the kernels
@@ -35,7 +47,7 @@ struct FarGeom {
     int tile[SD_FAR_LEVELS];            // pixels per tile
     int n_tiles[SD_FAR_LEVELS];         // global number of tiles
     const double *geom[SD_FAR_LEVELS];  // {centre frequency, half-width} per tile
-    unsigned *near[SD_FAR_LEVELS];      // per (depth, line): tiles [lo16, hi16) that are NOT far; nullptr = far field off
+    int enabled;                        // far field on (PairWin::near is filled, edge lists exist)
     int *near_rad;                      // [SD_FAR_LEVELS] largest half-extent (in tiles) of any near interval
     // far-capable pairs sorted by the position of their window edges (per depth: entries [d L, (d+1) L)); keys are
     // (depth << 32 | pixel), pixel = 0x7fffffff when the pair has no such edge inside the grid
@@ -80,8 +92,7 @@ struct sd_ctx {
     // K2 preparation
     DevBuf line_idx;   // int32 [L]
     DevBuf rec;        // LineRec [D*L]
-    DevBuf win_lo;     // int32 [D*L]
-    DevBuf win_hi;     // int32 [D*L]
+    DevBuf win;        // PairWin [D*L]
     DevBuf win_cls;    // uint8 [D*L]
     DevBuf cls_list;   // int32 [D*L]   per depth: lines of class 1.. concatenated by class (stable in l)
     DevBuf cls_off;    // int32 [D*(NCLS+1)] offsets into cls_list row d (class 0 is not listed)
@@ -90,13 +101,14 @@ struct sd_ctx {
     DevBuf near_rad;                   // int [SD_FAR_LEVELS]
     DevBuf edge_keys[2], edge_l[2];    // sorted (depth, edge pixel) keys / line indices: [0] window starts, [1] window ends
     DevBuf edge_tmp_keys, edge_tmp_l, edge_sort_tmp;
-    DevBuf near_tiles[SD_FAR_LEVELS];  // uint32 [D*L]: tiles [lo16, hi16) around the line centre that are not far
     DevBuf tile_geom[SD_FAR_LEVELS];   // double [2 * n_tiles]: centre frequency and half-width of every global tile
     DevBuf far_coef[SD_FAR_LEVELS];    // double [D * n_tiles_shard * (SD_FAR_K + 1)]
+    DevBuf far_part;                   // partial top-level coefficient sets (8 slices of the pair list per tile)
     FarGeom far_geom{};
     int k2_P = 4;      // pixels per thread chosen for the current grid
     int k2_NW = 8;     // warps per CTA of the line kernel (level-0 tile = 32 * k2_NW * k2_P pixels)
     bool farfield = true;
+    bool far_attr_set = false;  // dynamic shared memory opt-in of k_far_coeffs done on this device
     DevBuf alpha_line[2];
     bool have_alpha[2] = {false, false};
     bool records_ready = false;

@@ -20,6 +20,43 @@ def all_shards(n, world_size):
     return [shard_bounds(n, r, world_size) for r in range(world_size)]
 
 
+def line_balanced_bounds(tracing_nus, line_nus, world_size, line_weight=4.0, align=512):
+    """Contiguous pixel ranges of (nearly) equal COST instead of equal width.
+
+    With the far-field evaluation of the line wings the work of a pixel range is no longer proportional to its width:
+    what remains per range is a per-pixel part (polynomial evaluation, continuum, formal solution) plus the directly
+    evaluated line cores, which follow the number of lines whose centre lies in the range -- and a grid that is uniform
+    in wavelength holds an order of magnitude more lines per pixel at its blue end.  cost(range) = pixels +
+    ``line_weight`` * lines inside (one line core costs about four pixels on a B200; measured with
+    tools/shard_probe.py).  Cuts are multiples of ``align`` pixels (the level-0 tile of the line kernel) so that no
+    tile is evaluated by two ranks.  Every rank computes the same list from the same inputs; pass it to
+    ``allgather_spectrum(..., bounds=...)``."""
+    nus = np.asarray(tracing_nus, dtype=np.float64)
+    n, world_size = int(nus.shape[0]), int(world_size)
+    if world_size <= 1:
+        return [(0, n)]
+    line_nus = np.asarray(line_nus, dtype=np.float64)
+    if n >= 2 and nus[0] > nus[-1]:  # descending grid: position from the other end
+        pos = n - np.searchsorted(nus[::-1], line_nus, side="left")
+    else:
+        pos = np.searchsorted(nus, line_nus, side="left")
+    pos = pos[(pos > 0) & (pos < n)] if line_nus.size else np.zeros(0, dtype=np.int64)
+    align = max(1, min(int(align), n // (8 * world_size)))  # short grids: finer cuts rather than empty ranges
+    cuts = np.arange(0, n, align, dtype=np.int64)
+    cuts = np.append(cuts, n)  # candidate cut positions (aligned) and the end of the grid
+    lines_below = np.searchsorted(np.sort(pos), cuts, side="left")
+    cost = cuts.astype(np.float64) + float(line_weight) * lines_below
+    bounds, prev = [], 0
+    for r in range(1, world_size):
+        k = int(np.searchsorted(cost, cost[-1] * r / world_size, side="left"))
+        cut = int(cuts[min(max(k, 0), len(cuts) - 1)])
+        cut = min(max(cut, prev), n)
+        bounds.append((prev, cut))
+        prev = cut
+    bounds.append((prev, n))
+    return bounds
+
+
 def dist_info():
     try:
         import torch.distributed as dist
@@ -30,9 +67,10 @@ def dist_info():
     return None, 0, 1
 
 
-def allgather_spectrum(local, shard, n_total, device=None):
+def allgather_spectrum(local, shard, n_total, device=None, bounds=None):
     """Every rank contributes its (W_r,) slice of a length-``n_total`` vector; returns the full vector on every rank.
-    ``local`` may be a numpy array or a torch tensor (CUDA tensors are gathered with NCCL without touching the host)."""
+    ``local`` may be a numpy array or a torch tensor (CUDA tensors are gathered with NCCL without touching the host).
+    ``bounds``: the partition [(p0, p1)] * world all ranks agreed on (default: equal widths, ``all_shards``)."""
     import torch
 
     dist, rank, world = dist_info()
@@ -41,9 +79,9 @@ def allgather_spectrum(local, shard, n_total, device=None):
         if out.shape[0] != n_total:
             raise ValueError("a sharded result needs an initialised process group to be gathered")
         return out
-    bounds = all_shards(n_total, world)
+    bounds = _checked_bounds(bounds, n_total, world)
     if tuple(bounds[rank]) != tuple(int(x) for x in shard):
-        raise ValueError(f"rank {rank}: shard {shard} does not match the balanced partition {bounds[rank]}")
+        raise ValueError(f"rank {rank}: shard {shard} does not match the partition {bounds[rank]}")
     is_tensor = isinstance(local, torch.Tensor)
     t = local if is_tensor else torch.from_numpy(np.ascontiguousarray(local, dtype=np.float64))
     if device is not None:
@@ -58,7 +96,18 @@ def allgather_spectrum(local, shard, n_total, device=None):
     return full if is_tensor else full.cpu().numpy()
 
 
-def allgather_columns(local, shard, n_total):
+def _checked_bounds(bounds, n_total, world):
+    if bounds is None:
+        return all_shards(n_total, world)
+    bounds = [(int(a), int(b)) for a, b in bounds]
+    ok = len(bounds) == world and bounds[0][0] == 0 and bounds[-1][1] == n_total
+    ok = ok and all(a <= b for a, b in bounds) and all(bounds[i][1] == bounds[i + 1][0] for i in range(world - 1))
+    if not ok:
+        raise ValueError(f"{bounds} is not a contiguous partition of [0, {n_total}) into {world} ranges")
+    return bounds
+
+
+def allgather_columns(local, shard, n_total, bounds=None):
     """(D, W_r) column blocks -> (D, n_total) on every rank (used for F_nu / total_alphas when the caller wants the
     whole radiation field)."""
     import torch
@@ -69,7 +118,7 @@ def allgather_columns(local, shard, n_total):
     is_tensor = isinstance(local, torch.Tensor)
     t = local if is_tensor else torch.from_numpy(np.ascontiguousarray(local, dtype=np.float64))
     D = t.shape[0]
-    bounds = all_shards(n_total, world)
+    bounds = _checked_bounds(bounds, n_total, world)
     wmax = max(b - a for a, b in bounds)
     padded = torch.zeros((D, wmax), dtype=torch.float64, device=t.device)
     padded[:, : t.shape[1]] = t

@@ -6,6 +6,7 @@ import logging
 
 import numpy as np
 
+from .. import units as u
 from .opacities import Opacities
 from .opacities.opacities_solvers import calc_alphas
 from .radiation_field_solvers import raytrace
@@ -23,12 +24,13 @@ class RadiationField:
     ``F_nu`` / ``I_nus`` are allocated lazily (zeros) and replaced by device-backed arrays by ``raytrace``.
 
     B200 additions: ``device_context`` (None = the process-wide context of cuda:0) and ``shard`` = (p0, p1), the
-    pixel range of the global grid this rank evaluates (None = everything)."""
+    pixel range of the global grid this rank evaluates (None = everything); ``shard_bounds`` = the partition of all
+    ranks when it is not the equal-width one (``distributed.line_balanced_bounds``)."""
 
     hdf_properties = ["frequencies", "opacities", "F_nu"]
 
     def __init__(self, frequencies, source_function, stellar_model, num_of_thetas, track_individual_intensities=False,
-                 device_context=None, shard=None):
+                 device_context=None, shard=None, shard_bounds=None):
         self.frequencies = frequencies
         self.source_function = source_function
         self.opacities = Opacities(frequencies, stellar_model)
@@ -43,6 +45,7 @@ class RadiationField:
         self._I_nus = None
         self.device_context = device_context
         self.shard = shard
+        self.shard_bounds = shard_bounds
         self.token = next(_tokens)
 
     @property
@@ -69,11 +72,29 @@ class RadiationField:
 
 
 def create_stellar_radiation_field(tracing_nus, stellar_model, stellar_plasma, config, device_context=None, shard=None):
-    """radiation_field/base.py:71-117: RadiationField -> calc_alphas -> raytrace."""
+    """radiation_field/base.py:71-117: RadiationField -> calc_alphas -> raytrace.
+
+    ``shard="auto"``: inside an initialised torch.distributed job every rank takes its range of the cost-balanced
+    partition (``distributed.line_balanced_bounds`` over the lines the run uses)."""
+    shard_bounds = None
+    if isinstance(shard, str):
+        if shard != "auto":
+            raise ValueError("shard must be None, (p0, p1) or 'auto'")
+        from ..distributed import dist_info, line_balanced_bounds
+
+        _, rank, world = dist_info()
+        shard = None
+        if world > 1:
+            from .opacities.opacities_solvers.base import select_lines
+
+            line_nus = ([] if config.opacity.line.disable
+                        else select_lines(stellar_plasma, stellar_model, tracing_nus, config.opacity.line).nu)
+            shard_bounds = line_balanced_bounds(u.values_of(tracing_nus), line_nus, world)
+            shard = shard_bounds[rank]
     stellar_radiation_field = RadiationField(
         tracing_nus, blackbody_flux_at_nu, stellar_model, config.no_of_thetas,
         track_individual_intensities=config.result_options.return_radiation_field,
-        device_context=device_context, shard=shard)
+        device_context=device_context, shard=shard, shard_bounds=shard_bounds)
     logger.info("Calculating alphas")
     calc_alphas(stellar_plasma=stellar_plasma, stellar_model=stellar_model,
                 stellar_radiation_field=stellar_radiation_field, opacity_config=config.opacity,

@@ -395,7 +395,7 @@ import os, sys
 import numpy as np
 import torch.distributed as dist
 sys.path.insert(0, {root!r})
-from stardis_b200.distributed import shard_bounds, allgather_spectrum, allgather_columns
+from stardis_b200.distributed import shard_bounds, allgather_spectrum, allgather_columns, line_balanced_bounds
 rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
 dist.init_process_group("gloo", init_method="tcp://127.0.0.1:{port}", rank=rank, world_size=world)
 N, D = 1001, 5
@@ -407,6 +407,20 @@ mat = allgather_columns(np.ascontiguousarray(cols[:, p0:p1]), (p0, p1), N)
 ok = np.array_equal(spec, full) and np.array_equal(mat, cols)
 try:
     allgather_spectrum(full[p0:p1 - 1].copy(), (p0, p1 - 1), N)
+    ok = False
+except ValueError:
+    pass
+# unequal, cost-balanced ranges: twice as many lines per pixel in the first quarter of the grid
+nus = np.linspace(9.0e14, 3.0e14, N)
+line_nus = np.concatenate([np.linspace(8.9e14, 7.5e14, 600), np.linspace(7.4e14, 3.1e14, 300)])
+bounds = line_balanced_bounds(nus, line_nus, world, align=16)
+q0, q1 = bounds[rank]
+ok = ok and (bounds[0][1] - bounds[0][0]) < (bounds[1][1] - bounds[1][0])
+spec = allgather_spectrum(full[q0:q1].copy(), (q0, q1), N, bounds=bounds)
+mat = allgather_columns(np.ascontiguousarray(cols[:, q0:q1]), (q0, q1), N, bounds=bounds)
+ok = ok and np.array_equal(spec, full) and np.array_equal(mat, cols)
+try:
+    allgather_spectrum(full[q0:q1].copy(), (q0, q1), N, bounds=[(0, 10), (20, N)])
     ok = False
 except ValueError:
     pass
@@ -424,6 +438,20 @@ def test_nu_shards_gather_to_the_full_spectrum_gloo_world2(tmp_path):
         assert b[0][0] == 0 and b[-1][1] == n and all(b[i][1] == b[i + 1][0] for i in range(w - 1))
         assert max(q - p for p, q in b) - min(q - p for p, q in b) <= 1
         assert shard_bounds(n, w - 1, w) == b[-1]
+    from stardis_b200.distributed import line_balanced_bounds
+
+    lam = np.arange(3000, 10000, 0.01)
+    nus = 2.99792458e18 / lam
+    line_nus = np.random.default_rng(5).uniform(nus.min(), nus.max(), 50000)
+    idx = len(nus) - np.searchsorted(nus[::-1], line_nus)
+    for w in (1, 2, 8):
+        b = line_balanced_bounds(nus, line_nus, w, line_weight=4.0, align=512)
+        assert b[0][0] == 0 and b[-1][1] == len(nus) and all(b[i][1] == b[i + 1][0] for i in range(w - 1))
+        assert all(p % 512 == 0 for p, _ in b)
+        cost = [(q - p) + 4.0 * ((idx >= p) & (idx < q)).sum() for p, q in b]
+        assert max(cost) - min(cost) <= 2 * (512 + 4.0 * 512 * 50000 / len(nus) * 12)  # within about one cut of equal
+    assert line_balanced_bounds(nus, np.zeros(0), 3) == [(0, 233472), (233472, 466944), (466944, 700000)]
+    assert all(q > p for p, q in line_balanced_bounds(nus[:100], line_nus, 4))
     script = tmp_path / "worker.py"
     port = 29500 + os.getpid() % 2000
     script.write_text(_WORKER.format(root=ROOT, port=port))
