@@ -73,15 +73,32 @@ SD_HD double region1_re(double q, double y) {
     return INV_SQRT_PI * y * (q + c1) / den;
 }
 
-// Regions II-IV in real arithmetic.  t = y - i x (voigt.py:33), u = t^2.
+// Literal constants of regions II-IV and of exp_cos_small.  An fp64 literal costs two UMOV instructions at every use
+// (no 64-bit immediates); from a __constant__ table two of them arrive with one LDCU.128 and stay in uniform registers.
+enum W4Const { K_R3_A4, K_R3_A3, K_R3_A2, K_R3_A1, K_R3_A0, K_R3_B4, K_R3_B3, K_R3_B2, K_R3_B1, K_R4_P6, K_R4_P5, K_R4_P4, K_R4_P3, K_R4_P2, K_R4_P1, K_R4_P0, K_R4_Q6, K_R4_Q5, K_R4_Q4, K_R4_Q3, K_R4_Q2, K_R4_Q1, K_R4_Q0, K_R2_C, K_LOG2E, K_LN2_HI, K_LN2_LO, K_E13, K_E12, K_E11, K_E10, K_E9, K_E8, K_E7, K_E6, K_E5, K_E4, K_E3, K_TWO_OVER_PI, K_PIO2_HI, K_PIO2_LO, K_S6, K_S5, K_S4, K_S3, K_S2, K_S1, K_C6, K_C5, K_C4, K_C3, K_C2, K_C1, K_COUNT };
+#define SD_W4_VALUES { 0.5642236, 3.778987, 11.96482, 20.20933, 16.4955, 6.699398, 21.69274, 39.27121, 38.82363, 0.56419, 1.320522, 35.7668, 219.031, 1540.787, 3321.99, 36183.31, 1.84144, 61.5704, 364.219, 2186.18, 9022.23, 24322.8, 32066.6, 1.4104739589, 1.4426950408889634, 0.6931471805599453, 2.3190468138462996e-17, 1.6059043836821613e-10, 2.08767569878681e-09, 2.505210838544172e-08, 2.755731922398589e-07, 2.7557319223985893e-06, 2.48015873015873e-05, 0.0001984126984126984, 0.001388888888888889, 0.008333333333333333, 0.041666666666666664, 0.16666666666666666, 0.6366197723675814, 1.5707963267948966, 6.123233995736766e-17, 1.58969099521155010221e-10, -2.50507602534068634195e-08, 2.75573137070700676789e-06, -1.98412698298579493134e-04, 8.33333333332248946124e-03, -1.66666666666666324348e-01, -1.13596475577881948265e-11, 2.08757232129817482790e-09, -2.75573143513906633035e-07, 2.48015872894767294178e-05, -1.38888888888741095749e-03, 4.16666666666666019037e-02 }
+#if defined(__CUDACC__)
+static __constant__ double W4_TABLE_DEV[K_COUNT] = SD_W4_VALUES;
+#endif
+constexpr double W4_TABLE_HOST[K_COUNT] = SD_W4_VALUES;
+#if defined(__CUDA_ARCH__)
+#define W4K(name) (sdm::W4_TABLE_DEV[sdm::K_##name])
+#else
+#define W4K(name) (sdm::W4_TABLE_HOST[sdm::K_##name])
+#endif
+
+// Regions II-IV in real arithmetic.  t = y - i x (voigt.py:33), u = t^2.  The complex Horner steps are written as
+// fused multiply-adds (4 instructions per step) and the final complex quotient uses the ~1 ulp reciprocal above: the
+// results differ from a complex128 evaluation by rounding only (the W4 polynomials are evaluated with some
+// cancellation, so "rounding" here means up to ~1e-13 relative, five orders inside the 1e-8 parity tolerance).
 SD_HD double region2_re(double x, double y) {
     // w = i z (z^2/sqrt(pi) - 1.4104739589) / (0.75 + z^2 (z^2 - 3))  ->  Re w = -Im(N/Dn)
-    double qr = x * x - y * y, qi = 2.0 * x * y;
-    double pr = qr / SQRT_PI - 1.4104739589, pi_ = qi / SQRT_PI;
-    double nr = x * pr - y * pi_, ni = x * pi_ + y * pr;
+    double qr = fma(x, x, -(y * y)), qi = (x + x) * y;
+    double pr = fma(qr, INV_SQRT_PI, -W4K(R2_C)), pi_ = qi * INV_SQRT_PI;
+    double nr = fma(x, pr, -(y * pi_)), ni = fma(x, pi_, y * pr);
     double er = qr - 3.0;
-    double dr = 0.75 + (qr * er - qi * qi), di = qr * qi + qi * er;
-    return (nr * di - ni * dr) / (dr * dr + di * di);
+    double dr = fma(qr, er, fma(-qi, qi, 0.75)), di = qi * (qr + er);
+    return fma(nr, di, -(ni * dr)) * rcp_fast(fma(dr, dr, di * di));
 }
 
 SD_HD void cmul_add(double &ar, double &ai, double tr, double ti, double c) {
@@ -94,45 +111,101 @@ SD_HD void cmul_add(double &ar, double &ai, double tr, double ti, double c) {
 
 SD_HD double region3_re(double x, double y) {
     double tr = y, ti = -x;
-    double nr = fma(0.5642236, tr, 3.778987), ni = 0.5642236 * ti;
-    cmul_add(nr, ni, tr, ti, 11.96482);
-    cmul_add(nr, ni, tr, ti, 20.20933);
-    cmul_add(nr, ni, tr, ti, 16.4955);
-    double dr = tr + 6.699398, di = ti;
-    cmul_add(dr, di, tr, ti, 21.69274);
-    cmul_add(dr, di, tr, ti, 39.27121);
-    cmul_add(dr, di, tr, ti, 38.82363);
-    cmul_add(dr, di, tr, ti, 16.4955);
-    return (nr * dr + ni * di) / (dr * dr + di * di);
+    double nr = fma(W4K(R3_A4), tr, W4K(R3_A3)), ni = W4K(R3_A4) * ti;
+    cmul_add(nr, ni, tr, ti, W4K(R3_A2));
+    cmul_add(nr, ni, tr, ti, W4K(R3_A1));
+    cmul_add(nr, ni, tr, ti, W4K(R3_A0));
+    double dr = tr + W4K(R3_B4), di = ti;
+    cmul_add(dr, di, tr, ti, W4K(R3_B3));
+    cmul_add(dr, di, tr, ti, W4K(R3_B2));
+    cmul_add(dr, di, tr, ti, W4K(R3_B1));
+    cmul_add(dr, di, tr, ti, W4K(R3_A0));
+    return fma(nr, dr, ni * di) * rcp_fast(fma(dr, dr, di * di));
 }
 
 SD_HD void cmul_rsub(double &ar, double &ai, double ur, double ui, double c) {
     // (ar + i ai) <- c - u (ar + i ai)
-    double r = c - (ur * ar - ui * ai);
-    double i = -(ur * ai + ui * ar);
+    double r = fma(ui, ai, fma(-ur, ar, c));
+    double i = fma(-ur, ai, -(ui * ar));
     ar = r;
     ai = i;
 }
 
+// 2^n for -1022 <= n <= 1023
+SD_HD double pow2i(int n) {
+#if defined(__CUDA_ARCH__)
+    return __hiloint2double((1023 + n) << 20, 0);
+#else
+    return ldexp(1.0, n);
+#endif
+}
+
+// exp(a) cos(b) for the arguments region IV produces (-31 < a < 1, |b| < 11; NaN in -> NaN out).  The library
+// routines carry range checks, a table and a large-argument branch that this range never needs: here exp is
+// 2^n e^r (|r| <= ln2/2, Taylor to r^13, truncation 4e-18) and cos is a two-constant Cody-Waite reduction by pi/2
+// (|k| <= 7) with the fdlibm kernel polynomials, both evaluated without a branch (~45 instructions instead of ~115).
+SD_HD double exp_cos_small(double a, double b) {
+    const double nf = rint(a * W4K(LOG2E));
+    double r = fma(-nf, W4K(LN2_HI), a);
+    r = fma(-nf, W4K(LN2_LO), r);
+    double p = W4K(E13);          // 1/13!
+    p = fma(p, r, W4K(E12));
+    p = fma(p, r, W4K(E11));
+    p = fma(p, r, W4K(E10));
+    p = fma(p, r, W4K(E9));
+    p = fma(p, r, W4K(E8));
+    p = fma(p, r, W4K(E7));
+    p = fma(p, r, W4K(E6));
+    p = fma(p, r, W4K(E5));
+    p = fma(p, r, W4K(E4));
+    p = fma(p, r, W4K(E3));          // ... 1/3!
+    p = fma(p, r, 0.5);
+    p = fma(p, r, 1.0);
+    p = fma(p, r, 1.0);
+    const double ea = p * pow2i((int)nf);
+    const double kf = rint(b * W4K(TWO_OVER_PI));
+    double t = fma(-kf, W4K(PIO2_HI), b);
+    t = fma(-kf, W4K(PIO2_LO), t);
+    const double z = t * t;
+    double sp = W4K(S6);
+    sp = fma(sp, z, W4K(S5));
+    sp = fma(sp, z, W4K(S4));
+    sp = fma(sp, z, W4K(S3));
+    sp = fma(sp, z, W4K(S2));
+    sp = fma(sp, z, W4K(S1));
+    const double sn = fma(t * z, sp, t);
+    double cp = W4K(C6);
+    cp = fma(cp, z, W4K(C5));
+    cp = fma(cp, z, W4K(C4));
+    cp = fma(cp, z, W4K(C3));
+    cp = fma(cp, z, W4K(C2));
+    cp = fma(cp, z, W4K(C1));
+    const double cs = fma(z * z, cp, fma(-0.5, z, 1.0));
+    const int k = (int)kf;
+    double c = (k & 1) ? sn : cs;              // cos(t + k pi/2): cos t, -sin t, -cos t, sin t
+    if (((k + 1) >> 1) & 1) c = -c;
+    return ea * c;
+}
+
 SD_HD double region4_re(double x, double y) {
     double tr = y, ti = -x;
-    double ur = y * y - x * x, ui = -2.0 * x * y;
-    double pr = 1.320522 - ur * 0.56419, pi_ = -ui * 0.56419;
-    cmul_rsub(pr, pi_, ur, ui, 35.7668);
-    cmul_rsub(pr, pi_, ur, ui, 219.031);
-    cmul_rsub(pr, pi_, ur, ui, 1540.787);
-    cmul_rsub(pr, pi_, ur, ui, 3321.99);
-    cmul_rsub(pr, pi_, ur, ui, 36183.31);
-    double nr = tr * pr - ti * pi_, ni = tr * pi_ + ti * pr;
-    double qr = 1.84144 - ur, qi = -ui;
-    cmul_rsub(qr, qi, ur, ui, 61.5704);
-    cmul_rsub(qr, qi, ur, ui, 364.219);
-    cmul_rsub(qr, qi, ur, ui, 2186.18);
-    cmul_rsub(qr, qi, ur, ui, 9022.23);
-    cmul_rsub(qr, qi, ur, ui, 24322.8);
-    cmul_rsub(qr, qi, ur, ui, 32066.6);
-    double quot = (nr * qr + ni * qi) / (qr * qr + qi * qi);
-    return exp(ur) * cos(ui) - quot;
+    double ur = fma(y, y, -(x * x)), ui = -(x + x) * y;
+    double pr = fma(-ur, W4K(R4_P6), W4K(R4_P5)), pi_ = -ui * W4K(R4_P6);
+    cmul_rsub(pr, pi_, ur, ui, W4K(R4_P4));
+    cmul_rsub(pr, pi_, ur, ui, W4K(R4_P3));
+    cmul_rsub(pr, pi_, ur, ui, W4K(R4_P2));
+    cmul_rsub(pr, pi_, ur, ui, W4K(R4_P1));
+    cmul_rsub(pr, pi_, ur, ui, W4K(R4_P0));
+    double nr = fma(tr, pr, -(ti * pi_)), ni = fma(tr, pi_, ti * pr);
+    double qr = W4K(R4_Q6) - ur, qi = -ui;
+    cmul_rsub(qr, qi, ur, ui, W4K(R4_Q5));
+    cmul_rsub(qr, qi, ur, ui, W4K(R4_Q4));
+    cmul_rsub(qr, qi, ur, ui, W4K(R4_Q3));
+    cmul_rsub(qr, qi, ur, ui, W4K(R4_Q2));
+    cmul_rsub(qr, qi, ur, ui, W4K(R4_Q1));
+    cmul_rsub(qr, qi, ur, ui, W4K(R4_Q0));
+    double quot = fma(nr, qr, ni * qi) * rcp_fast(fma(qr, qr, qi * qi));
+    return exp_cos_small(ur, ui) - quot;
 }
 
 // Region index 0..3 with the reference's comparisons and order (voigt.py:37-44).
@@ -175,34 +248,34 @@ SD_HD void humlicek_complex(double x, double y, double &wr, double &wi) {
         wr = -fi;
         wi = fr;
     } else if (reg == 2) {
-        double nr = fma(0.5642236, tr, 3.778987), ni = 0.5642236 * ti;
-        cmul_add(nr, ni, tr, ti, 11.96482);
-        cmul_add(nr, ni, tr, ti, 20.20933);
-        cmul_add(nr, ni, tr, ti, 16.4955);
-        double dr = tr + 6.699398, di = ti;
-        cmul_add(dr, di, tr, ti, 21.69274);
-        cmul_add(dr, di, tr, ti, 39.27121);
-        cmul_add(dr, di, tr, ti, 38.82363);
-        cmul_add(dr, di, tr, ti, 16.4955);
+        double nr = fma(W4K(R3_A4), tr, W4K(R3_A3)), ni = W4K(R3_A4) * ti;
+        cmul_add(nr, ni, tr, ti, W4K(R3_A2));
+        cmul_add(nr, ni, tr, ti, W4K(R3_A1));
+        cmul_add(nr, ni, tr, ti, W4K(R3_A0));
+        double dr = tr + W4K(R3_B4), di = ti;
+        cmul_add(dr, di, tr, ti, W4K(R3_B3));
+        cmul_add(dr, di, tr, ti, W4K(R3_B2));
+        cmul_add(dr, di, tr, ti, W4K(R3_B1));
+        cmul_add(dr, di, tr, ti, W4K(R3_A0));
         double den = dr * dr + di * di;
         wr = (nr * dr + ni * di) / den;
         wi = (ni * dr - nr * di) / den;
     } else {
         double ur = y * y - x * x, ui = -2.0 * x * y;
         double pr = 1.320522 - ur * 0.56419, pi_ = -ui * 0.56419;
-        cmul_rsub(pr, pi_, ur, ui, 35.7668);
-        cmul_rsub(pr, pi_, ur, ui, 219.031);
-        cmul_rsub(pr, pi_, ur, ui, 1540.787);
-        cmul_rsub(pr, pi_, ur, ui, 3321.99);
-        cmul_rsub(pr, pi_, ur, ui, 36183.31);
+        cmul_rsub(pr, pi_, ur, ui, W4K(R4_P4));
+        cmul_rsub(pr, pi_, ur, ui, W4K(R4_P3));
+        cmul_rsub(pr, pi_, ur, ui, W4K(R4_P2));
+        cmul_rsub(pr, pi_, ur, ui, W4K(R4_P1));
+        cmul_rsub(pr, pi_, ur, ui, W4K(R4_P0));
         double nr = tr * pr - ti * pi_, ni = tr * pi_ + ti * pr;
-        double qr = 1.84144 - ur, qi = -ui;
-        cmul_rsub(qr, qi, ur, ui, 61.5704);
-        cmul_rsub(qr, qi, ur, ui, 364.219);
-        cmul_rsub(qr, qi, ur, ui, 2186.18);
-        cmul_rsub(qr, qi, ur, ui, 9022.23);
-        cmul_rsub(qr, qi, ur, ui, 24322.8);
-        cmul_rsub(qr, qi, ur, ui, 32066.6);
+        double qr = W4K(R4_Q6) - ur, qi = -ui;
+        cmul_rsub(qr, qi, ur, ui, W4K(R4_Q5));
+        cmul_rsub(qr, qi, ur, ui, W4K(R4_Q4));
+        cmul_rsub(qr, qi, ur, ui, W4K(R4_Q3));
+        cmul_rsub(qr, qi, ur, ui, W4K(R4_Q2));
+        cmul_rsub(qr, qi, ur, ui, W4K(R4_Q1));
+        cmul_rsub(qr, qi, ur, ui, W4K(R4_Q0));
         double den = qr * qr + qi * qi;
         double e = exp(ur);
         wr = e * cos(ui) - (nr * qr + ni * qi) / den;
