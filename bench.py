@@ -241,7 +241,7 @@ def run_b200_arm(args):
     line_cfg = cfg.opacity.line
     nus_q = u.Quantity(nus, u.Hz)
     lines = ob.select_lines(plasma, model, nus_q, line_cfg)
-    # cost-balanced contiguous nu ranges (pixels + 4 x lines inside): the blue end of the grid holds ~10x more lines per
+    # cost-balanced contiguous nu ranges (pixels + 10 x lines inside): the blue end of the grid holds ~10x more lines per
     # pixel than the red end, so equal-width ranges would leave rank 0 with several times the line-core work
     bounds = line_balanced_bounds(nus, lines.nu, world)
     p0, p1 = bounds[rank]
@@ -422,7 +422,7 @@ def run_b200_arm(args):
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": desc, "l2": "inputs larger than L2 (line records %.2f GB, outputs %.2f GB per array)"
-                       % (len(sel) * D * 64 / 1e9, cells * 8 / 1e9), "partition": f"{world} contiguous nu range(s), global windows, cut at equal (pixels + 4 x lines inside)",
+                       % (len(sel) * D * 64 / 1e9, cells * 8 / 1e9), "partition": f"{world} contiguous nu range(s), global windows, cut at equal (pixels + 10 x lines inside)",
                        "ranges": [list(b) for b in bounds]},
             "roofline": {"kernel": "k_lines, direct mode (K2: every (line, depth, pixel) Voigt evaluation done explicitly, "
                                    "far-field expansion off)", "bound": "fp64", "achieved": achieved_tflops,

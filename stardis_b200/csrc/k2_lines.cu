@@ -44,6 +44,7 @@ constexpr int WARPS = THREADS / 32;
 constexpr int FAR_R = 8;                    // candidates per lane and scan round of k_far_coeffs
 constexpr int FAR_QCAP = 32 * (FAR_R + 1);  // per-warp queue: a carried remainder (< 32 pairs) plus one scan round
 struct __align__(16) FarRec { double nu, dw, y, K; };  // = the first 32 bytes of LineRec
+static_assert(WARPS == (1 << SD_FAR_SHIFT), "k_far_coeffs maps the warps of a CTA to the children of a tile");
 constexpr size_t FAR_SMEM = (size_t)WARPS * FAR_QCAP * sizeof(FarRec);
 
 struct __align__(16) WEntry {
@@ -179,8 +180,21 @@ __device__ __forceinline__ unsigned near_of(const PairWin &w, int lev) {  // no 
     return lev == 0 ? w.near[0] : (lev == 1 ? w.near[1] : w.near[2]);
 }
 
-__device__ __noinline__ double exact_contribution(double nu_i, double nu_l, double dw, double y, double K) {
-    double x = (nu_i - nu_l) / dw;  // voigt.py:148, IEEE division
+// x = (nu_i - nu_l) / dw (voigt.py:148) must be the correctly rounded quotient: the W4 regions are chosen by comparing
+// |x| + y with literals and the approximation jumps by ~1e-4 across a region boundary.  With the correctly rounded
+// reciprocal r = RN(1 / dw) stored per pair, q = RN(n r) followed by one residual step q + (n - dw q) r is the correctly
+// rounded quotient (Markstein) in 3 instead of ~25 instructions; pairs with dw <= 0, inf or NaN (thr is NaN for them)
+// keep the IEEE division so that their special values propagate exactly as in the reference.
+__device__ __noinline__ double exact_contribution(double nu_i, double nu_l, double dw, double inv_dw, double thr, double y,
+                                                  double K) {
+    const double n = nu_i - nu_l;
+    double x;
+    if (thr == thr) {
+        const double q = n * inv_dw;
+        x = fma(fma(-dw, q, n), inv_dw, q);
+    } else {
+        x = n / dw;
+    }
     return sdm::humlicek_re(x, y) * K;
 }
 
@@ -210,14 +224,23 @@ __global__ void __launch_bounds__(THREADS) k_far_coeffs(LineArgs a, int lev, int
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int d = blockIdx.y;
     const int tile_px = a.fg.tile[lev];
-    const int tile_local = blockIdx.x / nsplit, split = blockIdx.x - tile_local * nsplit;
-    const int tile = a.far_tile0[lev] + tile_local;
+    const bool has_parent = lev + 1 < SD_FAR_LEVELS;
+    const int plev = has_parent ? lev + 1 : lev;
+    // Levels >= 1: CTA = (tile, slice of the pair list), the warps share the candidates and their sums are reduced through
+    // shared memory.  Level 0 (many tiles, short candidate lists): CTA = parent tile, warp w = its child w -- the
+    // candidate ranges are a property of the PARENT, so they are searched once per CTA, every warp walks them for its own
+    // tile (the gathers of the eight warps meet in L1) and there is no CTA-wide barrier or reduction.  The mode is a
+    // function of the level only, so the summation order does not depend on the shard.
+    const bool per_child = has_parent && lev == 0;
+    const int tile_local = per_child ? 0 : blockIdx.x / nsplit, split = per_child ? 0 : blockIdx.x - tile_local * nsplit;
+    const int tile_w = per_child ? ((((a.far_tile0[lev] >> SD_FAR_SHIFT) + (int)blockIdx.x) << SD_FAR_SHIFT) + warp)
+                                 : a.far_tile0[lev] + tile_local;
+    const bool tile_ok = tile_w >= a.far_tile0[lev] && tile_w < a.far_tile0[lev] + a.far_ntl[lev];
+    const int tile = tile_ok ? tile_w : a.far_tile0[lev];
+    const int ptile = tile_w >> SD_FAR_SHIFT;
     const int64_t t0 = (int64_t)tile * tile_px;
     const int64_t t1 = (t0 + tile_px < a.N) ? t0 + tile_px : a.N;
     const double nu_c = a.fg.geom[lev][2 * tile], h = a.fg.geom[lev][2 * tile + 1];
-    const bool has_parent = lev + 1 < SD_FAR_LEVELS;
-    const int plev = has_parent ? lev + 1 : lev;
-    const int ptile = tile >> SD_FAR_SHIFT;
     const int64_t pt0 = (int64_t)ptile * a.fg.tile[plev];
     const int64_t pt1 = (pt0 + a.fg.tile[plev] < a.N) ? pt0 + a.fg.tile[plev] : a.N;
     const size_t drow = (size_t)d * a.L;
@@ -293,7 +316,9 @@ __global__ void __launch_bounds__(THREADS) k_far_coeffs(LineArgs a, int lev, int
     int qn = 0;  // queue length of this warp
     for (int src = 0; src < 3; src++) {
         const int ja = s_ja[src], jb = s_jb[src];
-        for (int base = ja + warp * (32 * FAR_R); base < jb; base += THREADS * FAR_R) {
+        const int first = per_child ? ja : ja + warp * (32 * FAR_R);
+        const int stride = per_child ? 32 * FAR_R : THREADS * FAR_R;
+        for (int base = first; base < jb && tile_ok; base += stride) {
             int l_r[FAR_R];
             unsigned m_r[FAR_R];
 #pragma unroll
@@ -347,20 +372,32 @@ __global__ void __launch_bounds__(THREADS) k_far_coeffs(LineArgs a, int lev, int
         }
     }
     if (qn > 0) expand(lane < qn, q[lane < qn ? lane : 0]);
-    // deterministic block reduction: lanes by shuffle, warps through shared memory in fixed order
+    // deterministic reduction: lanes by shuffle; shared candidates: warps through shared memory in fixed order
+    if (per_child) {
+        double mine = 0.0;
 #pragma unroll
-    for (int k = 0; k < K1; k++) {
-        double v = C[k];
-        for (int o2 = 16; o2; o2 >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o2);
-        if (lane == 0) s_red[warp][k] = v;
-    }
-    __syncthreads();
-    if (tid < K1) {
-        double v = 0.0;
+        for (int k = 0; k < K1; k++) {
+            double v = C[k];
+            for (int o2 = 16; o2; o2 >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o2);
+            if (lane == k) mine = v;
+        }
+        if (tile_ok && lane < K1)
+            a.far_coef[lev][((size_t)d * a.far_ntl[lev] + (tile - a.far_tile0[lev])) * K1 + lane] = mine;
+    } else {
 #pragma unroll
-        for (int w = 0; w < WARPS; w++) v += s_red[w][tid];
-        if (nsplit > 1) part[((size_t)d * gridDim.x + blockIdx.x) * K1 + tid] = v;
-        else a.far_coef[lev][((size_t)d * gridDim.x + blockIdx.x) * K1 + tid] = v;
+        for (int k = 0; k < K1; k++) {
+            double v = C[k];
+            for (int o2 = 16; o2; o2 >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o2);
+            if (lane == 0) s_red[warp][k] = v;
+        }
+        __syncthreads();
+        if (tid < K1) {
+            double v = 0.0;
+#pragma unroll
+            for (int w = 0; w < WARPS; w++) v += s_red[w][tid];
+            if (nsplit > 1) part[((size_t)d * gridDim.x + blockIdx.x) * K1 + tid] = v;
+            else a.far_coef[lev][((size_t)d * gridDim.x + blockIdx.x) * K1 + tid] = v;
+        }
     }
     if (count_stats) {  // every far pair stands for one region-I evaluation per tile pixel inside the shard
         for (int o2 = 16; o2; o2 >>= 1) n_far += __shfl_xor_sync(0xffffffffu, n_far, o2);
@@ -540,7 +577,7 @@ __global__ void __launch_bounds__(32 * NW, MINB) k_lines(LineArgs a) {
                                 double num = fma(Kf, q, Kc);
                                 v = num * (RCP == 2 ? sdm::rcp_fast2(den) : sdm::rcp_fast(den));
                             } else {
-                                v = exact_contribution(nu, e2.nu, e2.dw, e2.y, e2.K);
+                                v = exact_contribution(nu, e2.nu, e2.dw, inv_dw, thr, e2.y, e2.K);
                             }
                             s_acc[warp][k] += v;
                             if (STATS && pix >= p0 && pix < p1) {
@@ -564,7 +601,7 @@ __global__ void __launch_bounds__(32 * NW, MINB) k_lines(LineArgs a) {
                         double num = fma(Kf, q, Kc);
                         double v = num * (RCP == 2 ? sdm::rcp_fast2(den) : sdm::rcp_fast(den));
                         if (fast) acc[p] += v;
-                        if (inwin && !fast) acc[p] += exact_contribution(nu_i[p], e2.nu, e2.dw, e2.y, e2.K);
+                        if (inwin && !fast) acc[p] += exact_contribution(nu_i[p], e2.nu, e2.dw, inv_dw, thr, e2.y, e2.K);
                         if (STATS && inwin && pix >= p0 && pix < p1) {
                             int r = sdm::humlicek_region((nu_i[p] - e2.nu) / e2.dw, e2.y);
                             h0 += (r == 0); h1 += (r == 1); h2 += (r == 2); h3 += (r == 3);
@@ -705,7 +742,11 @@ int sd_k2_lines(sd_ctx *c, int slot) {
         SD_TRY(sd_ensure(c, c->far_part, sizeof(double) * c->D * a.far_ntl[SD_FAR_LEVELS - 1] * TOP_SPLIT * (SD_FAR_K + 1)));
         for (int k = SD_FAR_LEVELS - 1; k >= 0; k--) {
             const int nsplit = (k == SD_FAR_LEVELS - 1) ? TOP_SPLIT : 1;
-            k_far_coeffs<<<dim3((unsigned)(a.far_ntl[k] * nsplit), (unsigned)c->D), THREADS, FAR_SMEM, c->stream>>>(
+            // levels >= 1: tiles x slices; level 0: one CTA per parent tile that has a child in the launched range
+            const int n_cta = (k > 0 || SD_FAR_LEVELS == 1)
+                                  ? a.far_ntl[k] * nsplit
+                                  : ((a.far_tile0[k] + a.far_ntl[k] - 1) >> SD_FAR_SHIFT) - (a.far_tile0[k] >> SD_FAR_SHIFT) + 1;
+            k_far_coeffs<<<dim3((unsigned)n_cta, (unsigned)c->D), THREADS, FAR_SMEM, c->stream>>>(
                 a, k, c->line_stats ? 1 : 0, nsplit, c->far_part.as<double>());
             SD_TRY(sd_launch_check(c, "k_far_coeffs"));
             if (nsplit > 1) {

@@ -20,14 +20,14 @@ def all_shards(n, world_size):
     return [shard_bounds(n, r, world_size) for r in range(world_size)]
 
 
-def line_balanced_bounds(tracing_nus, line_nus, world_size, line_weight=4.0, align=512):
+def line_balanced_bounds(tracing_nus, line_nus, world_size, line_weight=10.0, align=512):
     """Contiguous pixel ranges of (nearly) equal COST instead of equal width.
 
     With the far-field evaluation of the line wings the work of a pixel range is no longer proportional to its width:
     what remains per range is a per-pixel part (polynomial evaluation, continuum, formal solution) plus the directly
     evaluated line cores, which follow the number of lines whose centre lies in the range -- and a grid that is uniform
     in wavelength holds an order of magnitude more lines per pixel at its blue end.  cost(range) = pixels +
-    ``line_weight`` * lines inside (one line core costs about four pixels on a B200; measured with
+    ``line_weight`` * lines inside (one line core costs about ten pixels on a B200; measured with
     tools/shard_probe.py).  Cuts are multiples of ``align`` pixels (the level-0 tile of the line kernel) so that no
     tile is evaluated by two ranks.  Every rank computes the same list from the same inputs; pass it to
     ``allgather_spectrum(..., bounds=...)``."""
