@@ -175,9 +175,20 @@ __global__ void __launch_bounds__(256) k_build_records(int64_t L, int D, int64_t
                     const double *__restrict__ geom = fg.geom[k];
                     int tc = (int)(line_idx[l] / tile);
                     if (tc >= n_tiles) tc = n_tiles - 1;
-                    int a_ = tc, b_ = tc + 1;
+                    // [a_, b_): tiles around the line centre that are not far.  Farness is monotone in the distance from
+                    // the centre (the centre distance grows by 2 h per tile, the required distance by at most ~0.5 h), so
+                    // the two boundaries are found from an estimate (required distance / tile spacing at the centre
+                    // tile) plus a short walk in either direction instead of a walk from the centre.
+                    const double h_c = geom[2 * tc + 1];
+                    const double m_c = 15.0000001 - y;
+                    const double need = fmax(SD_FAR_RHO_INV * h_c + 0.7071067811865476 * dw, h_c + (m_c > 0.0 ? m_c : 0.0) * dw);
+                    const double est = need / (2.0 * h_c);
+                    const int n_est = (est < (double)n_tiles) ? (int)est : n_tiles;  // NaN / inf -> the whole grid
+                    int a_ = max(tc - n_est, 0), b_ = min(tc + n_est + 1, n_tiles);
                     while (a_ > 0 && !tile_is_far(geom[2 * (a_ - 1)], geom[2 * (a_ - 1) + 1], r.nu, dw, y)) a_--;
+                    while (a_ < tc && tile_is_far(geom[2 * a_], geom[2 * a_ + 1], r.nu, dw, y)) a_++;
                     while (b_ < n_tiles && !tile_is_far(geom[2 * b_], geom[2 * b_ + 1], r.nu, dw, y)) b_++;
+                    while (b_ > tc + 1 && tile_is_far(geom[2 * (b_ - 1)], geom[2 * (b_ - 1) + 1], r.nu, dw, y)) b_--;
                     nl = (unsigned)a_;
                     nh = (unsigned)b_;
                     rad = max(tc - a_, b_ - 1 - tc);
@@ -185,9 +196,9 @@ __global__ void __launch_bounds__(256) k_build_records(int64_t L, int D, int64_t
                 pw.near[k] = nl | (nh << 16);
                 rad_k[k] = rad;
             }
-            const unsigned long long dkey = (unsigned long long)d << 32;
-            fg.lo_keys[o] = dkey | (unsigned long long)((fc && lo > 0) ? lo : 0x7fffffff);
-            fg.hi_keys[o] = dkey | (unsigned long long)((fc && hi < N) ? hi : 0x7fffffff);
+            const unsigned dkey = (unsigned)d << fg.key_shift, none = (1u << fg.key_shift) - 1u;
+            fg.lo_keys[o] = dkey | ((fc && lo > 0) ? (unsigned)lo : none);
+            fg.hi_keys[o] = dkey | ((fc && hi < N) ? (unsigned)hi : none);
             fg.lo_l[o] = (int)l;
         }
         win[o] = pw;
@@ -327,6 +338,7 @@ int sd_k2_prepare(sd_ctx *c) {
     }
     fg.near_rad = nullptr;
     fg.enabled = 0;
+    fg.key_shift = 0;
     fg.lo_keys = fg.hi_keys = nullptr;
     fg.lo_l = fg.hi_l = nullptr;
     if (L == 0) {
@@ -341,18 +353,25 @@ int sd_k2_prepare(sd_ctx *c) {
     SD_TRY(sd_ensure(c, c->cls_list, sizeof(int) * n));
     if (c->farfield) {
         fg.enabled = 1;
+        int pix_bits = 1, depth_bits = 1;
+        while ((1LL << pix_bits) <= c->N) pix_bits++;
+        while ((1 << depth_bits) < D) depth_bits++;
+        SD_CHECK(c, pix_bits + depth_bits <= 32, SD_ERR_ARG,
+                 "far-field scheme: (depth, pixel) does not fit a 32-bit sort key (D = %d, N = %lld); use sd_set_farfield(ctx, 0)",
+                 D, (long long)c->N);
+        fg.key_shift = pix_bits;
         SD_TRY(sd_ensure(c, c->near_rad, sizeof(int) * SD_FAR_LEVELS));
         SD_CUDA(c, cudaMemsetAsync(c->near_rad.p, 0, sizeof(int) * SD_FAR_LEVELS, c->stream));
         fg.near_rad = c->near_rad.as<int>();
         // unsorted keys go to the temporaries (window starts) / to edge_keys[1] (window ends, sorted second)
-        SD_TRY(sd_ensure(c, c->edge_tmp_keys, sizeof(unsigned long long) * n));
+        SD_TRY(sd_ensure(c, c->edge_tmp_keys, sizeof(unsigned) * n));
         SD_TRY(sd_ensure(c, c->edge_tmp_l, sizeof(int) * n));
         for (int w = 0; w < 2; w++) {
-            SD_TRY(sd_ensure(c, c->edge_keys[w], sizeof(unsigned long long) * n));
+            SD_TRY(sd_ensure(c, c->edge_keys[w], sizeof(unsigned) * n));
             SD_TRY(sd_ensure(c, c->edge_l[w], sizeof(int) * n));
         }
-        fg.lo_keys = c->edge_tmp_keys.as<unsigned long long>();
-        fg.hi_keys = c->edge_keys[0].as<unsigned long long>();  // staging; overwritten by the first sort's output later
+        fg.lo_keys = c->edge_tmp_keys.as<unsigned>();
+        fg.hi_keys = c->edge_keys[0].as<unsigned>();  // staging; overwritten by the first sort's output later
         fg.lo_l = c->edge_tmp_l.as<int>();
     }
     int nchunks = (int)((L + CHUNK - 1) / CHUNK);
@@ -376,9 +395,9 @@ int sd_k2_prepare(sd_ctx *c) {
         // window ends were staged in edge_keys[0]: sort them first (into edge_keys[1]/edge_l[1]), then the starts
         SD_TRY(sd_sort_edges(c, 1, n));
         SD_TRY(sd_sort_edges(c, 0, n));
-        fg.lo_keys = c->edge_keys[0].as<unsigned long long>();
+        fg.lo_keys = c->edge_keys[0].as<unsigned>();
         fg.lo_l = c->edge_l[0].as<int>();
-        fg.hi_keys = c->edge_keys[1].as<unsigned long long>();
+        fg.hi_keys = c->edge_keys[1].as<unsigned>();
         fg.hi_l = c->edge_l[1].as<int>();
     }
     c->records_ready = true;

@@ -128,8 +128,7 @@ __device__ __forceinline__ void class_range(const LineArgs &a, int d, int cls, i
 }
 
 // first j in [a, b) with keys[j] >= X (keys ascending), b if none.  Warp-cooperative 32-ary search.
-__device__ __forceinline__ int warp_lower_bound_u64(const unsigned long long *__restrict__ keys, int a, int b,
-                                                    unsigned long long X) {
+__device__ __forceinline__ int warp_lower_bound_u32(const unsigned *__restrict__ keys, int a, int b, unsigned X) {
     const int lane = threadIdx.x & 31;
     while (b > a) {
         int n = b - a;
@@ -160,11 +159,11 @@ __device__ __forceinline__ void fc_near_range(const LineArgs &a, int d, int lev,
 
 // Far-capable pairs of depth d with a window start (which = 0) or end (which = 1) strictly inside (t0, t1).
 __device__ __forceinline__ void fc_edge_range(const LineArgs &a, int d, int which, int64_t t0, int64_t t1, int &ja, int &jb) {
-    const unsigned long long *keys = (which ? a.fg.hi_keys : a.fg.lo_keys);
-    const unsigned long long dk = (unsigned long long)d << 32;
+    const unsigned *keys = (which ? a.fg.hi_keys : a.fg.lo_keys);
+    const unsigned dk = (unsigned)d << a.fg.key_shift;
     const int lo = (int)((size_t)d * a.L), hi = lo + (int)a.L;
-    ja = warp_lower_bound_u64(keys, lo, hi, dk | (unsigned long long)(t0 + 1));
-    jb = warp_lower_bound_u64(keys, ja, hi, dk | (unsigned long long)t1);
+    ja = warp_lower_bound_u32(keys, lo, hi, dk | (unsigned)(t0 + 1));
+    jb = warp_lower_bound_u32(keys, ja, hi, dk | (unsigned)t1);
 }
 
 // one 32-byte gather (two 16-byte loads of the same sector)
@@ -288,16 +287,21 @@ __global__ void __launch_bounds__(THREADS) k_far_coeffs(LineArgs a, int lev, int
             n_far++;
         }
         // queue neighbours are neighbours in frequency, at similar distances from the tile: warp-uniform series length
-        const int nt = __reduce_max_sync(0xffffffffu, nterms);
-        double p1r = w1r, p1i = w1i, p2r = w2r, p2i = w2i;
+        const int nt = (count_stats & 2) ? 0 : __reduce_max_sync(0xffffffffu, nterms);  // bit 1: tuning experiment, scan only
+        // Im(w^(k+1)) by the real three-term recurrence of the powers of a complex number,
+        //   s_(k+1) = 2 Re(w) s_k - |w|^2 s_(k-1),  s_0 = 0, s_1 = Im w,
+        // two instructions per pole and term instead of the four of a complex product (the recurrence loses about one
+        // bit per step relative to |w|^k, i.e. < 1e-13 over 21 terms).
+        const double a1 = w1r + w1r, b1 = fma(w1r, w1r, w1i * w1i), a2 = w2r + w2r, b2 = fma(w2r, w2r, w2i * w2i);
+        double s1 = w1i, s1p = 0.0, s2 = w2i, s2p = 0.0;
 #pragma unroll
         for (int k = 0; k < K1; k++) {
             if (k >= nt) break;
-            C[k] = fma(Wn, p1i + p2i, C[k]);
+            C[k] = fma(Wn, s1 + s2, C[k]);
             if (k + 1 < K1) {
                 double t;
-                t = fma(p1r, w1r, -p1i * w1i); p1i = fma(p1r, w1i, p1i * w1r); p1r = t;
-                t = fma(p2r, w2r, -p2i * w2i); p2i = fma(p2r, w2i, p2i * w2r); p2r = t;
+                t = fma(a1, s1, -(b1 * s1p)); s1p = s1; s1 = t;
+                t = fma(a2, s2, -(b2 * s2p)); s2p = s2; s2 = t;
             }
         }
     };
@@ -399,7 +403,7 @@ __global__ void __launch_bounds__(THREADS) k_far_coeffs(LineArgs a, int lev, int
             else a.far_coef[lev][((size_t)d * gridDim.x + blockIdx.x) * K1 + tid] = v;
         }
     }
-    if (count_stats) {  // every far pair stands for one region-I evaluation per tile pixel inside the shard
+    if (count_stats & 1) {  // every far pair stands for one region-I evaluation per tile pixel inside the shard
         for (int o2 = 16; o2; o2 >>= 1) n_far += __shfl_xor_sync(0xffffffffu, n_far, o2);
         const int64_t e0 = t0 > a.p0 ? t0 : a.p0, e1 = t1 < a.p1 ? t1 : a.p1;
         if (lane == 0 && n_far && e1 > e0) atomicAdd(&a.stats[0], n_far * (unsigned long long)(e1 - e0));
@@ -735,6 +739,7 @@ int sd_k2_lines(sd_ctx *c, int slot) {
             a.far_coef[k] = c->far_coef[k].as<double>();
         }
         constexpr int TOP_SPLIT = 8;
+        static const int far_debug = env_int("SD_FAR_SCAN_ONLY", 0) ? 2 : 0;
         if (!c->far_attr_set) {  // per device: > 48 KB of dynamic shared memory needs the opt-in
             SD_CUDA(c, cudaFuncSetAttribute(k_far_coeffs, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FAR_SMEM));
             c->far_attr_set = true;
@@ -747,7 +752,7 @@ int sd_k2_lines(sd_ctx *c, int slot) {
                                   ? a.far_ntl[k] * nsplit
                                   : ((a.far_tile0[k] + a.far_ntl[k] - 1) >> SD_FAR_SHIFT) - (a.far_tile0[k] >> SD_FAR_SHIFT) + 1;
             k_far_coeffs<<<dim3((unsigned)n_cta, (unsigned)c->D), THREADS, FAR_SMEM, c->stream>>>(
-                a, k, c->line_stats ? 1 : 0, nsplit, c->far_part.as<double>());
+                a, k, (c->line_stats ? 1 : 0) | far_debug, nsplit, c->far_part.as<double>());
             SD_TRY(sd_launch_check(c, "k_far_coeffs"));
             if (nsplit > 1) {
                 const int n = c->D * a.far_ntl[k] * (SD_FAR_K + 1);

@@ -50,8 +50,10 @@ struct FarGeom {
     int enabled;                        // far field on (PairWin::near is filled, edge lists exist)
     int *near_rad;                      // [SD_FAR_LEVELS] largest half-extent (in tiles) of any near interval
     // far-capable pairs sorted by the position of their window edges (per depth: entries [d L, (d+1) L)); keys are
-    // (depth << 32 | pixel), pixel = 0x7fffffff when the pair has no such edge inside the grid
-    unsigned long long *lo_keys, *hi_keys;
+    // 32-bit (depth << key_shift | pixel), 2^key_shift > N, pixel = 2^key_shift - 1 when the pair has no such edge
+    // inside the grid (as few key bits as possible: the radix sort of the preparation pass is priced per byte)
+    unsigned *lo_keys, *hi_keys;
+    int key_shift;
     int *lo_l, *hi_l;
 };
 
