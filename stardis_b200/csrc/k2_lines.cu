@@ -41,11 +41,10 @@ namespace {
 
 constexpr int THREADS = 256;
 constexpr int WARPS = THREADS / 32;
-constexpr int FAR_R = 8;                    // candidates per lane and scan round of k_far_coeffs
-constexpr int FAR_QCAP = 32 * (FAR_R + 1);  // per-warp queue: a carried remainder (< 32 pairs) plus one scan round
+constexpr int FAR_CH = 1024;                // candidates per cooperative scan chunk of k_far_coeffs
 struct __align__(16) FarRec { double nu, dw, y, K; };  // = the first 32 bytes of LineRec
 static_assert(WARPS == (1 << SD_FAR_SHIFT), "k_far_coeffs maps the warps of a CTA to the children of a tile");
-constexpr size_t FAR_SMEM = (size_t)WARPS * FAR_QCAP * sizeof(FarRec);
+constexpr size_t FAR_SMEM = (size_t)(FAR_CH + WARPS * 64) * sizeof(FarRec) + FAR_CH;
 
 struct __align__(16) WEntry {
     // far-wing path (48 B)
@@ -212,51 +211,64 @@ __device__ __forceinline__ bool pair_is_far(int lo, int hi, unsigned near, int64
 //   (A) pairs that cover the parent but have it in their near interval: a contiguous range (by window centre) of the
 //       class-7 list around the parent;
 //   (B) pairs that do not cover the parent (a window edge lies strictly inside it): two ranges of the edge-sorted lists.
-// The top level has no parent and walks the whole class-7 list.
-// The top level is launched with `nsplit` CTAs per (tile, depth), each taking a fixed slice of the class-7 list (the
-// slices do not depend on the shard, so the summation order -- and the result, bit for bit -- is the same for every
-// partition of the grid); k_far_reduce adds the partial sums in slice order.
+// The candidates are a property of the PARENT, so one CTA serves the eight children of a parent (warp w = child w):
+//   scan     the CTA walks the candidate lists in chunks of FAR_CH; a thread gathers the 32-byte window record of a
+//            candidate ONCE, tests it against all eight children (integer compares) and leaves an 8-bit acceptance mask;
+//            the 32 bytes of LineRec the expansion needs are staged in shared memory with cp.async if any child wants
+//            them (one gather per candidate and parent instead of one per candidate and child);
+//   expand   every warp picks its child's bit out of the masks, compacts the accepted records into its own queue in list
+//            order (ballots) and expands full batches of 32, one pair per lane, all lanes busy.
+// The top level has no parent: groups of eight consecutive tiles walk a fixed slice of the whole class-7 list
+// (`nsplit` CTAs per group; k_far_reduce adds the partial sums in slice order).  Groups, slices, chunking and queue order
+// depend on the global tile index and the candidate lists only, never on the shard, so the summation order -- and the
+// result, bit for bit -- is the same for every partition of the grid.
 __global__ void __launch_bounds__(THREADS) k_far_coeffs(LineArgs a, int lev, int count_stats, int nsplit, double *part) {
     constexpr int K1 = SD_FAR_K + 1;
     __shared__ int s_ja[3], s_jb[3];
-    __shared__ double s_red[WARPS][K1];
+    extern __shared__ __align__(16) unsigned char far_smem[];
+    FarRec *const s_rec = reinterpret_cast<FarRec *>(far_smem);                        // [FAR_CH] staged records of the chunk
+    FarRec *const s_queue = s_rec + FAR_CH;                                            // [WARPS][64] per-warp queues
+    unsigned char *const s_mask = reinterpret_cast<unsigned char *>(s_queue + WARPS * 64);  // [FAR_CH] child masks
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int d = blockIdx.y;
     const int tile_px = a.fg.tile[lev];
     const bool has_parent = lev + 1 < SD_FAR_LEVELS;
     const int plev = has_parent ? lev + 1 : lev;
-    // Levels >= 1: CTA = (tile, slice of the pair list), the warps share the candidates and their sums are reduced through
-    // shared memory.  Level 0 (many tiles, short candidate lists): CTA = parent tile, warp w = its child w -- the
-    // candidate ranges are a property of the PARENT, so they are searched once per CTA, every warp walks them for its own
-    // tile (the gathers of the eight warps meet in L1) and there is no CTA-wide barrier or reduction.  The mode is a
-    // function of the level only, so the summation order does not depend on the shard.
-    const bool per_child = has_parent && lev == 0;
-    const int tile_local = per_child ? 0 : blockIdx.x / nsplit, split = per_child ? 0 : blockIdx.x - tile_local * nsplit;
-    const int tile_w = per_child ? ((((a.far_tile0[lev] >> SD_FAR_SHIFT) + (int)blockIdx.x) << SD_FAR_SHIFT) + warp)
-                                 : a.far_tile0[lev] + tile_local;
+    const int group = (a.far_tile0[lev] >> SD_FAR_SHIFT) + (int)blockIdx.x / nsplit;  // = parent tile index
+    const int split = (int)blockIdx.x % nsplit;
+    const int child0 = group << SD_FAR_SHIFT;
+    const int tile_w = child0 + warp;
     const bool tile_ok = tile_w >= a.far_tile0[lev] && tile_w < a.far_tile0[lev] + a.far_ntl[lev];
     const int tile = tile_ok ? tile_w : a.far_tile0[lev];
-    const int ptile = tile_w >> SD_FAR_SHIFT;
     const int64_t t0 = (int64_t)tile * tile_px;
     const int64_t t1 = (t0 + tile_px < a.N) ? t0 + tile_px : a.N;
     const double nu_c = a.fg.geom[lev][2 * tile], h = a.fg.geom[lev][2 * tile + 1];
+    const int ptile = group;
     const int64_t pt0 = (int64_t)ptile * a.fg.tile[plev];
     const int64_t pt1 = (pt0 + a.fg.tile[plev] < a.N) ? pt0 + a.fg.tile[plev] : a.N;
+    // children of this group that belong to the launched range (bit c = tile child0 + c)
+    unsigned valid = 0;
+#pragma unroll
+    for (int cc = 0; cc < WARPS; cc++) {
+        const int tc = child0 + cc;
+        if (tc >= a.far_tile0[lev] && tc < a.far_tile0[lev] + a.far_ntl[lev]) valid |= 1u << cc;
+    }
     const size_t drow = (size_t)d * a.L;
     const int *list_d = a.cls_list + drow;
     if (warp < 3) {
         int ja, jb;
         if (!has_parent) {
-            const int c0 = a.cls_off[d * (SD_NCLS + 1) + SD_FC_CLASS], c1 = a.cls_off[d * (SD_NCLS + 1) + SD_FC_CLASS + 1];
-            const int len = (c1 - c0 + nsplit - 1) / nsplit;
-            ja = min(c0 + split * len, c1);
-            jb = (warp == 0) ? min(ja + len, c1) : ja;
+            ja = a.cls_off[d * (SD_NCLS + 1) + SD_FC_CLASS];
+            jb = (warp == 0) ? a.cls_off[d * (SD_NCLS + 1) + SD_FC_CLASS + 1] : ja;
         } else if (warp == 0) {
             fc_near_range(a, d, plev, ptile, ja, jb);
         } else {
             fc_edge_range(a, d, warp - 1, pt0, pt1, ja, jb);
         }
-        if (lane == 0) { s_ja[warp] = ja; s_jb[warp] = jb; }
+        // this CTA's slice of the range (a function of the range and nsplit only)
+        const int len = (jb - ja + nsplit - 1) / nsplit;
+        const int sa = min(ja + split * len, jb), sb = min(sa + len, jb);
+        if (lane == 0) { s_ja[warp] = sa; s_jb[warp] = sb; }
     }
     __syncthreads();
     double C[K1];
@@ -267,7 +279,7 @@ __global__ void __launch_bounds__(THREADS) k_far_coeffs(LineArgs a, int lev, int
     const unsigned lt_mask = (1u << lane) - 1u;
 
     // One accepted pair: 21 Taylor coefficients of its two poles about the tile centre.  Called with a dense batch of
-    // pairs (one per thread); `have` is false only in the last, partial batch.
+    // pairs (one per lane); `have` is false only in the last, partial batch.
     auto expand = [&](bool have, const FarRec &r) {
         double Wn = 0.0, w1r = 0.0, w1i = 0.0, w2r = 0.0, w2i = 0.0;
         int nterms = 0;
@@ -306,102 +318,89 @@ __global__ void __launch_bounds__(THREADS) k_far_coeffs(LineArgs a, int lev, int
         }
     };
 
-    // Every warp works on its own, in rounds of FAR_R x 32 consecutive candidates:
-    //   scan     FAR_R independent 32-byte gathers per lane (PairWin), acceptance test, ballot compaction of the
-    //            accepted line numbers into the warp's queue, in list order;
-    //   stage    the 32 bytes of LineRec the expansion needs are copied to shared memory with cp.async for ALL newly
-    //            queued pairs at once (one memory latency per round, not one per batch);
-    //   expand   full batches of 32 queued pairs, one per lane, all lanes busy; the remainder is carried over.
-    // There is no CTA barrier in the loop, so the warps of an SM drift apart and the gathers of one overlap the
-    // arithmetic of the others.  Candidate -> warp assignment and queue order are functions of the candidate lists only:
-    // the summation order is fixed.
-    extern __shared__ __align__(16) unsigned char far_smem[];
-    FarRec *const q = reinterpret_cast<FarRec *>(far_smem) + (size_t)warp * FAR_QCAP;
+    FarRec *const q = s_queue + warp * 64;
     int qn = 0;  // queue length of this warp
     for (int src = 0; src < 3; src++) {
         const int ja = s_ja[src], jb = s_jb[src];
-        const int first = per_child ? ja : ja + warp * (32 * FAR_R);
-        const int stride = per_child ? 32 * FAR_R : THREADS * FAR_R;
-        for (int base = first; base < jb && tile_ok; base += stride) {
-            int l_r[FAR_R];
-            unsigned m_r[FAR_R];
+        for (int base = ja; base < jb; base += FAR_CH) {
+            // ---- scan: one gather per candidate, acceptance mask over the eight children
 #pragma unroll
-            for (int r = 0; r < FAR_R; r++) {
-                const int j = base + r * 32 + lane;
-                l_r[r] = (j < jb) ? ((src == 0) ? list_d[j] : (src == 1 ? a.fg.lo_l[j] : a.fg.hi_l[j])) : -1;
-            }
-#pragma unroll
-            for (int r = 0; r < FAR_R; r++) {
-                bool ok = l_r[r] >= 0;
-                if (ok) {
-                    const PairWin pw = load_win(a.win + drow + l_r[r]);
+            for (int r = 0; r < FAR_CH / THREADS; r++) {
+                const int idx = r * THREADS + tid, j = base + idx;
+                unsigned mask = 0;
+                if (j < jb) {
+                    const int l = (src == 0) ? list_d[j] : (src == 1 ? a.fg.lo_l[j] : a.fg.hi_l[j]);
+                    const PairWin pw = load_win(a.win + drow + l);
                     const int lo = pw.lo, hi = pw.hi;
-                    ok = pair_is_far(lo, hi, near_of(pw, lev), t0, t1, tile);  // must cover this tile and be far from it
+                    bool okp = true;
                     if (has_parent) {
                         const bool covers_parent = (lo <= pt0) && (hi >= pt1);
                         if (src == 0) {  // (A): covers the parent, parent inside the near interval
-                            ok = ok && covers_parent && !pair_is_far(lo, hi, near_of(pw, plev), pt0, pt1, ptile);
+                            okp = covers_parent && !pair_is_far(lo, hi, near_of(pw, plev), pt0, pt1, ptile);
                         } else {         // (B): an edge strictly inside the parent; both edges inside: via its start
-                            ok = ok && !covers_parent && !(src == 2 && lo > pt0 && lo < pt1);
+                            okp = !covers_parent && !(src == 2 && lo > pt0 && lo < pt1);
                         }
                     }
-                }
-                m_r[r] = __ballot_sync(0xffffffffu, ok);
-            }
+                    if (okp) {
+                        const unsigned near = near_of(pw, lev);
 #pragma unroll
-            for (int r = 0; r < FAR_R; r++) {
-                if ((m_r[r] >> lane) & 1u) {
-                    const unsigned dst = (unsigned)__cvta_generic_to_shared(q + qn + __popc(m_r[r] & lt_mask));
-                    const LineRec *srcp = a.rec + drow + l_r[r];
-                    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(srcp) : "memory");
-                    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst + 16u),
-                                 "l"(reinterpret_cast<const char *>(srcp) + 16) : "memory");
+                        for (int cc = 0; cc < WARPS; cc++) {
+                            const int64_t c0 = (int64_t)(child0 + cc) * tile_px;
+                            const int64_t c1 = (c0 + tile_px < a.N) ? c0 + tile_px : a.N;
+                            if (pair_is_far(lo, hi, near, c0, c1, child0 + cc)) mask |= 1u << cc;
+                        }
+                        mask &= valid;
+                    }
+                    if (mask) {
+                        const unsigned dst = (unsigned)__cvta_generic_to_shared(s_rec + idx);
+                        const LineRec *srcp = a.rec + drow + l;
+                        asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(srcp) : "memory");
+                        asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst + 16u),
+                                     "l"(reinterpret_cast<const char *>(srcp) + 16) : "memory");
+                    }
                 }
-                qn += __popc(m_r[r]);
+                s_mask[idx] = (unsigned char)mask;
             }
             asm volatile("cp.async.commit_group;" ::: "memory");
             asm volatile("cp.async.wait_group 0;" ::: "memory");
-            __syncwarp();
-            int b = 0;
-            for (; b + 32 <= qn; b += 32) expand(true, q[b + lane]);
-            if (b > 0) {  // move the remainder (< 32 entries) to the front
-                const int rem = qn - b;
-                FarRec v;
-                if (lane < rem) v = q[b + lane];
+            __syncthreads();
+            // ---- expand: this warp's child, in list order
+            const int n_here = (jb - base < FAR_CH) ? jb - base : FAR_CH;
+            for (int i0 = 0; i0 < n_here && tile_ok; i0 += 32) {
+                const int idx = i0 + lane;
+                const bool acc = (idx < n_here) && ((s_mask[idx] >> warp) & 1u);
+                const unsigned m = __ballot_sync(0xffffffffu, acc);
+                if (!m) continue;
+                if (acc) q[qn + __popc(m & lt_mask)] = s_rec[idx];
+                qn += __popc(m);
                 __syncwarp();
-                if (lane < rem) q[lane] = v;
-                qn = rem;
-                __syncwarp();
+                if (qn >= 32) {
+                    expand(true, q[lane]);
+                    const int rem = qn - 32;
+                    FarRec v;
+                    if (lane < rem) v = q[32 + lane];
+                    __syncwarp();
+                    if (lane < rem) q[lane] = v;
+                    qn = rem;
+                    __syncwarp();
+                }
             }
+            __syncthreads();  // the chunk buffers are overwritten by the next scan
         }
     }
     if (qn > 0) expand(lane < qn, q[lane < qn ? lane : 0]);
-    // deterministic reduction: lanes by shuffle; shared candidates: warps through shared memory in fixed order
-    if (per_child) {
-        double mine = 0.0;
+    // deterministic reduction: lanes by shuffle (every lane ends up with the sum; lane k keeps coefficient k)
+    double mine = 0.0;
 #pragma unroll
-        for (int k = 0; k < K1; k++) {
-            double v = C[k];
-            for (int o2 = 16; o2; o2 >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o2);
-            if (lane == k) mine = v;
-        }
-        if (tile_ok && lane < K1)
-            a.far_coef[lev][((size_t)d * a.far_ntl[lev] + (tile - a.far_tile0[lev])) * K1 + lane] = mine;
-    } else {
-#pragma unroll
-        for (int k = 0; k < K1; k++) {
-            double v = C[k];
-            for (int o2 = 16; o2; o2 >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o2);
-            if (lane == 0) s_red[warp][k] = v;
-        }
-        __syncthreads();
-        if (tid < K1) {
-            double v = 0.0;
-#pragma unroll
-            for (int w = 0; w < WARPS; w++) v += s_red[w][tid];
-            if (nsplit > 1) part[((size_t)d * gridDim.x + blockIdx.x) * K1 + tid] = v;
-            else a.far_coef[lev][((size_t)d * gridDim.x + blockIdx.x) * K1 + tid] = v;
-        }
+    for (int k = 0; k < K1; k++) {
+        double v = C[k];
+        for (int o2 = 16; o2; o2 >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o2);
+        if (lane == k) mine = v;
+    }
+    if (tile_ok && lane < K1) {
+        const size_t tl = (size_t)d * a.far_ntl[lev] + (tile - a.far_tile0[lev]);
+        if (nsplit > 1) part[(tl * nsplit + split) * K1 + lane] = mine;
+        else a.far_coef[lev][tl * K1 + lane] = mine;
     }
     if (count_stats & 1) {  // every far pair stands for one region-I evaluation per tile pixel inside the shard
         for (int o2 = 16; o2; o2 >>= 1) n_far += __shfl_xor_sync(0xffffffffu, n_far, o2);
@@ -410,7 +409,10 @@ __global__ void __launch_bounds__(THREADS) k_far_coeffs(LineArgs a, int lev, int
     }
 }
 
-// sum of the nsplit partial coefficient sets of the top level, in slice order
+// slices per level (constants: the summation order must not depend on the shard)
+__host__ __device__ constexpr int far_nsplit(int lev) { return lev == SD_FAR_LEVELS - 1 ? 32 : (lev == 0 ? 2 : 8); }
+
+// sum of the nsplit partial coefficient sets of a level, in slice order
 __global__ void k_far_reduce(int n, int nsplit, const double *__restrict__ part, double *__restrict__ coef) {
     constexpr int K1 = SD_FAR_K + 1;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;  // (depth, tile) * K1 + k
@@ -738,19 +740,23 @@ int sd_k2_lines(sd_ctx *c, int slot) {
             SD_TRY(sd_ensure(c, c->far_coef[k], sizeof(double) * c->D * a.far_ntl[k] * (SD_FAR_K + 1)));
             a.far_coef[k] = c->far_coef[k].as<double>();
         }
-        constexpr int TOP_SPLIT = 8;
+        // CTAs per (group of eight sibling tiles, depth): the candidate lists are cut into this many fixed slices so that
+        // even a narrow shard fills the chip; k_far_reduce adds the partial sums in slice order.
         static const int far_debug = env_int("SD_FAR_SCAN_ONLY", 0) ? 2 : 0;
         if (!c->far_attr_set) {  // per device: > 48 KB of dynamic shared memory needs the opt-in
             SD_CUDA(c, cudaFuncSetAttribute(k_far_coeffs, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FAR_SMEM));
             c->far_attr_set = true;
         }
-        SD_TRY(sd_ensure(c, c->far_part, sizeof(double) * c->D * a.far_ntl[SD_FAR_LEVELS - 1] * TOP_SPLIT * (SD_FAR_K + 1)));
+        size_t part_bytes = 0;
+        for (int k = 0; k < SD_FAR_LEVELS; k++) {
+            const size_t b = sizeof(double) * c->D * a.far_ntl[k] * far_nsplit(k) * (SD_FAR_K + 1);
+            part_bytes = b > part_bytes ? b : part_bytes;
+        }
+        SD_TRY(sd_ensure(c, c->far_part, part_bytes));
         for (int k = SD_FAR_LEVELS - 1; k >= 0; k--) {
-            const int nsplit = (k == SD_FAR_LEVELS - 1) ? TOP_SPLIT : 1;
-            // levels >= 1: tiles x slices; level 0: one CTA per parent tile that has a child in the launched range
-            const int n_cta = (k > 0 || SD_FAR_LEVELS == 1)
-                                  ? a.far_ntl[k] * nsplit
-                                  : ((a.far_tile0[k] + a.far_ntl[k] - 1) >> SD_FAR_SHIFT) - (a.far_tile0[k] >> SD_FAR_SHIFT) + 1;
+            const int nsplit = far_nsplit(k);
+            // one CTA per group of eight sibling tiles that has a member in the launched range, times the slices
+            const int n_cta = (((a.far_tile0[k] + a.far_ntl[k] - 1) >> SD_FAR_SHIFT) - (a.far_tile0[k] >> SD_FAR_SHIFT) + 1) * nsplit;
             k_far_coeffs<<<dim3((unsigned)n_cta, (unsigned)c->D), THREADS, FAR_SMEM, c->stream>>>(
                 a, k, (c->line_stats ? 1 : 0) | far_debug, nsplit, c->far_part.as<double>());
             SD_TRY(sd_launch_check(c, "k_far_coeffs"));
