@@ -417,6 +417,14 @@ def run_b200_arm(args):
         if os.path.exists(peaks_path):
             hbm_peak, hbm_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured"
         cells = D * W
+        # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` captures of this
+        # workload (profiles/ncu_traffic.json, written by tools/ncu_summary.py runs); null for any other configuration
+        traffic = {}
+        tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+        if os.path.exists(tpath) and world == 1:
+            t = json.load(open(tpath))
+            if (t.get("N"), t.get("D"), t.get("L")) == (N, D, len(sel)):
+                traffic = t.get("bytes_per_launch", {})
         out = {
             "metric": "emergent-spectrum nu-points/sec (opacity+raytrace)", "value": value, "unit": "nu-points/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
@@ -426,19 +434,20 @@ def run_b200_arm(args):
                        "ranges": [list(b) for b in bounds]},
             "roofline": {"kernel": "k_lines, direct mode (K2: every (line, depth, pixel) Voigt evaluation done explicitly, "
                                    "far-field expansion off)", "bound": "fp64", "achieved": achieved_tflops,
-                         "peak": dfma_peak, "unit": "TFLOP/s", "frac": achieved_tflops / dfma_peak, "traffic": None,
+                         "peak": dfma_peak, "unit": "TFLOP/s", "frac": achieved_tflops / dfma_peak, "traffic": traffic.get("k_lines_direct"),
                          "peak_source": "measured in this run: dependent-free DFMA loop on all SMs (sd_bench_dfma)",
                          "flops_per_eval": FLOPS_PER_EVAL.tolist(), "region_evals_all_ranks": region_evals.tolist(),
                          "kernel_ms": k2_kernel_ms, "gevals_per_s": float(stats["evals"] / k2_kernel_ms / 1e6)},
-            "farfield": {"what": "default mode: distant region-I wings summed as degree-20 Taylor coefficients per pixel "
-                                 "tile (k_far_coeffs) instead of per pixel; same result within max_rel_dev",
+            "farfield": {"what": "default mode: distant region-I wings summed as Taylor coefficients (degree <= 20) per pixel "
+                                 "tile on a 3-level tile hierarchy (k_far_coeffs) instead of per pixel; same result within "
+                                 "max_rel_dev",
                          "k2_ms": k2_far_ms, "k2_ms_direct": k2_kernel_ms, "k2_speedup": k2_kernel_ms / k2_far_ms,
                          "max_rel_dev_vs_direct": far_dev, "ms_per_step_direct": ms_direct,
                          "value_direct_mode": N / (ms_direct * 1e-3)},
             "roofline_hbm": {"kernel": "k_continuum + k_raytrace (K3+K4)", "bound": "hbm",
                              "achieved": BYTES_PER_CELL * cells / ((phase[2] + phase[3]) * 1e-3) / 1e9, "peak": hbm_peak,
                              "unit": "GB/s", "frac": BYTES_PER_CELL * cells / ((phase[2] + phase[3]) * 1e-3) / 1e9 / hbm_peak,
-                             "peak_source": hbm_src, "traffic": None},
+                             "peak_source": hbm_src, "traffic": traffic.get("k_continuum+k_raytrace")},
             "phase_ms": {"K1_broadening": phase[0], "K2_prepare_and_lines": phase[1], "K3_continuum": phase[2],
                          "K4_raytrace": phase[3], "spectrum_gather": phase[4]},
             "cpu_baseline": cpu,
