@@ -630,7 +630,8 @@ __global__ void __launch_bounds__(32 * NW, MINB) k_lines(LineArgs a) {
 #pragma unroll
         for (int lev = 0; lev < SD_FAR_LEVELS; lev++) {
             const int tk = tile >> (SD_FAR_SHIFT * lev);
-            const double nu_c = a.fg.geom[lev][2 * tk], inv_h = 1.0 / a.fg.geom[lev][2 * tk + 1];
+            const double nu_c = a.fg.geom[lev][2 * tk], h_k = a.fg.geom[lev][2 * tk + 1];
+            const double inv_h = (h_k > 0.0) ? 1.0 / h_k : 0.0;  // a one-pixel tile has h = 0: nothing is ever far from it, C = 0
             const double *__restrict__ C = a.far_coef[lev] + ((size_t)d * a.far_ntl[lev] + (tk - a.far_tile0[lev])) * K1;
             double tt[P], poly[P];
             const double ck = C[K1 - 1];
@@ -689,11 +690,13 @@ int launch(sd_ctx *c, const LineArgs &a, dim3 grid, bool stats, int rcp) {
 }  // namespace
 
 // pixels per thread: enough CTAs to fill the chip several times over, otherwise as much register reuse of the staged
-// entries as possible.  SD_K2_P overrides the choice (tuning experiments).
+// entries as possible.  The choice is made from the GLOBAL grid length, never from the shard: the tile size fixes the
+// summation order inside a pixel, and a nu shard must reproduce the columns of the full run bit for bit.
+// SD_K2_P / SD_K2_NW override the choice (tuning experiments).
 int sd_k2_choose_P(sd_ctx *c) {
     static const int force_p = env_int("SD_K2_P", 0);
     static const int force_nw = env_int("SD_K2_NW", 0);
-    const int64_t W = c->W();
+    const int64_t W = c->N;
     int P, NW = 8;
     if (c->farfield) {
         // Small level-0 tiles keep the directly evaluated near field small (the hierarchy absorbs the rest), wide
