@@ -88,9 +88,20 @@ typedef struct sd_lines {
     const double *mass;                 /* g; atomic, or sum of both constituents for molecules (:808-819) */
     const double *stark;                /* VALD log10 Stark parameter or NULL */
     const double *waals;                /* VALD van der Waals code or NULL */
-    const double *alpha_line;           /* (L, D) */
+    const double *alpha_line;           /* (L, D); NULL = filled on the device by sd_calc_alpha_line_vald */
 } sd_lines;
 int sd_set_lines(sd_ctx *ctx, const sd_lines *lines);
+
+/* Line strengths of a VALD linelist on the device -- the producer of `alpha_line` immediately upstream of the path
+ * (SURVEY 8f rank 1): stardis/plasma/base.py:178-321 (AlphaLineVald) and :324-455 (AlphaLineShortlistVald),
+ *   alpha[l, d] = (pi e^2 / m_e c) * (N_ion / U)[ion_row[l], d] * exp(-E_low[l] / k T_d) * [g_lo] * gf[l]
+ *                 * (1 - exp(-h nu_l / k T_d)),
+ * in the reference's order of operations.  Needs the atmosphere (T) and the line table (nu; alpha_line may be NULL).
+ * n_over_u: (n_ions, D) ion number density / partition function; ion_row[l]: row of that table for line l;
+ * gf[l]: f_lu = 10^log_gf / g_lo with g_lo[l] given (long lists) or 10^log_gf with g_lo == NULL (short lists);
+ * e_low_erg[l]: lower level energy [erg].  Replaces the (L, D) host->device upload of alpha_line by O(L) inputs. */
+int sd_calc_alpha_line_vald(sd_ctx *ctx, int64_t n_ions, const double *n_over_u, const int64_t *ion_row, const double *gf,
+                            const double *g_lo, const double *e_low_erg);
 
 /* ---- K1: broadening (calc_gamma broadening.py:550-656, calc_vald_gamma :1009-1085,
  *          calc_doppler_width :32-71) -> gammas (L,D), doppler_widths (L,D) on the device ------------- */
@@ -176,6 +187,7 @@ int sd_raytrace(sd_ctx *ctx, int32_t n_theta, const double *ray_ds, const double
 #define SD_BUF_TOTAL 5           /* (D, W) */
 #define SD_BUF_F_NU 6            /* (D, W) */
 #define SD_BUF_I_NUS 7           /* (D, W, n_theta) */
+#define SD_BUF_LINE_STRENGTH 8   /* (L, D) alpha_line of the line table (uploaded or sd_calc_alpha_line_vald) */
 #define SD_BUF_SOURCE0 16        /* + source index: (D, W) */
 /* Copy a result into dst (host or device); count = number of doubles, must equal the buffer size. */
 int sd_get(sd_ctx *ctx, int32_t which, double *dst, int64_t count);

@@ -396,3 +396,47 @@ def raytrace(T, alphas, nus, thetas, weights, dist=None, r=None, spherical=False
                        C.c_int(int(spherical)), C.c_double(scale), F.ctypes.data_as(_dp),
                        I_nus.ctypes.data_as(_dp) if track else None)
     return F, I_nus
+
+
+# ------------------------------------------------------------------ VALD line strengths (upstream of K1/K2)
+def alpha_line_vald(atomic_number, ion_charge, wavelength_aa, log_gf, e_low_ev, e_up_ev, j_lo, rad, ions, ion_number_density,
+                    partition_function, t_electrons, ionization_index, ionization_energy, max_atomic_number, shortlist=False):
+    """numpy restatement of ``AlphaLineVald.calculate`` (stardis/plasma/base.py:203-321) and, with ``shortlist=True``,
+    of ``AlphaLineShortlistVald.calculate`` (:346-455), in the reference's order of operations.
+
+    ``ions``: (n_ions, 2) (atomic_number, charge) rows of ``ion_number_density`` / ``partition_function`` (n_ions, D);
+    ``ionization_index``: (n, 2) (atomic_number, ion_number = charge + 1) rows of ``ionization_energy`` [erg].
+    Returns (alphas (L', D), lines dict) after the truncation to ``max_atomic_number`` (:235-237 / :375-377) and, for the
+    long list, the removal of auto-ionising lines (:316-318)."""
+    EV, KB, H, C_ = 1.602176634e-12, 1.380649e-16, 6.62607015e-27, 2.99792458e10
+    ALPHA_COEFFICIENT = (np.pi * 4.803204712570263e-10 ** 2) / (9.1093837015e-28 * C_)  # :35
+    keep = np.asarray(atomic_number) <= max_atomic_number
+    Z, q = np.asarray(atomic_number)[keep], np.asarray(ion_charge)[keep]
+    lam, lgf, e_low = np.asarray(wavelength_aa, float)[keep], np.asarray(log_gf, float)[keep], np.asarray(e_low_ev, float)[keep]
+    T = np.asarray(t_electrons, float)
+    if shortlist:  # :380-387
+        e_up = (e_low * EV + (H * C_) / (lam * 1e-8)) / EV
+    else:
+        e_up = np.asarray(e_up_ev, float)[keep]
+    exponent = np.exp(np.outer(-e_low * EV, 1.0 / (T * KB)))                       # :242-247 / :389-393
+    row = {(int(a), int(b)): i for i, (a, b) in enumerate(np.asarray(ions))}
+    n_over_u = (np.asarray(ion_number_density, float) / np.asarray(partition_function, float))[[row[(int(a), int(b))] for a, b in zip(Z, q)]]
+    line_nus = C_ / (lam * 1e-8)                                                    # :268-270
+    emission = 1.0 - np.exp((-H / KB) * np.outer(line_nus, 1.0 / T))               # :272-281
+    if shortlist:
+        prefactor = (exponent * n_over_u).T                                         # :401-403
+        alphas = (ALPHA_COEFFICIENT * prefactor * 10 ** lgf * emission.T).T         # :420-427
+    else:
+        g_lo = np.asarray(j_lo, float)[keep] * 2 + 1                                # :240
+        n_lower = (exponent * n_over_u).T * g_lo                                    # :256-262
+        f_lu = 10 ** lgf / g_lo                                                     # :264-266
+        alphas = (ALPHA_COEFFICIENT * n_lower * f_lu * emission.T).T                # :283-291
+    ion_e = {(int(a), int(b) - 1): e for (a, b), e in zip(np.asarray(ionization_index), np.asarray(ionization_energy, float))}
+    lines = dict(atomic_number=Z, ion_number=q, nu=line_nus, level_energy_lower=e_low * EV, level_energy_upper=e_up * EV,
+                 A_ul=10 ** np.asarray(rad, float)[keep],
+                 ionization_energy=np.array([ion_e.get((int(a), int(b)), np.nan) for a, b in zip(Z, q)]))
+    if not shortlist:
+        valid = lines["level_energy_upper"] < lines["ionization_energy"]
+        alphas = alphas[valid]
+        lines = {k: v[valid] for k, v in lines.items()}
+    return alphas, lines

@@ -16,6 +16,7 @@ LIB_PATH = os.path.join(HERE, "libstardis_b200.so")
 SD_OK = 0
 LINEAR_STARK, QUADRATIC_STARK, VAN_DER_WAALS, RADIATION, VALD = 1, 2, 4, 8, 16
 BUF_GAMMAS, BUF_DOPPLER, BUF_ALPHA_LINE, BUF_ALPHA_MOLECULE, BUF_TOTAL, BUF_F_NU, BUF_I_NUS = 1, 2, 3, 4, 5, 6, 7
+BUF_LINE_STRENGTH = 8
 BUF_SOURCE0 = 16
 SRC_BF, SRC_FF, SRC_RAYLEIGH, SRC_ELECTRON, SRC_TABLE0 = 0, 1, 2, 3, 4
 MAX_TABLES = 8
@@ -60,6 +61,7 @@ SIGNATURES = {
     "sd_calc_broadening": (C.c_int, [_V, C.c_uint32]),
     "sd_set_broadening": (C.c_int, [_V, _V, C.c_int32, _V]),
     "sd_calc_alpha_line": (C.c_int, [_V, C.c_int32]),
+    "sd_calc_alpha_line_vald": (C.c_int, [_V, C.c_int64, _V, _V, _V, _V, _V]),
     "sd_set_farfield": (C.c_int, [_V, C.c_int32]),
     "sd_set_line_stats": (C.c_int, [_V, C.c_int32]),
     "sd_line_stats": (C.c_int, [_V, _ip]),

@@ -85,7 +85,7 @@ void sd_destroy(sd_ctx *c) {
     cudaStreamSynchronize(c->stream);
     DevBuf *all[] = {&c->T, &c->ne, &c->nH, &c->nus, &c->d_nu, &c->l_nu, &c->l_Z, &c->l_ion, &c->l_eion, &c->l_eup,
                      &c->l_elo, &c->l_A, &c->l_mass, &c->l_stark, &c->l_waals, &c->l_alpha, &c->gammas, &c->dws,
-                     &c->line_idx, &c->rec, &c->win, &c->win_cls, &c->cls_list, &c->cls_off,
+                     &c->vald_stage, &c->line_idx, &c->rec, &c->win, &c->win_cls, &c->cls_list, &c->cls_off,
                      &c->chunk_cnt, &c->stats, &c->near_rad, &c->edge_keys[0], &c->edge_keys[1], &c->edge_l[0], &c->edge_l[1], &c->edge_tmp_keys, &c->edge_tmp_l,
                      &c->edge_sort_tmp, &c->alpha_line[0], &c->alpha_line[1], &c->total, &c->cont_small,
                      &c->F, &c->I_nus, &c->ray_small};
@@ -168,14 +168,16 @@ int sd_set_lines(sd_ctx *c, const sd_lines *ln) {
     SD_CHECK(c, c->D > 0, SD_ERR_STATE, "sd_set_lines: call sd_set_atmosphere first");
     int64_t L = ln->n_lines;
     SD_CHECK(c, L >= 0 && L * (int64_t)c->D < (int64_t)4e9, SD_ERR_ARG, "sd_set_lines: bad line count");
-    SD_CHECK(c, L == 0 || (ln->nu && ln->alpha_line), SD_ERR_ARG, "sd_set_lines: nu and alpha_line are required");
+    SD_CHECK(c, L == 0 || ln->nu, SD_ERR_ARG, "sd_set_lines: nu is required");
     SD_CUDA(c, cudaSetDevice(c->device));
     c->L = L;
     c->records_ready = false;
     c->have_broadening = false;
     size_t d8 = sizeof(double) * L;
     SD_TRY(sd_upload(c, c->l_nu, ln->nu, d8));
-    SD_TRY(sd_upload(c, c->l_alpha, ln->alpha_line, d8 * c->D));
+    if (ln->alpha_line) SD_TRY(sd_upload(c, c->l_alpha, ln->alpha_line, d8 * c->D));
+    else SD_TRY(sd_ensure(c, c->l_alpha, d8 * c->D));  // filled by sd_calc_alpha_line_vald
+    c->have_alpha_line = ln->alpha_line != nullptr || L == 0;
     if (ln->mass) SD_TRY(sd_upload(c, c->l_mass, ln->mass, d8));
     c->has_atomic_cols = ln->atomic_number && ln->ion_number && ln->ionization_energy && ln->level_energy_upper &&
                          ln->level_energy_lower && ln->A_ul && ln->mass;
@@ -192,6 +194,57 @@ int sd_set_lines(sd_ctx *c, const sd_lines *ln) {
         SD_TRY(sd_upload(c, c->l_stark, ln->stark, d8));
         SD_TRY(sd_upload(c, c->l_waals, ln->waals, d8));
     }
+    return SD_OK;
+}
+
+namespace {
+// one thread per (line, depth), depth fastest: coalesced (L, D) store, broadcast-friendly per-line loads
+__global__ void __launch_bounds__(256) k_alpha_line_vald(int64_t L, int D, const double *__restrict__ T,
+                                                         const double *__restrict__ line_nu, const double *__restrict__ n_over_u,
+                                                         const int64_t *__restrict__ ion_row, const double *__restrict__ gf,
+                                                         const double *__restrict__ g_lo, const double *__restrict__ e_low,
+                                                         double *__restrict__ alpha) {
+    const int64_t g = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (g >= L * D) return;
+    const int64_t l = g / D;
+    const int d = (int)(g - l * D);
+    const double Td = T[d];
+    // plasma/base.py:242-247: exp(outer(-E_low, 1 / (T k_B)))
+    const double boltz = exp((-e_low[l]) * (1.0 / (Td * sdm::KB_CGS)));
+    double n_lower = boltz * n_over_u[ion_row[l] * D + d];   // :256-262 (x g_lo for the long lists)
+    if (g_lo) n_lower *= g_lo[l];
+    // :272-281: 1 - exp((-h / k_B) * outer(nu, 1 / T))
+    const double emis = 1.0 - exp((-sdm::H_CGS / sdm::KB_CGS) * (line_nu[l] * (1.0 / Td)));
+    constexpr double ALPHA_COEFFICIENT = (sdm::PI * sdm::E_ESU * sdm::E_ESU) / (9.1093837015e-28 * sdm::C_CGS);  // :35
+    alpha[g] = ALPHA_COEFFICIENT * n_lower * gf[l] * emis;  // :283-291, left to right
+}
+}  // namespace
+
+int sd_calc_alpha_line_vald(sd_ctx *c, int64_t n_ions, const double *n_over_u, const int64_t *ion_row, const double *gf,
+                            const double *g_lo, const double *e_low_erg) {
+    if (!c) return SD_ERR_ARG;
+    SD_CHECK(c, c->D > 0, SD_ERR_STATE, "sd_calc_alpha_line_vald: no atmosphere");
+    SD_CHECK(c, n_ions > 0 && n_over_u && ion_row && gf && e_low_erg, SD_ERR_ARG, "sd_calc_alpha_line_vald: missing input");
+    SD_CUDA(c, cudaSetDevice(c->device));
+    const int64_t L = c->L, n = L * c->D;
+    if (n == 0) return SD_OK;
+    // staged inputs: [n_over_u | ion_row | gf | e_low | g_lo]
+    const size_t b_tab = sizeof(double) * n_ions * c->D, b8 = sizeof(double) * L;
+    SD_TRY(sd_ensure(c, c->vald_stage, b_tab + 4 * b8));
+    char *base = c->vald_stage.as<char>();
+    SD_CUDA(c, cudaMemcpyAsync(base, n_over_u, b_tab, cudaMemcpyDefault, c->stream));
+    SD_CUDA(c, cudaMemcpyAsync(base + b_tab, ion_row, b8, cudaMemcpyDefault, c->stream));
+    SD_CUDA(c, cudaMemcpyAsync(base + b_tab + b8, gf, b8, cudaMemcpyDefault, c->stream));
+    SD_CUDA(c, cudaMemcpyAsync(base + b_tab + 2 * b8, e_low_erg, b8, cudaMemcpyDefault, c->stream));
+    if (g_lo) SD_CUDA(c, cudaMemcpyAsync(base + b_tab + 3 * b8, g_lo, b8, cudaMemcpyDefault, c->stream));
+    k_alpha_line_vald<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(
+        L, c->D, c->T.as<double>(), c->l_nu.as<double>(), reinterpret_cast<const double *>(base),
+        reinterpret_cast<const int64_t *>(base + b_tab), reinterpret_cast<const double *>(base + b_tab + b8),
+        g_lo ? reinterpret_cast<const double *>(base + b_tab + 3 * b8) : nullptr,
+        reinterpret_cast<const double *>(base + b_tab + 2 * b8), c->l_alpha.as<double>());
+    SD_TRY(sd_launch_check(c, "k_alpha_line_vald"));
+    c->have_alpha_line = true;
+    c->records_ready = false;
     return SD_OK;
 }
 
@@ -225,6 +278,8 @@ int sd_calc_alpha_line(sd_ctx *c, int32_t slot) {
     SD_CHECK(c, slot == 0 || slot == 1, SD_ERR_ARG, "sd_calc_alpha_line: slot must be 0 or 1");
     SD_CHECK(c, c->N > 0 && c->D > 0, SD_ERR_STATE, "sd_calc_alpha_line: grid/atmosphere not set");
     SD_CHECK(c, c->have_broadening || c->L == 0, SD_ERR_STATE, "sd_calc_alpha_line: no broadening (K1) yet");
+    SD_CHECK(c, c->have_alpha_line || c->L == 0, SD_ERR_STATE,
+             "sd_calc_alpha_line: the line table has no alpha_line (pass it to sd_set_lines or call sd_calc_alpha_line_vald)");
     SD_CUDA(c, cudaSetDevice(c->device));
     if (!c->records_ready) SD_TRY(sd_k2_prepare(c));
     SD_TRY(sd_k2_lines(c, slot));
@@ -292,6 +347,9 @@ static int find_buffer(sd_ctx *c, int which, DevBuf **b, int64_t *rows, int64_t 
             SD_CHECK(c, c->have_alpha[s], SD_ERR_STATE, "alpha_line slot %d not computed", s);
             *b = &c->alpha_line[s]; *rows = c->D; *cols = W; return SD_OK;
         }
+        case SD_BUF_LINE_STRENGTH:
+            SD_CHECK(c, c->have_alpha_line, SD_ERR_STATE, "line strengths not set");
+            *b = &c->l_alpha; *rows = c->L; *cols = c->D; return SD_OK;
         case SD_BUF_TOTAL:
             SD_CHECK(c, c->have_total, SD_ERR_STATE, "total opacity not computed");
             *b = &c->total; *rows = c->D; *cols = W; return SD_OK;

@@ -88,6 +88,8 @@ struct sd_ctx {
     bool has_atomic_cols = false, has_vald_cols = false;
     DevBuf l_nu, l_Z, l_ion, l_eion, l_eup, l_elo, l_A, l_mass, l_stark, l_waals, l_alpha;
     DevBuf gammas, dws;
+    DevBuf vald_stage;            // staged inputs of sd_calc_alpha_line_vald
+    bool have_alpha_line = false; // l_alpha holds line strengths (uploaded or computed on the device)
     int gamma_cols = 0;
     bool have_broadening = false;
 

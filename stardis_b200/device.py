@@ -129,6 +129,19 @@ class DeviceContext:
     def calc_alpha_line(self, slot=0):
         self._ck(self.lib.sd_calc_alpha_line(self.h, int(slot)))
 
+    def calc_alpha_line_vald(self, n_over_u, ion_row, gf, e_low_erg, g_lo=None):
+        """Line strengths (L, D) of a VALD linelist on the device (plasma/base.py:178-455); see include/stardis_b200.h.
+        Needs ``set_atmosphere`` and ``set_lines(nu, None, ...)`` first; the result feeds K2 without a host round trip
+        (``get(BUF_LINE_STRENGTH)`` copies it back)."""
+        t = L.f64(n_over_u)
+        if t.ndim != 2 or t.shape[1] != self.D:
+            raise ValueError("n_over_u must have shape (n_ions, D)")
+        rows = np.ascontiguousarray(ion_row, dtype=np.int64)
+        if rows.shape[0] != self.L or (rows.size and (rows.min() < 0 or rows.max() >= t.shape[0])):
+            raise ValueError("ion_row must hold one valid row of n_over_u per line")
+        self._ck(self.lib.sd_calc_alpha_line_vald(self.h, int(t.shape[0]), self._in(t), self._in(rows, integer=True),
+                                                  self._in(gf), self._in(g_lo), self._in(e_low_erg)))
+
     def set_farfield(self, on=True):
         """Far-field (Taylor) expansion of distant region-I wings per pixel tile; off = evaluate every pixel directly."""
         self._ck(self.lib.sd_set_farfield(self.h, int(bool(on))))
@@ -185,7 +198,7 @@ class DeviceContext:
 
     # ------------------------------------------------------------------ results
     def _shape(self, which):
-        if which in (L.BUF_GAMMAS, L.BUF_DOPPLER):
+        if which in (L.BUF_GAMMAS, L.BUF_DOPPLER, L.BUF_LINE_STRENGTH):
             return None
         if which == L.BUF_I_NUS:
             return (self.D, self.W, self.n_theta)

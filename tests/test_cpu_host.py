@@ -458,3 +458,20 @@ def test_nu_shards_gather_to_the_full_spectrum_gloo_world2(tmp_path):
     procs = [subprocess.Popen([sys.executable, str(script)], env=dict(os.environ, RANK=str(r), WORLD_SIZE="2"))
              for r in range(2)]
     assert [p.wait(timeout=240) for p in procs] == [0, 0]
+
+
+# ------------------------------------------------------------------ VALD line strengths: host preparation
+@pytest.mark.parametrize("kind", ["long", "short"])
+def test_vald_linelist_preparation_matches_the_reference_line_table(kind):
+    from stardis_b200.plasma.alpha_line_vald import prepare_vald_linelist
+
+    g = golden("plasma_golden.npz")
+    ll = {k[3:]: g[k] for k in g.files if k.startswith("ll_")}
+    lines = prepare_vald_linelist(ll, g["ions"], g["ionization_index"], g["ionization_energy"], int(g["max_atomic_number"]),
+                                  shortlist=(kind == "short"))
+    assert len(lines) == g[f"{kind}_alpha"].shape[0]
+    for col in ("atomic_number", "ion_number", "nu", "level_energy_lower", "level_energy_upper", "A_ul", "ionization_energy"):
+        np.testing.assert_allclose(getattr(lines, col), g[f"{kind}_lines_{col}"], rtol=1e-14, err_msg=col)
+    assert (lines.g_lo is None) == (kind == "short")
+    with pytest.raises(ValueError):
+        prepare_vald_linelist(ll, g["ions"][:3], g["ionization_index"], g["ionization_energy"], 28)

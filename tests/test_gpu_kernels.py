@@ -240,3 +240,46 @@ def test_k2_far_field_expansion_matches_direct_evaluation_and_oracle(ctx, oracle
     ctx.set_grid(nus, p0, p1)
     ctx.calc_alpha_line(0)
     assert np.array_equal(ctx.get(L.BUF_ALPHA_LINE), results[True][:, p0:p1])
+
+
+# ------------------------------------------------------------------ VALD line strengths on the device
+@pytest.mark.parametrize("kind", ["long", "short"])
+def test_alpha_line_vald_device_vs_reference_golden(ctx, kind):
+    """k_alpha_line_vald against AlphaLineVald / AlphaLineShortlistVald (plasma/base.py:178-455, golden generated from
+    the reference's unmodified classes), then K1 + K2 straight from the device-resident strengths."""
+    from stardis_b200 import _lib as L
+    from stardis_b200.plasma.alpha_line_vald import alpha_line_vald, prepare_vald_linelist
+
+    g = golden("plasma_golden.npz")
+    ll = {k[3:]: g[k] for k in g.files if k.startswith("ll_")}
+    lines = prepare_vald_linelist(ll, g["ions"], g["ionization_index"], g["ionization_energy"], int(g["max_atomic_number"]),
+                                  shortlist=(kind == "short"))
+    T = g["T"]
+    ctx.set_atmosphere(T, np.full(T.size, 1e13), np.full(T.size, 1e16), 1e5)
+    alpha_line_vald(ctx, lines, g["ion_number_density"], g["partition_function"], masses=np.full(len(lines), 9.3e-23))
+    got = ctx.get(L.BUF_LINE_STRENGTH)
+    np.testing.assert_allclose(got, g[f"{kind}_alpha"], rtol=1e-13)
+    # the line table is usable as it is: broadening + line opacity without a host copy of alpha_line
+    order = np.argsort(lines.nu, kind="stable")
+    assert np.all(np.diff(lines.nu[order]) >= 0)
+    nus = 2.99792458e18 / np.arange(3000.0, 9000.0, 0.5)
+    ctx.set_grid(nus)
+    ctx.calc_broadening(L.RADIATION | L.VAN_DER_WAALS | L.QUADRATIC_STARK)
+    ctx.calc_alpha_line(0)
+    from_device = ctx.get(L.BUF_ALPHA_LINE)
+    gam, dws = ctx.get(L.BUF_GAMMAS), ctx.get(L.BUF_DOPPLER)
+    # same run with the reference's (L, D) array uploaded from the host
+    ctx.set_lines(lines.nu, g[f"{kind}_alpha"], mass=np.full(len(lines), 9.3e-23), atomic_number=lines.atomic_number,
+                  ion_number=lines.ion_number, ionization_energy=lines.ionization_energy,
+                  level_energy_upper=lines.level_energy_upper, level_energy_lower=lines.level_energy_lower, A_ul=lines.A_ul)
+    ctx.set_broadening(gam, dws)
+    ctx.calc_alpha_line(0)
+    np.testing.assert_allclose(from_device, ctx.get(L.BUF_ALPHA_LINE), rtol=1e-10, atol=1e-300)
+    # the short format keeps auto-ionising lines (plasma/base.py:455): their n_eff, hence gamma, is NaN (K1b quirk)
+    assert (np.isfinite(from_device).all() or kind == "short") and np.nanmax(from_device) > 0
+    from stardis_b200._lib import StardisB200Error
+
+    ctx.set_lines(lines.nu, None)
+    ctx.set_broadening(gam, dws)
+    with pytest.raises(StardisB200Error):
+        ctx.calc_alpha_line(0)  # no strengths yet -> loud error, not garbage

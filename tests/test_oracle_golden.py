@@ -147,3 +147,26 @@ def test_raytrace_golden(oracle):
     F, I_nus = oracle.raytrace(T, alphas, nus, th, w, r=g["r_sph"], spherical=True, reference_r=float(g["refr_sph"]), track=True)
     np.testing.assert_allclose(F, g["F_sph"], rtol=1e-12, atol=1e-300)
     np.testing.assert_allclose(I_nus, g["I_sph"], rtol=1e-12, atol=1e-300)
+
+
+# ------------------------------------------------------------------ VALD line strengths
+def _vald_inputs(g):
+    ll = {k[3:]: g[k] for k in g.files if k.startswith("ll_")}
+    return ll
+
+
+@pytest.mark.parametrize("kind", ["long", "short"])
+def test_alpha_line_vald_oracle_vs_reference_golden(oracle, kind):
+    """oracle.alpha_line_vald against AlphaLineVald / AlphaLineShortlistVald (plasma/base.py:178-455) run unmodified
+    through oracle/ref_shim_plasma.py (tests/golden/plasma_golden.npz)."""
+    g = golden("plasma_golden.npz")
+    ll = _vald_inputs(g)
+    alphas, lines = oracle.alpha_line_vald(ll["atomic_number"], ll["ion_charge"], ll["wavelength"], ll["log_gf"], ll["e_low"],
+                                           ll["e_up"], ll["j_lo"], ll["rad"], g["ions"], g["ion_number_density"],
+                                           g["partition_function"], g["T"], g["ionization_index"], g["ionization_energy"],
+                                           int(g["max_atomic_number"]), shortlist=(kind == "short"))
+    assert alphas.shape == g[f"{kind}_alpha"].shape
+    np.testing.assert_allclose(alphas, g[f"{kind}_alpha"], rtol=1e-14)
+    for col in ("atomic_number", "ion_number", "nu", "level_energy_lower", "level_energy_upper", "A_ul", "ionization_energy"):
+        np.testing.assert_allclose(lines[col], g[f"{kind}_lines_{col}"], rtol=1e-14, err_msg=col)
+    assert (kind == "long") == (alphas.shape[0] < (ll["atomic_number"] <= 28).sum())  # auto-ionising lines dropped (long only)
