@@ -1,6 +1,6 @@
 #!/bin/bash
-# 1/2/4/8-GPU scaling of bench.py (run under gpurun --gpus 8)
-for n in 1 2 4 8; do
+# multi-GPU scaling of bench.py (run under gpurun --gpus 8): usage scale_run.sh "4 8"
+for n in ${1:-1 2 4 8}; do
   if [ $n -eq 1 ]; then
     python bench.py --gpus 1 --steps 5 --warmup 3 --no-cpu-baseline 2>&1 | tail -1 > gpurun_out/scale_$n.json
   else
