@@ -378,9 +378,13 @@ def run_b200_arm(args):
     nus_host = u.Quantity(nus, u.Hz)
     h_spec = torch.empty(W, dtype=torch.float64).pin_memory()
     sel = ob.select_lines(plasma, model, nus_host, line_cfg)
+    # per rank: grid + per-line columns + this rank's row block of the (L, D) strengths (striped upload, the other blocks
+    # arrive over NVLink: distributed.upload_rows_striped) + atmosphere
+    from stardis_b200.distributed import stripe_rows
+    r0, r1, _ = stripe_rows(len(sel), rank, world)
     h2d = int(pinned_nus.numel() * 8 + sum(np.asarray(getattr(sel, k)).nbytes for k in
-              ("nu", "alpha_line", "mass", "atomic_number", "ion_number", "ionization_energy", "level_energy_upper",
-               "level_energy_lower", "A_ul")) + 3 * D * 8)
+              ("nu", "mass", "atomic_number", "ion_number", "ionization_energy", "level_energy_upper",
+               "level_energy_lower", "A_ul")) + (r1 - r0) * D * 8 + 3 * D * 8)
     d2h = int(W * 8)
 
     def api_step():

@@ -126,3 +126,34 @@ def allgather_columns(local, shard, n_total, bounds=None):
     dist.all_gather(pieces, padded)
     full = torch.cat([p[:, : b - a] for p, (a, b) in zip(pieces, bounds)], dim=1)
     return full if is_tensor else full.cpu().numpy()
+
+
+def stripe_rows(n_rows, rank, world_size):
+    """Row block [r0, r1) of an (n_rows, D) host array that rank `rank` uploads in ``upload_rows_striped`` (equal blocks
+    of ceil(n_rows / world) rows; the last ones may be short or empty)."""
+    rows = -(-int(n_rows) // int(world_size))
+    r0 = min(rank * rows, n_rows)
+    return r0, min(r0 + rows, n_rows), rows
+
+
+def upload_rows_striped(host_array, device):
+    """(n, D) float64 HOST array, identical on every rank -> the same array in the HBM of every rank, moved over PCIe only
+    once in total: every rank uploads 1/world of the rows and the blocks are exchanged with one NCCL all-gather over
+    NVLink (gloo in the CPU test).  The (L, D) line-strength table is the largest host->device transfer of a run
+    (134 MB at the flagship size); in a sharded run every rank needs all of it, and 8 ranks pulling it through the host
+    at the same time is what keeps the end-to-end rate below the device rate.  Returns a torch tensor (n, D) on
+    ``device`` (or the input when there is no process group).  Collective: every rank must call it with the same data."""
+    import torch
+
+    dist, rank, world = dist_info()
+    if dist is None or world == 1:
+        return host_array
+    a = np.ascontiguousarray(host_array, dtype=np.float64)
+    n, d = a.shape
+    r0, r1, rows = stripe_rows(n, rank, world)
+    local = torch.zeros((rows, d), dtype=torch.float64, device=device)
+    if r1 > r0:
+        local[: r1 - r0].copy_(torch.from_numpy(a[r0:r1]), non_blocking=True)
+    full = torch.empty((rows * world, d), dtype=torch.float64, device=device)
+    dist.all_gather_into_tensor(full, local)
+    return full[:n]

@@ -226,12 +226,12 @@ def _line_flags(line_opacity_config):
     return broadening_flags(line_opacity_config.broadening) | (L.VALD if use_vald_broadening else 0)
 
 
-def _device_line_opacity(ctx, stellar_plasma, stellar_model, tracing_nus, line_opacity_config):
+def _device_line_opacity(ctx, stellar_plasma, stellar_model, tracing_nus, line_opacity_config, collective=False):
     """K1 + K2 for the atomic lines on an already prepared context (atmosphere + grid set).  Returns the number of
     lines used."""
     lines = select_lines(stellar_plasma, stellar_model, tracing_nus, line_opacity_config)
     upload_lines_and_broaden(ctx, lines, lines.alpha_line, lines.mass, stellar_model, stellar_plasma,
-                             _line_flags(line_opacity_config))
+                             _line_flags(line_opacity_config), collective=collective)
     logger.info("Calculating line opacities at spectral points.")
     ctx.calc_alpha_line(0)
     return len(lines)
@@ -354,7 +354,9 @@ def calc_alphas(stellar_plasma, stellar_model, stellar_radiation_field, opacity_
     line_cfg = opacity_config.line
     n_lines = None
     if not line_cfg.disable:
-        n_lines = _device_line_opacity(ctx, stellar_plasma, stellar_model, nus_q, line_cfg)
+        # sharded run (every rank of the job is here with the same line table): stripe the big upload
+        n_lines = _device_line_opacity(ctx, stellar_plasma, stellar_model, nus_q, line_cfg,
+                                       collective=getattr(srf, "shard", None) is not None)
         mol = None
         if line_cfg.include_molecules:
             mol = _device_molecular_opacity(ctx, stellar_plasma, stellar_model, nus_q, line_cfg)

@@ -84,10 +84,20 @@ def _line_columns(lines):
     return get, has
 
 
-def upload_lines_and_broaden(ctx, lines, alphas_array, masses, stellar_model, stellar_plasma, flags):
-    """Upload a (sorted, range-selected) line table and run K1.  ``lines``: DataFrame or ColumnarLines."""
+def upload_lines_and_broaden(ctx, lines, alphas_array, masses, stellar_model, stellar_plasma, flags, collective=False):
+    """Upload a (sorted, range-selected) line table and run K1.  ``lines``: DataFrame or ColumnarLines.
+    ``collective``: this is a sharded multi-GPU run in which every rank holds the same table -- the (L, D) strengths
+    then travel over PCIe once in total and reach the other ranks over NVLink (``distributed.upload_rows_striped``)."""
     get, has = _line_columns(lines)
     vald = bool(flags & L.VALD)
+    if collective and alphas_array is not None:
+        import torch
+
+        from ....distributed import upload_rows_striped
+
+        alphas_array = upload_rows_striped(alphas_array, torch.device("cuda", ctx.device))
+        if hasattr(alphas_array, "data_ptr"):
+            torch.cuda.current_stream(ctx.device).synchronize()  # the gather ran on torch's stream, K1 runs on ctx's
     ctx.set_lines(get("nu"), alphas_array, mass=masses, atomic_number=get("atomic_number"), ion_number=get("ion_number"),
                   ionization_energy=get("ionization_energy"), level_energy_upper=get("level_energy_upper"),
                   level_energy_lower=get("level_energy_lower"), A_ul=get("A_ul"),

@@ -395,7 +395,8 @@ import os, sys
 import numpy as np
 import torch.distributed as dist
 sys.path.insert(0, {root!r})
-from stardis_b200.distributed import shard_bounds, allgather_spectrum, allgather_columns, line_balanced_bounds
+from stardis_b200.distributed import (shard_bounds, allgather_spectrum, allgather_columns, line_balanced_bounds,
+                                      upload_rows_striped, stripe_rows)
 rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
 dist.init_process_group("gloo", init_method="tcp://127.0.0.1:{port}", rank=rank, world_size=world)
 N, D = 1001, 5
@@ -424,6 +425,13 @@ try:
     ok = False
 except ValueError:
     pass
+# striped upload of a table every rank holds: each rank contributes its row block, everyone ends up with all rows
+table = np.arange(37 * 3, dtype=np.float64).reshape(37, 3) ** 1.1
+got = upload_rows_striped(table, "cpu")
+ok = ok and tuple(got.shape) == (37, 3) and np.array_equal(got.numpy(), table)
+ok = ok and stripe_rows(37, 0, 2) == (0, 19, 19) and stripe_rows(37, 1, 2) == (19, 37, 19) and stripe_rows(1, 1, 2) == (1, 1, 1)
+got1 = upload_rows_striped(table[:1], "cpu")   # fewer rows than ranks: one rank contributes nothing
+ok = ok and np.array_equal(got1.numpy(), table[:1])
 dist.barrier()
 dist.destroy_process_group()
 sys.exit(0 if ok else 3)
