@@ -299,7 +299,7 @@ __global__ void __launch_bounds__(THREADS) k_far_coeffs(LineArgs a, int lev, int
             n_far++;
         }
         // queue neighbours are neighbours in frequency, at similar distances from the tile: warp-uniform series length
-        const int nt = (count_stats & 2) ? 0 : __reduce_max_sync(0xffffffffu, nterms);  // bit 1: tuning experiment, scan only
+        const int nt = __reduce_max_sync(0xffffffffu, nterms);
         // Im(w^(k+1)) by the real three-term recurrence of the powers of a complex number,
         //   s_(k+1) = 2 Re(w) s_k - |w|^2 s_(k-1),  s_0 = 0, s_1 = Im w,
         // two instructions per pole and term instead of the four of a complex product (the recurrence loses about one
@@ -402,7 +402,7 @@ __global__ void __launch_bounds__(THREADS) k_far_coeffs(LineArgs a, int lev, int
         if (nsplit > 1) part[(tl * nsplit + split) * K1 + lane] = mine;
         else a.far_coef[lev][tl * K1 + lane] = mine;
     }
-    if (count_stats & 1) {  // every far pair stands for one region-I evaluation per tile pixel inside the shard
+    if (count_stats) {  // every far pair stands for one region-I evaluation per tile pixel inside the shard
         for (int o2 = 16; o2; o2 >>= 1) n_far += __shfl_xor_sync(0xffffffffu, n_far, o2);
         const int64_t e0 = t0 > a.p0 ? t0 : a.p0, e1 = t1 < a.p1 ? t1 : a.p1;
         if (lane == 0 && n_far && e1 > e0) atomicAdd(&a.stats[0], n_far * (unsigned long long)(e1 - e0));
@@ -745,7 +745,6 @@ int sd_k2_lines(sd_ctx *c, int slot) {
         }
         // CTAs per (group of eight sibling tiles, depth): the candidate lists are cut into this many fixed slices so that
         // even a narrow shard fills the chip; k_far_reduce adds the partial sums in slice order.
-        static const int far_debug = env_int("SD_FAR_SCAN_ONLY", 0) ? 2 : 0;
         if (!c->far_attr_set) {  // per device: > 48 KB of dynamic shared memory needs the opt-in
             SD_CUDA(c, cudaFuncSetAttribute(k_far_coeffs, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FAR_SMEM));
             c->far_attr_set = true;
@@ -761,7 +760,7 @@ int sd_k2_lines(sd_ctx *c, int slot) {
             // one CTA per group of eight sibling tiles that has a member in the launched range, times the slices
             const int n_cta = (((a.far_tile0[k] + a.far_ntl[k] - 1) >> SD_FAR_SHIFT) - (a.far_tile0[k] >> SD_FAR_SHIFT) + 1) * nsplit;
             k_far_coeffs<<<dim3((unsigned)n_cta, (unsigned)c->D), THREADS, FAR_SMEM, c->stream>>>(
-                a, k, (c->line_stats ? 1 : 0) | far_debug, nsplit, c->far_part.as<double>());
+                a, k, c->line_stats ? 1 : 0, nsplit, c->far_part.as<double>());
             SD_TRY(sd_launch_check(c, "k_far_coeffs"));
             if (nsplit > 1) {
                 const int n = c->D * a.far_ntl[k] * (SD_FAR_K + 1);
