@@ -167,7 +167,8 @@ int sd_set_lines(sd_ctx *c, const sd_lines *ln) {
     if (!c || !ln) return SD_ERR_ARG;
     SD_CHECK(c, c->D > 0, SD_ERR_STATE, "sd_set_lines: call sd_set_atmosphere first");
     int64_t L = ln->n_lines;
-    SD_CHECK(c, L >= 0 && L * (int64_t)c->D < (int64_t)4e9, SD_ERR_ARG, "sd_set_lines: bad line count");
+    SD_CHECK(c, L >= 0 && L * (int64_t)c->D < (int64_t)2147483647, SD_ERR_ARG,
+             "sd_set_lines: bad line count (lines x depth points must stay below 2^31: 32-bit pair indices)");
     SD_CHECK(c, L == 0 || ln->nu, SD_ERR_ARG, "sd_set_lines: nu is required");
     SD_CUDA(c, cudaSetDevice(c->device));
     c->L = L;
