@@ -132,8 +132,9 @@ def cpu_reference_sample(w, cfg, target_seconds, threads=None):
     from stardis_b200 import units as u
 
     O.build()
-    if threads:
-        O.set_threads(threads)
+    # all host cores this process may use, set explicitly: torch.distributed.run exports OMP_NUM_THREADS=1 to its workers
+    # and the reference arm must not be throttled by that
+    O.set_threads(threads or len(os.sched_getaffinity(0)))
     cores = O.max_threads()
     model, plasma, nus = w["model"], w["plasma"], w["nus"]
     N, D = len(nus), model.no_of_depth_points
