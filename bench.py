@@ -2,19 +2,26 @@
 """Benchmark of the STARDIS opacity + formal-solution hot path on B200 (BASELINE.json metric).
 
     python bench.py --gpus N --steps K --warmup W            # this repository's CUDA path
-    python bench.py --impl reference --gpus N --steps K ...  # the CPU port of the reference (oracle/), host cores
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's own numba CPU path on the host cores
+    python bench.py --workload {sim10aa,sim100aa,solar_full,solar_weak,astar,coolgiant_ir,grid_sweep64}
 
 metric  : emergent-spectrum nu-points/sec (opacity + raytrace); a "step" is ONE pass of the hot path over the whole
           frequency grid of the workload: broadening (K1) -> line windows/records -> Voigt accumulation (K2) ->
           continuum + total (K3) -> formal solution for all angles (K4).
-workload: BASELINE.json configs[1]: solar MARCS structure, 3000-10000 A at 0.01 A (N = 700 000), D = 56, 10 angles,
-          all four broadening mechanisms, H- bf table + H I bf/ff + electron scattering, SYNTHETIC line list of
+workload: default = BASELINE.json configs[1]: solar MARCS structure, 3000-10000 A at 0.01 A (N = 700 000), D = 56, 10
+          angles, all four broadening mechanisms, H- bf table + H I bf/ff + electron scattering, SYNTHETIC line list of
           300 000 lines (real Kurucz/CD23 data does not exist offline; recipe in SURVEY.md 8d / plasma/synthetic.py).
+          The other names are the remaining BASELINE configs (and a weak-line regime of the flagship).
 value   : N / (device time of one step), inputs resident in HBM, CUDA events on the launching stream, max over ranks.
 e2e     : same metric through the public API (calc_alphas + raytrace + read of the emergent spectrum) with HOST
           (pinned) inputs: H2D of the line table / grid and D2H of the spectrum inside the timed region.
+parity  : the GPU's total opacity and flux on a sampled nu shard against the CPU oracle evaluated on the same shard in
+          the same run (rtol 1e-8 / 1e-6, BASELINE north_star); the process exits non-zero when it fails.
+roofline: per kernel from EXECUTED work (counting instantiation of the kernels) and the kernel's device time measured
+          live with CUDA events inside the library (sd_phase_times), against the FP64 peak measured in the same run.
 N > 1   : the frequency grid is sharded across ranks (strong scaling; global windows, no exchange inside the
-          kernels); the emergent spectrum is all-gathered with NCCL inside the timed region.
+          kernels); the emergent spectrum is all-gathered with NCCL inside the timed region.  grid_sweep64 instead
+          scatters 64 independent stellar models over the ranks (replicas, spectra gathered).
 """
 from __future__ import annotations
 
@@ -32,8 +39,14 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+METRIC = "emergent-spectrum nu-points/sec (opacity+raytrace)"
 FLOPS_PER_EVAL = np.array([19.0, 33.0, 65.0, 164.0])  # Humlicek regions I..IV, FMA = 2 flops
 BYTES_PER_CELL = 16.0                                  # write total_alphas + write F_nu
+# executed work of the far-field path, FP64 flops (FMA = 2), counted from the source (csrc/k2_lines.cu):
+FLOPS_FAR_SETUP = 38.0   # per (pair, tile) expansion: pole distances, two reciprocals, recurrence constants
+FLOPS_FAR_TERM = 9.0     # per Taylor term: coefficient FMA + add, two three-term recurrences (FMA + MUL each)
+FLOPS_HORNER = 43.0      # per (pixel, depth, level): 20 Horner FMAs + scaled argument + accumulate
+ALPHA_RTOL, F_RTOL = 1e-8, 1e-6
 
 
 def parse_args():
@@ -45,34 +58,45 @@ def parse_args():
     ap.add_argument("--workload", default="solar_full")
     ap.add_argument("--lines", type=int, default=None, help="override the number of synthetic lines")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-direct", action="store_true", help="skip the direct-mode (far field off) comparison run")
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="target CPU time of one reference sample")
+    ap.add_argument("--cpu-kind", default="reference", choices=["reference", "port"],
+                    help="CPU leg: the reference's numba path (oracle/_ref) or the C port (oracle/)")
     return ap.parse_args()
 
 
 # ----------------------------------------------------------------------------------------------- workload
-def opacity_config(table_dir):
-    from stardis_b200.data import write_cross_section_files
+def opacity_config(table_dir, n_thetas):
     from stardis_b200.io.config import Configuration, validate_config
+    from stardis_b200.synthetic import write_cross_section_files
 
     paths = write_cross_section_files(table_dir)
     raw = dict(stardis_config_version=1.0, atom_data="synthetic:0", input_model=dict(type="marcs", fname="sun.mod"),
                opacity=dict(file={"Hminus_bf": paths["Hminus_bf"]}, bf={"H_I": {}}, ff={"H_I": {}},
                             disable_electron_scattering=False,
                             line=dict(disable=False, broadening=["radiation", "linear_stark", "quadratic_stark", "van_der_waals"])),
-               no_of_thetas=10)
+               no_of_thetas=n_thetas)
     return Configuration(validate_config(raw))
 
 
-def build_workload(args):
+def build_workload(args, name=None):
     from stardis_b200.synthetic import WORKLOADS, make_workload
 
-    w = make_workload(args.workload, seed=1, n_lines=args.lines)
-    cfg = opacity_config(tempfile.mkdtemp(prefix="sdb200_tables_"))
-    cfg["no_of_thetas"] = WORKLOADS[args.workload][5]
-    desc = (f"{args.workload}: MARCS solar structure D={len(w['atmosphere']['T'])}, lambda {w['lambdas'].value[0]:.0f}-"
-            f"{w['lambdas'].value[-1]:.0f} A step 0.01 (N={len(w['nus'])}), {len(w['plasma']._line_table)} synthetic lines, "
-            f"{cfg.no_of_thetas} angles, 4 broadenings, Hminus_bf+H_I bf/ff+e- continuum")
+    name = name or args.workload
+    w = make_workload(name, seed=1, n_lines=args.lines)
+    cfg = opacity_config(tempfile.mkdtemp(prefix="sdb200_tables_"), WORKLOADS[name][5])
+    desc = (f"{name}: MARCS {WORKLOADS[name][0]} structure (T x {WORKLOADS[name][1]:.3f}) D={len(w['atmosphere']['T'])}, lambda "
+            f"{w['lambdas'].value[0]:.0f}-{w['lambdas'].value[-1]:.0f} A step 0.01 (N={len(w['nus'])}), "
+            f"{len(w['plasma']._line_table)} synthetic lines, {cfg.no_of_thetas} angles, 4 broadenings, "
+            f"Hminus_bf+H_I bf/ff+e- continuum")
     return w, cfg, desc
+
+
+def config_block(desc, n_lines, D, cells, world, bounds):
+    return {"workload": desc,
+            "l2": "inputs larger than L2 (line records %.2f GB, outputs %.2f GB per array)" % (n_lines * D * 64 / 1e9, cells * 8 / 1e9),
+            "partition": f"{world} contiguous nu range(s), global windows, cut at equal (pixels + 10 x lines inside)",
+            "ranges": [list(b) for b in bounds]}
 
 
 # ----------------------------------------------------------------------------------------------- clocks
@@ -122,88 +146,120 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------------------------- CPU reference arm
-def cpu_reference_sample(w, cfg, target_seconds, threads=None):
-    """The CPU port of the reference (oracle/, C + OpenMP over all host cores) on a bounded SAMPLE of the workload: a
-    contiguous nu shard in the middle of the grid, evaluated with GLOBAL windows (the same decomposition the multi-GPU
-    path uses), sized by a calibration shard so that one sample takes about ``target_seconds``.
-    Returns (nu-points/s, description, cores)."""
-    from oracle import oracle as O
-    from stardis_b200.radiation_field.opacities.opacities_solvers import base as ob
-    from stardis_b200 import units as u
-
-    O.build()
-    # all host cores this process may use, set explicitly: torch.distributed.run exports OMP_NUM_THREADS=1 to its workers
-    # and the reference arm must not be throttled by that
-    O.set_threads(threads or len(os.sched_getaffinity(0)))
-    cores = O.max_threads()
-    model, plasma, nus = w["model"], w["plasma"], w["nus"]
-    N, D = len(nus), model.no_of_depth_points
-    T = u.values_of(model.temperatures)
-    lt = plasma._line_table.with_masses(model.composition.nuclide_masses)
-    lines = dict(nu=lt.nu, atomic_number=lt.atomic_number, ion_number=lt.ion_number, ionization_energy=lt.ionization_energy,
-                 level_energy_upper=lt.level_energy_upper, level_energy_lower=lt.level_energy_lower, A_ul=lt.A_ul, mass=lt.mass)
-    n_e = plasma.electron_densities.values
-    n_H = plasma.ion_number_density.loc[1, 0].values
-    vmic = float(u.cgs_values_of(model.microturbulence))
-    th, wts = O.thetas_and_weights(cfg.no_of_thetas)
-    dist = model.geometry.dist_to_next_depth_point
-    bf_levels = plasma.levels
-    exc = plasma.excitation_energy.values
-    nu_cut = (float(plasma.ionization_data.loc[(1, 1)]) - exc) / ob.H_CGS
-    hm_path = cfg.opacity.file["Hminus_bf"]
-
-    def run(p0, p1):
-        t0 = time.perf_counter()
-        gam, dws = O.calc_broadening(lines, T, n_e, n_H, vmic, 15)
-        t1 = time.perf_counter()
-        a_line, evals, _ = O.calc_alan_entries(D, nus, lt.nu, dws, gam, lt.alpha_line, p0=p0, p1=p1, with_stats=True)
-        sub = nus[p0:p1]
-        total = O.alpha_file(sub, T, hm_path, "Hminus_bf", plasma.h_minus_density.values)
-        total = total + O.alpha_bf(sub, nu_cut, np.ones(len(nu_cut)), plasma.level_number_density.values)
-        total = total + O.alpha_ff(sub, [(1, n_e * plasma.ion_number_density.loc[1, 1].values)], T)
-        total = total + O.alpha_electron(n_e, p1 - p0) + a_line
-        F, _ = O.raytrace(T, total, sub, th, wts, dist=dist)
-        t2 = time.perf_counter()
-        return t2 - t0, evals, t1 - t0, t2 - t1
-
-    # calibration shard -> per-pixel cost -> shard width for the requested CPU time
-    mid = N // 2
-    cal = 64
-    _, _, t_fix, t_var = run(mid - cal // 2, mid + cal // 2)
-    _, _, t_fix, t_var = run(mid - cal // 2, mid + cal // 2)
-    width = int(np.clip((target_seconds - t_fix) / max(t_var / cal, 1e-7), cal, N))
-    p0 = max(0, mid - width // 2)
-    p1 = min(N, p0 + width)
-    t, evals, _, _ = run(p0, p1)
-    sample = (f"contiguous nu shard of {p1 - p0} pixels [{p0},{p1}) of the {N}-pixel grid, all {len(lt)} lines with global "
-              f"windows, {evals:.3e} Voigt evaluations, {t:.1f} s on {cores} OpenMP threads (oracle/stardis_oracle.c)")
-    return (p1 - p0) / t, sample, cores, t
+def cpu_block(r):
+    out = {"value": r["value"], "unit": "nu-points/s", "cores": r["cores"], "kind": r["kind"], "sample": r["sample"]}
+    if "full_step_seconds" in r:
+        out["full_step_seconds"] = r["full_step_seconds"]
+    return out
 
 
 def run_reference_arm(args):
+    """The reference's own CPU implementation of the path (its numba-parallel functions, executed unmodified from
+    oracle/_ref through oracle/ref_shim.py; the C port when numba or the staged modules are missing -- `kind` says
+    which), all host cores, each step one bounded sample of the workload."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    w, cfg, desc = build_workload(args)
-    vals, sample, cores = [], "", 1
+    from oracle import ref_leg
+
+    name = "solar_full" if args.workload == "grid_sweep64" else args.workload
+    w, cfg, desc = build_workload(args, name)
+    vals, r = [], None
     for i in range(args.warmup + args.steps):
         secs = args.cpu_seconds if i >= args.warmup else min(args.cpu_seconds, 3.0)
-        v, sample, cores, t = cpu_reference_sample(w, cfg, secs)
+        r = ref_leg.cpu_sample(w, cfg, secs, prefer=args.cpu_kind)
         if i >= args.warmup:
-            vals.append((v, t))
+            vals.append((r["value"], r["seconds"]))
     value = float(np.mean([v for v, _ in vals]))
     ms = float(np.mean([t for _, t in vals]) * 1e3)
-    out = {"impl": "reference", "metric": "emergent-spectrum nu-points/sec (opacity+raytrace)", "value": value,
-           "unit": "nu-points/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
-           "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-           "config": {"workload": desc},
-           "cpu_baseline": {"value": value, "unit": "nu-points/s", "cores": cores, "kind": "port", "sample": sample},
+    N, D, L = len(w["nus"]), w["model"].no_of_depth_points, len(w["plasma"]._line_table)
+    blk = cpu_block(r)
+    blk["value"] = value
+    out = {"impl": "reference", "metric": METRIC, "value": value, "unit": "nu-points/s", "n_gpus": args.gpus,
+           "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong",
+           "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+           "config": config_block(desc, L, D, D * N, 1, [(0, N)]), "cpu_baseline": blk,
            "e2e": {"value": value, "unit": "nu-points/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
            "gpu_launches": 0}
     print(json.dumps(out), flush=True)
 
 
 # ----------------------------------------------------------------------------------------------- B200 arm
+def rel_err(a, b):
+    """max |a - b| / |b| with 0/0 = 0 (np.testing.assert_allclose semantics, atol = 0)."""
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    diff = np.abs(a - b)
+    den = np.abs(b)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        r = np.where(diff == 0.0, 0.0, diff / den)
+    return float(np.nanmax(r)) if r.size else 0.0
+
+
+class HotPath:
+    """Resident inputs of one workload on one context + the device step (pointers into the C ABI)."""
+
+    def __init__(self, ctx, w, cfg, rank, world, torch):
+        from stardis_b200 import _lib as L
+        from stardis_b200 import units as u
+        from stardis_b200.distributed import line_balanced_bounds
+        from stardis_b200.radiation_field import RadiationField
+        from stardis_b200.radiation_field.opacities.opacities_solvers import base as ob
+        from stardis_b200.radiation_field.opacities.opacities_solvers.broadening import set_device_atmosphere
+        from stardis_b200.radiation_field.radiation_field_solvers.base import ray_distances
+
+        self.L_, self.ctx, self.torch, self.world = L, ctx, torch, world
+        model, plasma, nus = w["model"], w["plasma"], w["nus"]
+        self.model, self.plasma, self.nus, self.cfg = model, plasma, nus, cfg
+        self.N, self.D = len(nus), model.no_of_depth_points
+        line_cfg = cfg.opacity.line
+        self.nus_q = u.Quantity(nus, u.Hz)
+        self.lines = ob.select_lines(plasma, model, self.nus_q, line_cfg)
+        # cost-balanced contiguous nu ranges (pixels + 10 x lines inside): the blue end of the grid holds ~10x more
+        # lines per pixel than the red end, so equal-width ranges would leave rank 0 with several times the core work
+        self.bounds = line_balanced_bounds(nus, self.lines.nu, world)
+        self.p0, self.p1 = self.bounds[rank]
+        self.W = self.p1 - self.p0
+        self.flags = ob._line_flags(line_cfg)
+        self.tables, _ = ob.file_tables(plasma, model, cfg.opacity.file)
+        self.bf_cut, self.bf_prefix = ob.bf_descriptor(plasma, cfg.opacity.bf)
+        self.ff_coef = ob.ff_descriptor(plasma, model, cfg.opacity.ff)
+        self.rayleigh = ob.rayleigh_descriptor(plasma, model, cfg.opacity.rayleigh)
+        self.electron = ob.electron_descriptor(plasma)
+        self.srf0 = RadiationField(self.nus_q, None, model, cfg.no_of_thetas)
+        self.ds, self.inward = ray_distances(model, self.srf0.thetas)
+        self.set_atmosphere = lambda: set_device_atmosphere(ctx, model, plasma)
+        self.set_atmosphere()
+        ctx.set_grid(nus, self.p0, self.p1)
+        self.d_lines = {k: torch.from_numpy(np.ascontiguousarray(getattr(self.lines, k))).cuda() for k in
+                        ("nu", "alpha_line", "mass", "atomic_number", "ion_number", "ionization_energy", "level_energy_upper",
+                         "level_energy_lower", "A_ul")}
+        self.d_spec = torch.empty(self.W, dtype=torch.float64, device="cuda")
+
+    def step(self, ev=None, stream=None, gather=True):
+        """One pass of the hot path on resident inputs."""
+        from stardis_b200.distributed import allgather_spectrum
+
+        ctx, d, L = self.ctx, self.d_lines, self.L_
+        rec = (lambda i: ev[i].record(stream)) if ev is not None else (lambda i: None)
+        rec(0)
+        ctx.set_lines(d["nu"], d["alpha_line"], mass=d["mass"], atomic_number=d["atomic_number"], ion_number=d["ion_number"],
+                      ionization_energy=d["ionization_energy"], level_energy_upper=d["level_energy_upper"],
+                      level_energy_lower=d["level_energy_lower"], A_ul=d["A_ul"])
+        ctx.calc_broadening(self.flags)                       # K1
+        rec(1)
+        ctx.calc_alpha_line(0)                                # K2 (+ window/record preparation)
+        rec(2)
+        ctx.calc_continuum(bf_nu_cut=self.bf_cut, bf_prefix=self.bf_prefix, ff_coef=self.ff_coef, rayleigh=self.rayleigh,
+                           electron=self.electron, tables=self.tables, store_mask=0)  # K3
+        rec(3)
+        ctx.raytrace(self.ds, self.srf0.I_nus_weights, inward_rays=self.inward)  # K4
+        rec(4)
+        ctx.get_row(L.BUF_F_NU, -1, out=self.d_spec)
+        if self.world > 1 and gather:
+            allgather_spectrum(self.d_spec, (self.p0, self.p1), self.N, bounds=self.bounds)
+        rec(5)
+
+
 def run_b200_arm(args):
     import torch
     import torch.distributed as dist
@@ -211,11 +267,10 @@ def run_b200_arm(args):
     from stardis_b200 import _lib as L
     from stardis_b200 import units as u
     from stardis_b200.device import DeviceContext
-    from stardis_b200.distributed import allgather_spectrum, line_balanced_bounds
+    from stardis_b200.distributed import allgather_spectrum, stripe_rows
     from stardis_b200.radiation_field import RadiationField
     from stardis_b200.radiation_field.opacities.opacities_solvers import base as ob
-    from stardis_b200.radiation_field.opacities.opacities_solvers.broadening import set_device_atmosphere, upload_lines_and_broaden
-    from stardis_b200.radiation_field.radiation_field_solvers.base import ray_distances, raytrace
+    from stardis_b200.radiation_field.radiation_field_solvers.base import raytrace
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -225,10 +280,6 @@ def run_b200_arm(args):
     torch.cuda.set_device(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-
-    w, cfg, desc = build_workload(args)
-    model, plasma, nus = w["model"], w["plasma"], w["nus"]
-    N, D = len(nus), model.no_of_depth_points
     stream = torch.cuda.Stream()  # all kernels, copies and timing events of this benchmark live on this stream
     torch.cuda.set_stream(stream)
     ctx = DeviceContext(local_rank, stream=stream)
@@ -238,83 +289,54 @@ def run_b200_arm(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- resident inputs (uploaded once, outside the timed region)
-    line_cfg = cfg.opacity.line
-    nus_q = u.Quantity(nus, u.Hz)
-    lines = ob.select_lines(plasma, model, nus_q, line_cfg)
-    # cost-balanced contiguous nu ranges (pixels + 10 x lines inside): the blue end of the grid holds ~10x more lines per
-    # pixel than the red end, so equal-width ranges would leave rank 0 with several times the line-core work
-    bounds = line_balanced_bounds(nus, lines.nu, world)
-    p0, p1 = bounds[rank]
-    W = p1 - p0
-    flags = ob._line_flags(line_cfg)
-    tables, _ = ob.file_tables(plasma, model, cfg.opacity.file)
-    bf_cut, bf_prefix = ob.bf_descriptor(plasma, cfg.opacity.bf)
-    ff_coef = ob.ff_descriptor(plasma, model, cfg.opacity.ff)
-    rayleigh = ob.rayleigh_descriptor(plasma, model, cfg.opacity.rayleigh)
-    electron = ob.electron_descriptor(plasma)
-    srf0 = RadiationField(nus_q, None, model, cfg.no_of_thetas)
-    ds, inward = ray_distances(model, srf0.thetas)
-    set_device_atmosphere(ctx, model, plasma)
-    ctx.set_grid(nus, p0, p1)
-    d_lines = {k: torch.from_numpy(np.ascontiguousarray(getattr(lines, k))).cuda() for k in
-               ("nu", "alpha_line", "mass", "atomic_number", "ion_number", "ionization_energy", "level_energy_upper",
-                "level_energy_lower", "A_ul")}
-    d_spec = torch.empty(W, dtype=torch.float64, device="cuda")
-    ev = [torch.cuda.Event(enable_timing=True) for _ in range(6)]
-
-    def device_step(record=False):
-        """One pass of the hot path on resident inputs (device pointers into the C ABI)."""
-        if record: ev[0].record(stream)
-        ctx.set_lines(d_lines["nu"], d_lines["alpha_line"], mass=d_lines["mass"], atomic_number=d_lines["atomic_number"],
-                      ion_number=d_lines["ion_number"], ionization_energy=d_lines["ionization_energy"],
-                      level_energy_upper=d_lines["level_energy_upper"], level_energy_lower=d_lines["level_energy_lower"],
-                      A_ul=d_lines["A_ul"])
-        ctx.calc_broadening(flags)                       # K1
-        if record: ev[1].record(stream)
-        ctx.calc_alpha_line(0)                           # K2 (+ window/record preparation)
-        if record: ev[2].record(stream)
-        ctx.calc_continuum(bf_nu_cut=bf_cut, bf_prefix=bf_prefix, ff_coef=ff_coef, rayleigh=rayleigh, electron=electron,
-                           tables=tables, store_mask=0)  # K3
-        if record: ev[3].record(stream)
-        ctx.raytrace(ds, srf0.I_nus_weights, inward_rays=inward)  # K4
-        if record: ev[4].record(stream)
-        ctx.get_row(L.BUF_F_NU, -1, out=d_spec)
+    def max_over_ranks(x):
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
         if world > 1:
-            allgather_spectrum(d_spec, (p0, p1), N, bounds=bounds)
-        if record: ev[5].record(stream)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    if args.workload == "grid_sweep64":
+        return run_grid_sweep(args, ctx, stream, rank, world, local_rank, barrier, max_over_ranks)
+
+    w, cfg, desc = build_workload(args)
+    hp = HotPath(ctx, w, cfg, rank, world, torch)
+    model, plasma, nus, N, D, W, p0, p1, bounds = hp.model, hp.plasma, hp.nus, hp.N, hp.D, hp.W, hp.p0, hp.p1, hp.bounds
+    line_cfg = cfg.opacity.line
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(6)]
 
     sampler = ClockSampler(local_rank)  # sampled from the warm-up on: the timed region itself may last < 1 s
     sampler.start()
-    for _ in range(args.warmup):
-        device_step()
+    for _ in range(max(args.warmup, 3)):
+        hp.step()
     barrier()
     launches0 = ctx.launch_count()
     phase = np.zeros(5)
+    kern = {}
     t_start = torch.cuda.Event(enable_timing=True)
     t_end = torch.cuda.Event(enable_timing=True)
     barrier()
     t_start.record(stream)
     for _ in range(args.steps):
-        device_step(record=True)
+        hp.step(ev, stream)
         ev[5].synchronize()
+        ctx._keep.clear()
         phase += [ev[i].elapsed_time(ev[i + 1]) for i in range(5)]
+        for k, v in ctx.phase_times().items():  # per-kernel device times of this step (events inside the library)
+            kern[k] = kern.get(k, 0.0) + max(v, 0.0)
     t_end.record(stream)
     barrier()
     clocks = sampler.stop()
     launches = ctx.launch_count() - launches0
-    ms_total = t_start.elapsed_time(t_end)
-    t = torch.tensor([ms_total], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_per_step = float(t.item()) / args.steps
+    ms_per_step = max_over_ranks(t_start.elapsed_time(t_end)) / args.steps
     phase /= args.steps
+    kern = {k: v / args.steps for k, v in kern.items()}
     value = N / (ms_per_step * 1e-3)
 
-    # ---- K2 statistics (untimed): Voigt evaluations per Humlicek region -> algorithmic flops
+    # ---- K2 statistics (untimed): executed work of the default mode + reference-equivalent evaluation counts
     ctx.set_line_stats(True)
     ctx.calc_alpha_line(0)
     stats = ctx.line_stats()
+    ex = ctx.line_stats_ex()
     ctx.set_line_stats(False)
     reg = torch.tensor(stats["region_evals"].astype(np.float64), device="cuda")
     if world > 1:
@@ -336,52 +358,74 @@ def run_b200_arm(args):
         return float(np.mean(ms))
 
     k2_far_ms = time_k2(max(2, args.steps))
-    a_far = torch.empty((D, W), dtype=torch.float64, device="cuda")
-    ctx.get(L.BUF_ALPHA_LINE, out=a_far)
-    # ---- the same step with the far-field expansion switched OFF: every (line, depth, pixel) triple is evaluated
-    # directly, like the reference's loop.  This is the kernel the FP64 roofline is quoted for.
-    ctx.set_farfield(False)
-    device_step()
-    barrier()
-    n_direct = max(1, args.steps // 3)
-    td0, td1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    td0.record(stream)
-    for _ in range(n_direct):
-        device_step()
-    td1.record(stream)
-    barrier()
-    t = torch.tensor([td0.elapsed_time(td1) / n_direct], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_direct = float(t.item())
-    k2_kernel_ms = time_k2(max(1, n_direct))
-    a_dir = torch.empty((D, W), dtype=torch.float64, device="cuda")
-    ctx.get(L.BUF_ALPHA_LINE, out=a_dir)
-    torch.cuda.synchronize()
-    far_dev = float(((a_far - a_dir).abs() / a_dir.abs().clamp_min(1e-300)).max().item())
-    del a_far, a_dir
-    ctx.set_farfield(True)
-    ctx.calc_alpha_line(0)
     dfma_peak = ctx.bench_dfma(8192)
-    flops = float((stats["region_evals"] * FLOPS_PER_EVAL).sum())  # this rank's launch
-    achieved_tflops = flops / (k2_kernel_ms * 1e-3) / 1e12
+
+    # ---- the same step with the far-field expansion switched OFF: every (line, depth, pixel) triple is evaluated
+    # directly, like the reference's loop ("roofline_direct").
+    direct = None
+    if not args.no_direct:
+        a_far = torch.empty((D, W), dtype=torch.float64, device="cuda")
+        ctx.get(L.BUF_ALPHA_LINE, out=a_far)
+        ctx.set_farfield(False)
+        hp.step()
+        barrier()
+        n_direct = max(1, args.steps // 3)
+        td0, td1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        td0.record(stream)
+        for _ in range(n_direct):
+            hp.step()
+        td1.record(stream)
+        barrier()
+        ms_direct = max_over_ranks(td0.elapsed_time(td1) / n_direct)
+        k2_kernel_ms = time_k2(max(1, n_direct))
+        a_dir = torch.empty((D, W), dtype=torch.float64, device="cuda")
+        ctx.get(L.BUF_ALPHA_LINE, out=a_dir)
+        torch.cuda.synchronize()
+        far_dev = float(((a_far - a_dir).abs() / a_dir.abs().clamp_min(1e-300)).max().item())
+        del a_far, a_dir
+        ctx.set_farfield(True)
+        flops_direct = float((stats["region_evals"] * FLOPS_PER_EVAL).sum())  # this rank's launch
+        direct = dict(ms_per_step=ms_direct, k2_ms=k2_kernel_ms, far_dev=far_dev,
+                      tflops=flops_direct / (k2_kernel_ms * 1e-3) / 1e12)
+    hp.step()  # default mode again: the buffers hold this rank's total opacity and flux
+    barrier()
+
+    # ---- parity on the benched workload: GPU total opacity / flux on a sampled shard vs the CPU oracle (rank 0)
+    parity, port = None, None
+    if rank == 0 and not args.no_cpu_baseline:
+        from oracle import ref_leg
+
+        port = ref_leg.port_sample(w, cfg, args.cpu_seconds if args.cpu_kind == "port" else min(args.cpu_seconds, 8.0),
+                                   centre=(p0 + p1) // 2, limits=(p0, p1))
+        s0, s1 = port["p0"] - p0, port["p1"] - p0
+        g_total = torch.empty((D, W), dtype=torch.float64, device="cuda")
+        ctx.get(L.BUF_TOTAL, out=g_total)
+        a_gpu = g_total[:, s0:s1].cpu().numpy()
+        ctx.get(L.BUF_F_NU, out=g_total)
+        f_gpu = g_total[:, s0:s1].cpu().numpy()
+        del g_total
+        parity = {"alpha_max_rel": rel_err(a_gpu, port["total"]), "F_max_rel": rel_err(f_gpu, port["F"]),
+                  "pixels": [int(port["p0"]), int(port["p1"])], "rtol_alpha": ALPHA_RTOL, "rtol_F": F_RTOL,
+                  "checker": "oracle/stardis_oracle.c on the same shard, same run"}
+        parity["ok"] = bool(parity["alpha_max_rel"] <= ALPHA_RTOL and parity["F_max_rel"] <= F_RTOL)
 
     # ---- end to end through the public API with pinned host inputs
     lt = plasma._line_table
     for name in ("nu", "alpha_line", "atomic_number", "ion_number", "ionization_energy", "level_energy_upper",
                  "level_energy_lower", "A_ul", "mass"):
         a = getattr(lt, name)
+        if a is None:
+            continue
         pinned = torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
         setattr(lt, name, pinned.numpy())
         lt.__dict__.setdefault("_pins", []).append(pinned)
     lt._no_autoion = None
     pinned_nus = torch.from_numpy(nus.copy()).pin_memory()
-    nus_host = u.Quantity(nus, u.Hz)
+    nus_host = u.Quantity(pinned_nus.numpy(), u.Hz)
     h_spec = torch.empty(W, dtype=torch.float64).pin_memory()
     sel = ob.select_lines(plasma, model, nus_host, line_cfg)
     # per rank: grid + per-line columns + this rank's row block of the (L, D) strengths (striped upload, the other blocks
     # arrive over NVLink: distributed.upload_rows_striped) + atmosphere
-    from stardis_b200.distributed import stripe_rows
     r0, r1, _ = stripe_rows(len(sel), rank, world)
     h2d = int(pinned_nus.numel() * 8 + sum(np.asarray(getattr(sel, k)).nbytes for k in
               ("nu", "mass", "atomic_number", "ion_number", "ionization_energy", "level_energy_upper",
@@ -403,24 +447,27 @@ def run_b200_arm(args):
     api_step()
     barrier()
     t0 = time.perf_counter()
-    n_e2e = max(1, min(args.steps, 3))
+    n_e2e = max(1, min(args.steps, 5))
     for _ in range(n_e2e):
         api_step()
     barrier()
-    te = torch.tensor([(time.perf_counter() - t0) / n_e2e], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_value = N / float(te.item())
+    e2e_value = N / max_over_ranks((time.perf_counter() - t0) / n_e2e)
 
+    rc = 0
     if rank == 0:
         cpu = None
-        if not args.no_cpu_baseline and world == 1:
-            v, sample, cores, _ = cpu_reference_sample(w, cfg, args.cpu_seconds)
-            cpu = {"value": v, "unit": "nu-points/s", "cores": cores, "kind": "port", "sample": sample}
+        if not args.no_cpu_baseline:
+            from oracle import ref_leg
+
+            if args.cpu_kind == "reference" and ref_leg.numba_available():
+                cpu = cpu_block(ref_leg.numba_sample(w, cfg, args.cpu_seconds))
+                cpu["port"] = cpu_block(port)  # the C port, timed on the parity shard in the same run
+            else:
+                cpu = cpu_block(port)
         peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
-        hbm_peak, hbm_src = 6650.0, "fallback"
+        hbm_peak, hbm_src = 6650.0, "fallback (B200_PROFILING.md)"
         if os.path.exists(peaks_path):
-            hbm_peak, hbm_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured"
+            hbm_peak, hbm_src = float(json.load(open(peaks_path))["hbm_gbs"]), "MEASURED_PEAKS.json"
         cells = D * W
         # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` captures of this
         # workload (profiles/ncu_traffic.json, written by tools/ncu_summary.py runs); null for any other configuration
@@ -430,35 +477,140 @@ def run_b200_arm(args):
             t = json.load(open(tpath))
             if (t.get("N"), t.get("D"), t.get("L")) == (N, D, len(sel)):
                 traffic = t.get("bytes_per_launch", {})
+        # executed work of this rank's launches in the default (far-field) mode
+        flops_lines = float((ex["direct_region_evals"] * FLOPS_PER_EVAL).sum()) + FLOPS_HORNER * 3.0 * cells
+        flops_far = FLOPS_FAR_SETUP * ex["far_expansions"] + FLOPS_FAR_TERM * ex["far_terms"]
+        t_lines, t_far = kern.get("K2_lines", 0.0), kern.get("K2_far_coeffs", 0.0)
+        tf_lines = flops_lines / max(t_lines * 1e-3, 1e-12) / 1e12
+        tf_far = flops_far / max(t_far * 1e-3, 1e-12) / 1e12
+        t_hbm = kern.get("K3_continuum", 0.0) + kern.get("K4_raytrace", 0.0)
         out = {
-            "metric": "emergent-spectrum nu-points/sec (opacity+raytrace)", "value": value, "unit": "nu-points/s",
+            "metric": METRIC, "value": value, "unit": "nu-points/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": desc, "l2": "inputs larger than L2 (line records %.2f GB, outputs %.2f GB per array)"
-                       % (len(sel) * D * 64 / 1e9, cells * 8 / 1e9), "partition": f"{world} contiguous nu range(s), global windows, cut at equal (pixels + 10 x lines inside)",
-                       "ranges": [list(b) for b in bounds]},
-            "roofline": {"kernel": "k_lines, direct mode (K2: every (line, depth, pixel) Voigt evaluation done explicitly, "
-                                   "far-field expansion off)", "bound": "fp64", "achieved": achieved_tflops,
-                         "peak": dfma_peak, "unit": "TFLOP/s", "frac": achieved_tflops / dfma_peak, "traffic": traffic.get("k_lines_direct"),
+            "config": config_block(desc, len(sel), D, cells, world, bounds),
+            "roofline": {"kernel": "k_lines, default (far-field) mode: the dominant kernel of the timed step", "bound": "fp64",
+                         "achieved": tf_lines, "peak": dfma_peak, "unit": "TFLOP/s", "frac": tf_lines / dfma_peak,
+                         "traffic": traffic.get("k_lines"),
                          "peak_source": "measured in this run: dependent-free DFMA loop on all SMs (sd_bench_dfma)",
-                         "flops_per_eval": FLOPS_PER_EVAL.tolist(), "region_evals_all_ranks": region_evals.tolist(),
-                         "kernel_ms": k2_kernel_ms, "gevals_per_s": float(stats["evals"] / k2_kernel_ms / 1e6)},
-            "farfield": {"what": "default mode: distant region-I wings summed as Taylor coefficients (degree <= 20) per pixel "
-                                 "tile on a 3-level tile hierarchy (k_far_coeffs) instead of per pixel; same result within "
-                                 "max_rel_dev",
-                         "k2_ms": k2_far_ms, "k2_ms_direct": k2_kernel_ms, "k2_speedup": k2_kernel_ms / k2_far_ms,
-                         "max_rel_dev_vs_direct": far_dev, "ms_per_step_direct": ms_direct,
-                         "value_direct_mode": N / (ms_direct * 1e-3)},
+                         "work": "EXECUTED Voigt evaluations per Humlicek region x SURVEY 8d flops + Horner evaluation of "
+                                 "the three far-field polynomials per (pixel, depth)",
+                         "flops_per_eval": FLOPS_PER_EVAL.tolist(), "executed_region_evals": ex["direct_region_evals"].tolist(),
+                         "flops_horner_per_cell_level": FLOPS_HORNER, "kernel_ms": t_lines,
+                         "share_of_step": t_lines / ms_per_step},
+            "roofline_far": {"kernel": "k_far_coeffs (+ k_far_reduce), all three levels", "bound": "fp64", "achieved": tf_far,
+                             "peak": dfma_peak, "unit": "TFLOP/s", "frac": tf_far / dfma_peak, "traffic": traffic.get("k_far_coeffs"),
+                             "work": "EXECUTED (pair, tile) expansions x setup flops + Taylor terms x flops per term",
+                             "expansions": ex["far_expansions"], "terms": ex["far_terms"],
+                             "flops_setup": FLOPS_FAR_SETUP, "flops_per_term": FLOPS_FAR_TERM, "kernel_ms": t_far,
+                             "share_of_step": t_far / ms_per_step},
             "roofline_hbm": {"kernel": "k_continuum + k_raytrace (K3+K4)", "bound": "hbm",
-                             "achieved": BYTES_PER_CELL * cells / ((phase[2] + phase[3]) * 1e-3) / 1e9, "peak": hbm_peak,
-                             "unit": "GB/s", "frac": BYTES_PER_CELL * cells / ((phase[2] + phase[3]) * 1e-3) / 1e9 / hbm_peak,
-                             "peak_source": hbm_src, "traffic": traffic.get("k_continuum+k_raytrace")},
+                             "achieved": BYTES_PER_CELL * cells / max(t_hbm * 1e-3, 1e-12) / 1e9, "peak": hbm_peak,
+                             "unit": "GB/s", "frac": BYTES_PER_CELL * cells / max(t_hbm * 1e-3, 1e-12) / 1e9 / hbm_peak,
+                             "peak_source": hbm_src, "traffic": traffic.get("k_continuum+k_raytrace"), "kernel_ms": t_hbm},
+            "farfield": {"what": "default mode: distant region-I wings summed as Taylor coefficients (degree <= 20) per pixel "
+                                 "tile on a 3-level tile hierarchy (k_far_coeffs) instead of per pixel",
+                         "k2_ms": k2_far_ms, "reference_equivalent_region_evals_all_ranks": region_evals.tolist(),
+                         "far_replaced_evals": ex["far_replaced_evals"]},
             "phase_ms": {"K1_broadening": phase[0], "K2_prepare_and_lines": phase[1], "K3_continuum": phase[2],
                          "K4_raytrace": phase[3], "spectrum_gather": phase[4]},
+            "kernel_ms": kern,
+            "parity": parity,
             "cpu_baseline": cpu,
             "e2e": {"value": e2e_value, "unit": "nu-points/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": int(launches), "clocks": clocks,
         }
+        if direct is not None:
+            out["roofline_direct"] = {
+                "kernel": "k_lines, direct mode (every (line, depth, pixel) Voigt evaluation done explicitly, far field off)",
+                "bound": "fp64", "achieved": direct["tflops"], "peak": dfma_peak, "unit": "TFLOP/s",
+                "frac": direct["tflops"] / dfma_peak, "traffic": traffic.get("k_lines_direct"), "kernel_ms": direct["k2_ms"],
+                "gevals_per_s": float(stats["evals"] / direct["k2_ms"] / 1e6)}
+            out["farfield"].update(k2_ms_direct=direct["k2_ms"], k2_speedup=direct["k2_ms"] / k2_far_ms,
+                                   max_rel_dev_vs_direct=direct["far_dev"], ms_per_step_direct=direct["ms_per_step"],
+                                   value_direct_mode=N / (direct["ms_per_step"] * 1e-3))
+        print(json.dumps(out), flush=True)
+        if parity is not None and not parity["ok"]:
+            print(f"PARITY FAILURE on the benched workload: {parity}", file=sys.stderr, flush=True)
+            rc = 3
+    if world > 1:
+        dist.destroy_process_group()
+    if rc:
+        sys.exit(rc)
+
+
+# ----------------------------------------------------------------------------------------------- grid sweep (config #5)
+def run_grid_sweep(args, ctx, stream, rank, world, local_rank, barrier, max_over_ranks):
+    """BASELINE.json configs[4]: 64 stellar models (Teff / log g / [Fe/H] grid) scattered over the ranks as independent
+    replicas -- every model is one full hot-path pass over the flagship grid on one GPU; the only collective is the
+    gather of the emergent spectra.  Reports whole-box spectra/s (and nu-points/s = 64 N / time)."""
+    import torch
+    import torch.distributed as dist
+
+    from stardis_b200 import _lib as L
+    from stardis_b200.synthetic import sweep_models
+
+    n_models = 64
+    w, cfg, desc = build_workload(args, "solar_full")
+    models = sweep_models(w, n_models)                 # per model: atmosphere-dependent inputs (host, O(D) + (L, D))
+    mine = list(range(rank, n_models, world))
+    hp = HotPath(ctx, w, cfg, 0, 1, torch)             # every rank evaluates the WHOLE grid of its models
+    N, D = hp.N, hp.D
+    resident = []
+    for m in mine:                                      # inputs resident in HBM before the timed region
+        mm = models(m)
+        resident.append(dict(T=mm["T"], n_e=mm["n_e"], n_H=mm["n_H"], desc=mm["desc"],
+                             alpha=torch.from_numpy(mm["alpha_line"]).cuda(), cont=mm["continuum"]))
+    spectra = torch.empty((len(mine), N), dtype=torch.float64, device="cuda")
+    gathered = [torch.empty((len(range(r, n_models, world)), N), dtype=torch.float64, device="cuda") for r in range(world)]
+
+    def sweep():
+        for i, r in enumerate(resident):
+            ctx.set_atmosphere(r["T"], r["n_e"], r["n_H"], hp.model_vmic)
+            hp.d_lines["alpha_line"] = r["alpha"]
+            hp.bf_prefix, hp.ff_coef, hp.electron, hp.tables = r["cont"]
+            hp.d_spec = spectra[i]
+            hp.step(gather=False)
+        if world > 1:
+            if all(g.shape == gathered[0].shape for g in gathered):
+                dist.all_gather(gathered, spectra)
+            else:
+                for src in range(world):
+                    buf = spectra if src == rank else gathered[src]
+                    dist.broadcast(buf, src)
+
+    from stardis_b200 import units as u
+    hp.model_vmic = float(u.cgs_values_of(hp.model.microturbulence))
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    sweep()
+    barrier()
+    launches0 = ctx.launch_count()
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    t0.record(stream)
+    for _ in range(args.steps):
+        sweep()
+        ctx.synchronize()
+    t1.record(stream)
+    barrier()
+    clocks = sampler.stop()
+    ms = max_over_ranks(t0.elapsed_time(t1)) / args.steps
+    launches = ctx.launch_count() - launches0
+    if rank == 0:
+        spec = spectra.cpu().numpy()
+        out = {"metric": METRIC, "value": n_models * N / (ms * 1e-3), "unit": "nu-points/s", "n_gpus": world,
+               "steps": args.steps, "warmup": 1, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong",
+               "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+               "config": {"workload": f"grid_sweep64: {n_models} stellar models (Teff x log g x [Fe/H] variations of the solar "
+                                      f"MARCS structure) x [{desc}], scattered {len(mine)} per GPU as independent replicas; "
+                                      f"a step = all {n_models} models", "l2": "inputs larger than L2",
+                          "partition": f"replicas: models r, r + {world}, ... on rank r; spectra gathered with NCCL"},
+               "spectra_per_s": n_models / (ms * 1e-3), "ms_per_model": ms / len(mine),
+               "spectrum_checks": {"finite": bool(np.isfinite(spec).all()), "positive": bool((spec > 0).all()),
+                                   "distinct_models": int(len({float(s[N // 2]) for s in spec}))},
+               "gpu_launches": int(launches), "clocks": clocks, "cpu_baseline": None,
+               "e2e": None, "roofline": None}
         print(json.dumps(out), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -1,5 +1,7 @@
-"""Packaged numeric data: MARCS structure columns (atmospheres.npz) and the three continuum cross-section tables
-(cross_sections.npz) extracted from the files the reference ships (tools/make_atmospheres.py)."""
+"""Bench / test fixtures, NOT part of the product package: MARCS structure columns (atmospheres.npz) and the three
+continuum cross-section tables (cross_sections.npz), extracted as plain numbers from the model and table files the
+reference ships (tools/make_atmospheres.py; published physics tables / model data).  ``stardis_b200.synthetic`` builds the
+bench workloads from them; the product path itself reads whatever files its configuration names."""
 import os
 
 import numpy as np

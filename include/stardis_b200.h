@@ -129,6 +129,12 @@ int sd_set_farfield(sd_ctx *ctx, int32_t on);
  * raises ZeroDivisionError for those, voigt.py:148), out[7] reserved. */
 int sd_set_line_stats(sd_ctx *ctx, int32_t on);
 int sd_line_stats(sd_ctx *ctx, int64_t out[8]);
+/* EXECUTED work of the last counting pass (bench.py's roofline of the default, far-field mode), raw counters:
+ * out[0..3] = Voigt evaluations k_lines performed itself per Humlicek region I..IV (pixels of this context's range),
+ * out[4..6] as sd_line_stats, out[8] = region-I evaluations the far-field expansions stand for
+ * (sd_line_stats()[0] = out[0] + out[8]), out[9] = far-field expansions performed ((pair, tile) products),
+ * out[10] = Taylor terms summed over those expansions, out[7], out[11..15] reserved. */
+int sd_line_stats_ex(sd_ctx *ctx, int64_t out[16]);
 
 /* ---- K3: continuum terms fused in one depth x nu pass + total ---------------------------------------- */
 /* 1-D or 2-D cross-section table (sigma_file, opacities_solvers/util.py:14-108).
@@ -233,6 +239,12 @@ int sd_debug_rcp(sd_ctx *ctx, int64_t n, const double *x, double *seed, double *
 int64_t sd_launch_count(const sd_ctx *ctx);
 int sd_timer_start(sd_ctx *ctx);
 int sd_timer_stop(sd_ctx *ctx, float *ms);
+/* Device time [ms] of the most recent run of each kernel group, from CUDA events the library records on the context's
+ * stream around the launches (synchronises on them); -1 for a group that has not run.  out_ms[0] K1 k_broadening,
+ * [1] K2 preparation (records, windows, class lists), [2] K2 edge sorts, [3] K2 k_far_coeffs (+ reduce, all levels),
+ * [4] K2 k_lines, [5] K3 k_continuum, [6] K4 k_raytrace, [7] line-strength producer (sd_calc_alpha_line_*). */
+#define SD_N_PHASE_TIMES 8
+int sd_phase_times(sd_ctx *ctx, float out_ms[SD_N_PHASE_TIMES]);
 
 #ifdef __cplusplus
 }

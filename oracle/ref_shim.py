@@ -11,12 +11,13 @@ those in ``sys.modules`` and then executes the reference's own source files,
 from where they lie, under their real dotted names.
 
 It is used ONLY
-  * by ``oracle/make_golden.py`` to generate the fixtures in ``tests/golden/``
+  * by ``oracle/make_golden*.py`` to generate the fixtures in ``tests/golden/``
     (in the build container, where ``/root/reference`` exists), and
-  * by ``tests/test_oracle_vs_reference.py`` (skipped when the reference tree
-    is not present, e.g. on the GPU box).
+  * by ``oracle/ref_leg.py``, the CPU reference leg of ``bench.py`` (on the GPU
+    box the modules come from ``oracle/_ref``, staged verbatim and git-ignored
+    by ``oracle/stage_ref.py``).
 
-Nothing of the reference is copied into this repository.
+Nothing of the reference enters this repository's history.
 """
 from __future__ import annotations
 
@@ -27,7 +28,10 @@ import types
 
 import numpy as np
 
-REFERENCE_ROOT = os.environ.get("STARDIS_REFERENCE_ROOT", "/root/reference")
+_STAGED = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")  # oracle/stage_ref.py (travels to the GPU box)
+REFERENCE_ROOT = os.environ.get(
+    "STARDIS_REFERENCE_ROOT",
+    "/root/reference" if os.path.isdir("/root/reference/stardis/radiation_field") else _STAGED)
 
 
 def reference_available() -> bool:

@@ -65,6 +65,8 @@ SIGNATURES = {
     "sd_set_farfield": (C.c_int, [_V, C.c_int32]),
     "sd_set_line_stats": (C.c_int, [_V, C.c_int32]),
     "sd_line_stats": (C.c_int, [_V, _ip]),
+    "sd_line_stats_ex": (C.c_int, [_V, _ip]),
+    "sd_phase_times": (C.c_int, [_V, C.POINTER(C.c_float)]),
     "sd_calc_continuum": (C.c_int, [_V, C.POINTER(SdContinuum), C.c_uint32]),
     "sd_raytrace": (C.c_int, [_V, C.c_int32, _V, _V, C.c_int32, C.c_double, C.c_int32]),
     "sd_get": (C.c_int, [_V, C.c_int32, _V, C.c_int64]),

@@ -74,6 +74,10 @@ int sd_create(sd_ctx **out, int device) {
     c->stream = c->own_stream;
     cudaEventCreate(&c->ev0);
     cudaEventCreate(&c->ev1);
+    for (int k = 0; k < SD_N_PHASES; k++) {
+        cudaEventCreate(&c->ph_ev[k][0]);
+        cudaEventCreate(&c->ph_ev[k][1]);
+    }
     cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device);
     *out = c;
     return SD_OK;
@@ -98,6 +102,10 @@ void sd_destroy(sd_ctx *c) {
     free_buf(c->far_part);
     cudaEventDestroy(c->ev0);
     cudaEventDestroy(c->ev1);
+    for (int k = 0; k < SD_N_PHASES; k++) {
+        cudaEventDestroy(c->ph_ev[k][0]);
+        cudaEventDestroy(c->ph_ev[k][1]);
+    }
     cudaStreamDestroy(c->own_stream);
     delete c;
 }
@@ -238,12 +246,14 @@ int sd_calc_alpha_line_vald(sd_ctx *c, int64_t n_ions, const double *n_over_u, c
     SD_CUDA(c, cudaMemcpyAsync(base + b_tab + b8, gf, b8, cudaMemcpyDefault, c->stream));
     SD_CUDA(c, cudaMemcpyAsync(base + b_tab + 2 * b8, e_low_erg, b8, cudaMemcpyDefault, c->stream));
     if (g_lo) SD_CUDA(c, cudaMemcpyAsync(base + b_tab + 3 * b8, g_lo, b8, cudaMemcpyDefault, c->stream));
+    sd_phase_begin(c, SD_PH_STRENGTH);
     k_alpha_line_vald<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(
         L, c->D, c->T.as<double>(), c->l_nu.as<double>(), reinterpret_cast<const double *>(base),
         reinterpret_cast<const int64_t *>(base + b_tab), reinterpret_cast<const double *>(base + b_tab + b8),
         g_lo ? reinterpret_cast<const double *>(base + b_tab + 3 * b8) : nullptr,
         reinterpret_cast<const double *>(base + b_tab + 2 * b8), c->l_alpha.as<double>());
     SD_TRY(sd_launch_check(c, "k_alpha_line_vald"));
+    sd_phase_end(c, SD_PH_STRENGTH);
     c->have_alpha_line = true;
     c->records_ready = false;
     return SD_OK;
@@ -255,7 +265,9 @@ int sd_calc_broadening(sd_ctx *c, uint32_t flags) {
     SD_CHECK(c, c->has_atomic_cols, SD_ERR_STATE, "sd_calc_broadening: line table lacks the level/ion columns");
     SD_CHECK(c, !(flags & SD_VALD) || c->has_vald_cols, SD_ERR_STATE, "sd_calc_broadening: SD_VALD needs stark/waals");
     SD_CUDA(c, cudaSetDevice(c->device));
+    sd_phase_begin(c, SD_PH_K1);
     SD_TRY(sd_k1_broadening(c, flags));
+    sd_phase_end(c, SD_PH_K1);
     c->gamma_cols = c->D;
     c->have_broadening = true;
     c->records_ready = false;
@@ -301,13 +313,33 @@ int sd_set_line_stats(sd_ctx *c, int32_t on) {
     return SD_OK;
 }
 
-int sd_line_stats(sd_ctx *c, int64_t out[8]) {
+int sd_line_stats_ex(sd_ctx *c, int64_t out[16]) {
     if (!c || !out) return SD_ERR_ARG;
     SD_CHECK(c, c->stats.p, SD_ERR_STATE, "sd_line_stats: nothing computed yet");
-    unsigned long long h[8];
+    unsigned long long h[SD_N_STATS];
     SD_CUDA(c, cudaMemcpyAsync(h, c->stats.p, sizeof h, cudaMemcpyDeviceToHost, c->stream));
     SD_CUDA(c, cudaStreamSynchronize(c->stream));
-    for (int i = 0; i < 8; i++) out[i] = (int64_t)h[i];
+    for (int i = 0; i < SD_N_STATS; i++) out[i] = (int64_t)h[i];
+    return SD_OK;
+}
+
+int sd_line_stats(sd_ctx *c, int64_t out[8]) {
+    int64_t h[SD_N_STATS];
+    SD_TRY(sd_line_stats_ex(c, h));
+    for (int i = 0; i < 8; i++) out[i] = h[i];
+    out[0] += h[8];  // region-I evaluations the far-field expansion stands for: counted as the reference would
+    return SD_OK;
+}
+
+int sd_phase_times(sd_ctx *c, float out_ms[8]) {
+    if (!c || !out_ms) return SD_ERR_ARG;
+    SD_CUDA(c, cudaSetDevice(c->device));
+    for (int k = 0; k < SD_N_PHASES; k++) {
+        out_ms[k] = -1.0f;
+        if (!c->ph_rec[k]) continue;
+        SD_CUDA(c, cudaEventSynchronize(c->ph_ev[k][1]));
+        SD_CUDA(c, cudaEventElapsedTime(&out_ms[k], c->ph_ev[k][0], c->ph_ev[k][1]));
+    }
     return SD_OK;
 }
 
@@ -316,7 +348,9 @@ int sd_calc_continuum(sd_ctx *c, const sd_continuum *desc, uint32_t store_mask) 
     SD_CHECK(c, c->N > 0 && c->D > 0, SD_ERR_STATE, "sd_calc_continuum: grid/atmosphere not set");
     SD_CHECK(c, desc->n_tables >= 0 && desc->n_tables <= SD_MAX_TABLES, SD_ERR_ARG, "sd_calc_continuum: too many tables");
     SD_CUDA(c, cudaSetDevice(c->device));
+    sd_phase_begin(c, SD_PH_K3);
     SD_TRY(sd_k3_continuum(c, desc, store_mask));
+    sd_phase_end(c, SD_PH_K3);
     c->have_total = true;
     return SD_OK;
 }
@@ -328,6 +362,7 @@ int sd_raytrace(sd_ctx *c, int32_t n_theta, const double *ray_ds, const double *
     SD_CHECK(c, c->have_total, SD_ERR_STATE, "sd_raytrace: no total opacity (sd_calc_continuum / sd_set_total)");
     SD_CUDA(c, cudaSetDevice(c->device));
     SD_TRY(sd_k4_raytrace(c, n_theta, ray_ds, weights, inward, scale, track));
+    sd_phase_end(c, SD_PH_K4);
     c->have_F = true;
     c->n_theta_tracked = track ? n_theta : 0;
     return SD_OK;
@@ -692,7 +727,7 @@ extern "C" {
 int sd_bench_dfma(sd_ctx *c, int32_t iters, double *tflops) {
     if (!c || !tflops || iters <= 0) return SD_ERR_ARG;
     SD_CUDA(c, cudaSetDevice(c->device));
-    SD_TRY(sd_ensure(c, c->stats, 64));
+    SD_TRY(sd_ensure(c, c->stats, sizeof(unsigned long long) * SD_N_STATS));
     int blocks = c->sm_count * 8;
     k_dfma<<<blocks, 256, 0, c->stream>>>(iters / 8 + 1, 1.0, c->stats.as<double>() + 7);  // warm-up
     float best = 1e30f;
@@ -714,7 +749,7 @@ int sd_bench_dfma(sd_ctx *c, int32_t iters, double *tflops) {
 int sd_bench_fp64(sd_ctx *c, int32_t mode, int32_t iters, double *tflops) {
     if (!c || !tflops || iters <= 0 || mode < 0 || mode > 3) return SD_ERR_ARG;
     SD_CUDA(c, cudaSetDevice(c->device));
-    SD_TRY(sd_ensure(c, c->stats, 64));
+    SD_TRY(sd_ensure(c, c->stats, sizeof(unsigned long long) * SD_N_STATS));
     int blocks = c->sm_count * 8;
     double *sink = c->stats.as<double>() + 7;
     float best = 1e30f;
@@ -740,7 +775,7 @@ int sd_bench_fp64(sd_ctx *c, int32_t mode, int32_t iters, double *tflops) {
 int sd_bench_fareval(sd_ctx *c, int32_t variant, int32_t iters, double *gevals) {
     if (!c || !gevals || iters <= 0) return SD_ERR_ARG;
     SD_CUDA(c, cudaSetDevice(c->device));
-    SD_TRY(sd_ensure(c, c->stats, 64));
+    SD_TRY(sd_ensure(c, c->stats, sizeof(unsigned long long) * SD_N_STATS));
     int blocks = c->sm_count * 2;
     double *sink = c->stats.as<double>() + 7;
     float best = 1e30f;

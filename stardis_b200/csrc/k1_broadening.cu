@@ -317,8 +317,9 @@ int sd_k1_broadening(sd_ctx *c, uint32_t flags) {
 int sd_k2_prepare(sd_ctx *c) {
     int64_t L = c->L, n = c->L * c->D;
     int D = c->D;
-    SD_TRY(sd_ensure(c, c->stats, 64));
-    SD_CUDA(c, cudaMemsetAsync(c->stats.p, 0, 64, c->stream));
+    SD_TRY(sd_ensure(c, c->stats, sizeof(unsigned long long) * SD_N_STATS));
+    SD_CUDA(c, cudaMemsetAsync(c->stats.p, 0, sizeof(unsigned long long) * SD_N_STATS, c->stream));
+    sd_phase_begin(c, SD_PH_PREP);
     SD_TRY(sd_ensure(c, c->d_nu, sizeof(double)));
     SD_TRY(sd_ensure(c, c->cls_off, sizeof(int) * D * (SD_NCLS + 1)));
     k_dnu<<<1, 1024, 0, c->stream>>>(c->N, c->nus.as<double>(), c->d_nu.as<double>());
@@ -343,6 +344,7 @@ int sd_k2_prepare(sd_ctx *c) {
     fg.lo_l = fg.hi_l = nullptr;
     if (L == 0) {
         SD_CUDA(c, cudaMemsetAsync(c->cls_off.p, 0, sizeof(int) * D * (SD_NCLS + 1), c->stream));
+        sd_phase_end(c, SD_PH_PREP);
         c->records_ready = true;
         return SD_OK;
     }
@@ -391,7 +393,9 @@ int sd_k2_prepare(sd_ctx *c) {
     k_cls_scatter<<<dim3(nchunks, D), CHUNK, 0, c->stream>>>(L, c->win_cls.as<uint8_t>(), nchunks, c->chunk_cnt.as<int>(),
                                                            c->cls_list.as<int>());
     SD_TRY(sd_launch_check(c, "k_cls_scatter"));
+    sd_phase_end(c, SD_PH_PREP);
     if (c->farfield) {
+        sd_phase_begin(c, SD_PH_SORT);
         // window ends were staged in edge_keys[0]: sort them first (into edge_keys[1]/edge_l[1]), then the starts
         SD_TRY(sd_sort_edges(c, 1, n));
         SD_TRY(sd_sort_edges(c, 0, n));
@@ -399,6 +403,7 @@ int sd_k2_prepare(sd_ctx *c) {
         fg.lo_l = c->edge_l[0].as<int>();
         fg.hi_keys = c->edge_keys[1].as<unsigned>();
         fg.hi_l = c->edge_l[1].as<int>();
+        sd_phase_end(c, SD_PH_SORT);
     }
     c->records_ready = true;
     return SD_OK;

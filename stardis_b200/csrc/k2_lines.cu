@@ -274,7 +274,7 @@ __global__ void __launch_bounds__(THREADS) k_far_coeffs(LineArgs a, int lev, int
     double C[K1];
 #pragma unroll
     for (int k = 0; k < K1; k++) C[k] = 0.0;
-    unsigned long long n_far = 0;
+    unsigned long long n_far = 0, n_terms = 0;
     const double inv_h = 1.0 / h;
     const unsigned lt_mask = (1u << lane) - 1u;
 
@@ -300,6 +300,7 @@ __global__ void __launch_bounds__(THREADS) k_far_coeffs(LineArgs a, int lev, int
         }
         // queue neighbours are neighbours in frequency, at similar distances from the tile: warp-uniform series length
         const int nt = __reduce_max_sync(0xffffffffu, nterms);
+        if (have) n_terms += (unsigned long long)min(K1, 3 * ((nt + 2) / 3));  // terms the loop below executes
         // Im(w^(k+1)) by the real three-term recurrence of the powers of a complex number,
         //   s_(k+1) = 2 Re(w) s_k - |w|^2 s_(k-1),  s_0 = 0, s_1 = Im w,
         // two instructions per pole and term instead of the four of a complex product (the recurrence loses about one
@@ -403,9 +404,16 @@ __global__ void __launch_bounds__(THREADS) k_far_coeffs(LineArgs a, int lev, int
         else a.far_coef[lev][tl * K1 + lane] = mine;
     }
     if (count_stats) {  // every far pair stands for one region-I evaluation per tile pixel inside the shard
-        for (int o2 = 16; o2; o2 >>= 1) n_far += __shfl_xor_sync(0xffffffffu, n_far, o2);
+        for (int o2 = 16; o2; o2 >>= 1) {
+            n_far += __shfl_xor_sync(0xffffffffu, n_far, o2);
+            n_terms += __shfl_xor_sync(0xffffffffu, n_terms, o2);
+        }
         const int64_t e0 = t0 > a.p0 ? t0 : a.p0, e1 = t1 < a.p1 ? t1 : a.p1;
-        if (lane == 0 && n_far && e1 > e0) atomicAdd(&a.stats[0], n_far * (unsigned long long)(e1 - e0));
+        if (lane == 0 && n_far) {
+            if (e1 > e0) atomicAdd(&a.stats[8], n_far * (unsigned long long)(e1 - e0));  // evaluations these expansions replace
+            atomicAdd(&a.stats[9], n_far);     // executed expansions (pair, tile)
+            atomicAdd(&a.stats[10], n_terms);  // executed series terms (both poles count as one)
+        }
     }
 }
 
@@ -721,7 +729,10 @@ int sd_k2_lines(sd_ctx *c, int slot) {
         SD_CUDA(c, cudaMemsetAsync(c->alpha_line[slot].p, 0, sizeof(double) * c->D * W, c->stream));
         return SD_OK;
     }
-    if (c->line_stats) SD_CUDA(c, cudaMemsetAsync(c->stats.p, 0, 4 * sizeof(unsigned long long), c->stream));
+    if (c->line_stats) {
+        SD_CUDA(c, cudaMemsetAsync(c->stats.p, 0, 4 * sizeof(unsigned long long), c->stream));
+        SD_CUDA(c, cudaMemsetAsync(c->stats.as<unsigned long long>() + 8, 0, 8 * sizeof(unsigned long long), c->stream));
+    }
     static const int rcp = env_int("SD_K2_RCP", 2);
     const int P = c->k2_P, NW = c->k2_NW, tile = 32 * NW * P;
     LineArgs a{};
@@ -755,6 +766,7 @@ int sd_k2_lines(sd_ctx *c, int slot) {
             part_bytes = b > part_bytes ? b : part_bytes;
         }
         SD_TRY(sd_ensure(c, c->far_part, part_bytes));
+        sd_phase_begin(c, SD_PH_FAR);
         for (int k = SD_FAR_LEVELS - 1; k >= 0; k--) {
             const int nsplit = far_nsplit(k);
             // one CTA per group of eight sibling tiles that has a member in the launched range, times the slices
@@ -768,14 +780,19 @@ int sd_k2_lines(sd_ctx *c, int slot) {
                 SD_TRY(sd_launch_check(c, "k_far_reduce"));
             }
         }
+        sd_phase_end(c, SD_PH_FAR);
     }
     dim3 grid((unsigned)n_launch, (unsigned)c->D);
-    if (NW == 2) return launch<8, 2>(c, a, grid, c->line_stats, rcp);
-    if (NW == 1) return launch<8, 1>(c, a, grid, c->line_stats, rcp);
-    switch (P) {
-        case 8: return launch<8, 8>(c, a, grid, c->line_stats, rcp);
-        case 4: return launch<4, 8>(c, a, grid, c->line_stats, rcp);
-        case 2: return launch<2, 8>(c, a, grid, c->line_stats, rcp);
-        default: return launch<1, 8>(c, a, grid, c->line_stats, rcp);
+    sd_phase_begin(c, SD_PH_LINES);
+    int rc;
+    if (NW == 2) rc = launch<8, 2>(c, a, grid, c->line_stats, rcp);
+    else if (NW == 1) rc = launch<8, 1>(c, a, grid, c->line_stats, rcp);
+    else switch (P) {
+        case 8: rc = launch<8, 8>(c, a, grid, c->line_stats, rcp); break;
+        case 4: rc = launch<4, 8>(c, a, grid, c->line_stats, rcp); break;
+        case 2: rc = launch<2, 8>(c, a, grid, c->line_stats, rcp); break;
+        default: rc = launch<1, 8>(c, a, grid, c->line_stats, rcp); break;
     }
+    sd_phase_end(c, SD_PH_LINES);
+    return rc;
 }

@@ -211,6 +211,7 @@ int sd_k4_raytrace(sd_ctx *c, int n_theta, const double *ray_ds, const double *w
     SD_CUDA(c, cudaMemcpyAsync(d_w, weights, sizeof(double) * n_theta, cudaMemcpyDefault, c->stream));
     SD_TRY(sd_ensure(c, c->F, sizeof(double) * D * W));
     if (track) SD_TRY(sd_ensure(c, c->I_nus, sizeof(double) * D * W * n_theta));
+    sd_phase_begin(c, SD_PH_K4);  // after the small descriptor copies: the kernel launches only
     RayArgs a{};
     a.D = D; a.N = c->N; a.p0 = c->p0; a.p1 = c->p1;
     a.nus = c->nus.as<double>(); a.T = c->T.as<double>(); a.alpha = c->total.as<double>();

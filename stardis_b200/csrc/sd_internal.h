@@ -64,6 +64,12 @@ struct DevBuf {
     T *as() const { return reinterpret_cast<T *>(p); }
 };
 
+// device-side phase timers: CUDA events recorded on the context's stream around each group of kernels, read back by
+// sd_phase_times (bench.py's per-kernel roofline figures are measured live with these, not under a profiler)
+constexpr int SD_N_PHASES = 8;
+enum { SD_PH_K1 = 0, SD_PH_PREP = 1, SD_PH_SORT = 2, SD_PH_FAR = 3, SD_PH_LINES = 4, SD_PH_K3 = 5, SD_PH_K4 = 6, SD_PH_STRENGTH = 7 };
+constexpr int SD_N_STATS = 16;  // uint64 counters, see sd_line_stats_ex
+
 struct sd_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;      // stream in use
@@ -72,6 +78,8 @@ struct sd_ctx {
     std::string err;
     int sm_count = 148;
     int64_t launches = 0;  // kernels launched so far
+    cudaEvent_t ph_ev[SD_N_PHASES][2] = {};
+    bool ph_rec[SD_N_PHASES] = {};
 
     // atmosphere
     int D = 0;
@@ -132,6 +140,12 @@ struct sd_ctx {
 };
 
 int sd_fail(sd_ctx *c, int code, const char *fmt, ...);
+
+inline void sd_phase_begin(sd_ctx *c, int ph) { cudaEventRecord(c->ph_ev[ph][0], c->stream); }
+inline void sd_phase_end(sd_ctx *c, int ph) {
+    cudaEventRecord(c->ph_ev[ph][1], c->stream);
+    c->ph_rec[ph] = true;
+}
 
 #define SD_CUDA(c, call)                                                                              \
     do {                                                                                              \

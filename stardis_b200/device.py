@@ -155,6 +155,22 @@ class DeviceContext:
         return dict(region_evals=out[:4].copy(), evals=int(out[:4].sum()), pairs=int(out[4]), wide_pairs=int(out[5]),
                     zero_doppler_pairs=int(out[6]))
 
+    def line_stats_ex(self):
+        """Executed work of the last counting pass (see sd_line_stats_ex in include/stardis_b200.h)."""
+        out = np.zeros(16, dtype=np.int64)
+        self._ck(self.lib.sd_line_stats_ex(self.h, out.ctypes.data_as(C.POINTER(C.c_int64))))
+        return dict(direct_region_evals=out[:4].copy(), far_replaced_evals=int(out[8]), far_expansions=int(out[9]),
+                    far_terms=int(out[10]))
+
+    PHASES = ("K1_broadening", "K2_prepare", "K2_edge_sort", "K2_far_coeffs", "K2_lines", "K3_continuum", "K4_raytrace",
+              "line_strengths")
+
+    def phase_times(self):
+        """Device time [ms] of the most recent run of every kernel group (CUDA events inside the library)."""
+        out = (C.c_float * 8)()
+        self._ck(self.lib.sd_phase_times(self.h, out))
+        return {name: float(out[k]) for k, name in enumerate(self.PHASES)}
+
     def calc_continuum(self, bf_nu_cut=None, bf_prefix=None, ff_coef=None, rayleigh=None, electron=None, tables=(),
                        store_mask=0):
         """tables: sequence of dicts(kind, x, y, values, diag, depth_y, depth_scale)."""

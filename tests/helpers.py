@@ -9,14 +9,14 @@ GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 def write_table_files(dirpath):
     """Write the three cross-section tables in the text formats the reference ships (stardis/data/*.dat)."""
-    from stardis_b200.data import write_cross_section_files
+    from stardis_b200.synthetic import write_cross_section_files
 
     return write_cross_section_files(dirpath)
 
 
 def write_marcs_mod(path, name="sun"):
     """A plane-parallel MARCS .mod file with the structure columns of the fixture atmosphere."""
-    z = np.load(os.path.join(os.path.dirname(GOLDEN), "..", "stardis_b200", "data", "atmospheres.npz"))
+    z = np.load(os.path.join(os.path.dirname(GOLDEN), "..", "benchdata", "atmospheres.npz"))
     depth, T, pe, pg, rho = (z[f"{name}_{k}"][::-1] for k in ("depth", "t", "pe", "pg", "density"))  # surface first
     logA = z[f"{name}_logA"]
     n = len(T)

@@ -303,3 +303,39 @@ def test_molecular_lines_vs_oracle(table_paths, oracle):
     cfg.opacity.line.broadening.remove("radiation")  # the reference's latent AttributeError (broadening.py:802-806)
     with pytest.raises(AttributeError):
         calc_molecular_alpha_line_at_nu(plasma, model, q, cfg.opacity.line)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["solar_full", "solar_weak"])
+def test_benched_workload_vs_oracle_on_shards(name, oracle):
+    """The workload bench.py times, at its FULL size (N = 700 000, L = 300 000 lines, seed 1; 38 % of the (line, depth)
+    pairs have whole-grid windows, ~1e5 far-field terms per pixel) and its weak-line twin: GPU on the whole grid through
+    the same device step as the bench, CPU oracle on three 256-pixel shards with global windows (a few seconds each)."""
+    import argparse
+
+    import bench
+    from oracle import ref_leg
+    from stardis_b200 import _lib as L
+    from stardis_b200.device import default_context
+
+    import torch
+
+    args = argparse.Namespace(workload=name, lines=None)
+    w, cfg, _ = bench.build_workload(args)
+    ctx = default_context()
+    ctx.evict()
+    hp = bench.HotPath(ctx, w, cfg, 0, 1, torch)
+    hp.step()
+    ctx.synchronize()
+    total, F = ctx.get(L.BUF_TOTAL), ctx.get(L.BUF_F_NU)
+    N = hp.N
+    assert total.shape == (56, N) and np.isfinite(total).all() and np.isfinite(F).all() and (F[-1] > 0).all()
+    inp = ref_leg.workload_inputs(w, cfg)
+    gam, dws = oracle.calc_broadening(inp["lines"], inp["T"], inp["n_e"], inp["n_H"], inp["vmic"], 15)
+    th, wts = oracle.thetas_and_weights(inp["n_theta"])
+    for p0 in (1024, N // 3 + 11, N - 256):
+        a_line = oracle.calc_alan_entries(56, inp["nus"], inp["lines"]["nu"], dws, gam, inp["alpha_line"], p0=p0, p1=p0 + 256)
+        ref_total = ref_leg.continuum_total(oracle, inp, inp["nus"][p0:p0 + 256]) + a_line
+        ref_F, _ = oracle.raytrace(inp["T"], ref_total, inp["nus"][p0:p0 + 256], th, wts, dist=inp["dist"])
+        np.testing.assert_allclose(total[:, p0:p0 + 256], ref_total, rtol=RTOL_ALPHA)
+        np.testing.assert_allclose(F[:, p0:p0 + 256], ref_F, rtol=RTOL_F, atol=1e-300)

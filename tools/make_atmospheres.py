@@ -1,5 +1,5 @@
 """Extract the depth structure of the two MARCS models that ship with the reference into
-stardis_b200/data/atmospheres.npz (build container only; the GPU box has no /root/reference).
+benchdata/atmospheres.npz (build container only; the GPU box has no /root/reference).
 
 Only the numeric structure columns are stored (depth, T, Pe, Pg, density, microturbulence, Teff); they feed the
 synthetic workloads of bench.py and the tests.  Parsed with the product's own MARCS reader.
@@ -23,12 +23,12 @@ for name, rel in SRC.items():
     out[f"{name}_vmic_kms"] = float(m.metadata["microturbulence"].value)
     out[f"{name}_teff"] = float(m.metadata["teff"].value)
     out[f"{name}_logA"] = m.log_abundances
-dst = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "stardis_b200", "data", "atmospheres.npz")
+dst = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "benchdata", "atmospheres.npz")
 np.savez_compressed(dst, **out)
 print(dst, os.path.getsize(dst))
 
 # ---- numeric content of the three cross-section tables the reference ships in stardis/data/ (Wishart 1979 H- bf,
-# Bell & Berrington 1987 H- ff, Stancil 1994 H2+ bf) -> stardis_b200/data/cross_sections.npz
+# Bell & Berrington 1987 H- ff, Stancil 1994 H2+ bf) -> benchdata/cross_sections.npz
 from stardis_b200.radiation_field.opacities.opacities_solvers.util import read_table  # noqa: E402
 
 TABLES = {"Hminus_bf": "h_minus_bf_W1979.dat", "Hminus_ff": "h_minus_ff_B1987.dat", "H2plus_bf": "h2_plus_bf_S1994.dat"}
