@@ -83,7 +83,7 @@ def build_workload(args, name=None):
     from stardis_b200.synthetic import WORKLOADS, make_workload
 
     name = name or args.workload
-    w = make_workload(name, seed=1, n_lines=args.lines)
+    w = make_workload(name, seed=1, n_lines=args.lines, device_strengths=True)
     cfg = opacity_config(tempfile.mkdtemp(prefix="sdb200_tables_"), WORKLOADS[name][5])
     desc = (f"{name}: MARCS {WORKLOADS[name][0]} structure (T x {WORKLOADS[name][1]:.3f}) D={len(w['atmosphere']['T'])}, lambda "
             f"{w['lambdas'].value[0]:.0f}-{w['lambdas'].value[-1]:.0f} A step 0.01 (N={len(w['nus'])}), "
@@ -419,17 +419,25 @@ def run_b200_arm(args):
         pinned = torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
         setattr(lt, name, pinned.numpy())
         lt.__dict__.setdefault("_pins", []).append(pinned)
+    if lt.strength is not None:
+        for k, v in list(lt.strength.per_line.items()):
+            if v is not None:
+                pinned = torch.from_numpy(np.ascontiguousarray(v)).pin_memory()
+                lt.strength.per_line[k] = pinned.numpy()
+                lt.__dict__["_pins"].append(pinned)
     lt._no_autoion = None
     pinned_nus = torch.from_numpy(nus.copy()).pin_memory()
     nus_host = u.Quantity(pinned_nus.numpy(), u.Hz)
     h_spec = torch.empty(W, dtype=torch.float64).pin_memory()
     sel = ob.select_lines(plasma, model, nus_host, line_cfg)
-    # per rank: grid + per-line columns + this rank's row block of the (L, D) strengths (striped upload, the other blocks
-    # arrive over NVLink: distributed.upload_rows_striped) + atmosphere
+    # per rank: grid + per-line columns + atmosphere + the O(L) inputs of the device line-strength producer
+    # (sd_calc_alpha_line_vald fills the (L, D) table in HBM; without producer inputs the table itself travels, striped
+    # over the ranks and exchanged over NVLink: distributed.upload_rows_striped)
     r0, r1, _ = stripe_rows(len(sel), rank, world)
     h2d = int(pinned_nus.numel() * 8 + sum(np.asarray(getattr(sel, k)).nbytes for k in
               ("nu", "mass", "atomic_number", "ion_number", "ionization_energy", "level_energy_upper",
-               "level_energy_lower", "A_ul")) + (r1 - r0) * D * 8 + 3 * D * 8)
+               "level_energy_lower", "A_ul")) + 3 * D * 8 +
+              (sel.strength.nbytes() if sel.strength is not None else (r1 - r0) * D * 8))
     d2h = int(W * 8)
 
     def api_step():

@@ -99,9 +99,20 @@ int sd_set_lines(sd_ctx *ctx, const sd_lines *lines);
  * in the reference's order of operations.  Needs the atmosphere (T) and the line table (nu; alpha_line may be NULL).
  * n_over_u: (n_ions, D) ion number density / partition function; ion_row[l]: row of that table for line l;
  * gf[l]: f_lu = 10^log_gf / g_lo with g_lo[l] given (long lists) or 10^log_gf with g_lo == NULL (short lists);
- * e_low_erg[l]: lower level energy [erg].  Replaces the (L, D) host->device upload of alpha_line by O(L) inputs. */
+ * e_low_erg[l]: lower level energy [erg] (NULL = the line table's level_energy_lower column, which holds the same
+ * numbers in the reference's lines_from_linelist).  Replaces the (L, D) host->device upload of alpha_line by O(L)
+ * inputs.  Non-finite results are counted (sd_line_stats_ex out[11]); the reference raises ValueError for them. */
 int sd_calc_alpha_line_vald(sd_ctx *ctx, int64_t n_ions, const double *n_over_u, const int64_t *ion_row, const double *gf,
                             const double *g_lo, const double *e_low_erg);
+/* Line strengths of the tardis line list on the device: stardis/plasma/base.py:130-175 (AlphaLine),
+ *   alpha[l, d] = (pi e^2 / m_e c) * n_lower[l, d] * stimulated_emission_factor[l, d] * f_lu[l],
+ * n_lower / n_upper = rows lower_level_index[l] / upper_level_index[l] of level_number_density (n_levels, D), and the
+ * stimulated emission factor of tardis (release-2024.08.25, plasma/properties/radiative_properties.py):
+ * 1 - (g_lower n_upper) / (g_upper n_lower), set to 0 where n_lower == 0, where it is -inf, and where it is negative for
+ * a line whose upper level is metastable (metastable_upper[l] != 0; NULL = no metastable levels).  g: [n_levels]. */
+int sd_calc_alpha_line_levels(sd_ctx *ctx, int64_t n_levels, const double *level_number_density, const double *g,
+                              const int64_t *lower_level_index, const int64_t *upper_level_index,
+                              const int64_t *metastable_upper, const double *f_lu);
 
 /* ---- K1: broadening (calc_gamma broadening.py:550-656, calc_vald_gamma :1009-1085,
  *          calc_doppler_width :32-71) -> gammas (L,D), doppler_widths (L,D) on the device ------------- */
@@ -133,7 +144,8 @@ int sd_line_stats(sd_ctx *ctx, int64_t out[8]);
  * out[0..3] = Voigt evaluations k_lines performed itself per Humlicek region I..IV (pixels of this context's range),
  * out[4..6] as sd_line_stats, out[8] = region-I evaluations the far-field expansions stand for
  * (sd_line_stats()[0] = out[0] + out[8]), out[9] = far-field expansions performed ((pair, tile) products),
- * out[10] = Taylor terms summed over those expansions, out[7], out[11..15] reserved. */
+ * out[10] = Taylor terms summed over those expansions, out[11] = non-finite line strengths written by the last
+ * sd_calc_alpha_line_vald / sd_calc_alpha_line_levels call, out[7], out[12..15] reserved. */
 int sd_line_stats_ex(sd_ctx *ctx, int64_t out[16]);
 
 /* ---- K3: continuum terms fused in one depth x nu pass + total ---------------------------------------- */

@@ -62,6 +62,7 @@ SIGNATURES = {
     "sd_set_broadening": (C.c_int, [_V, _V, C.c_int32, _V]),
     "sd_calc_alpha_line": (C.c_int, [_V, C.c_int32]),
     "sd_calc_alpha_line_vald": (C.c_int, [_V, C.c_int64, _V, _V, _V, _V, _V]),
+    "sd_calc_alpha_line_levels": (C.c_int, [_V, C.c_int64, _V, _V, _V, _V, _V, _V]),
     "sd_set_farfield": (C.c_int, [_V, C.c_int32]),
     "sd_set_line_stats": (C.c_int, [_V, C.c_int32]),
     "sd_line_stats": (C.c_int, [_V, _ip]),

@@ -20,3 +20,4 @@ FF_CONSTANT = 4 / (3 * H_CGS * C_CGS) * E_ESU**6 * np.sqrt(2 * np.pi / (3 * ME_C
 RYDBERG_FREQUENCY = C_CGS * RYD_CGS
 # broadening.py:20
 RYDBERG_ENERGY = H_CGS * C_CGS * RYD_CGS
+ALPHA_COEFFICIENT = (np.pi * E_ESU**2) / (ME_CGS * C_CGS)  # stardis/plasma/base.py:35

@@ -79,6 +79,11 @@ int sd_create(sd_ctx **out, int device) {
         cudaEventCreate(&c->ph_ev[k][1]);
     }
     cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device);
+    if (sd_ensure(c, c->stats, sizeof(unsigned long long) * SD_N_STATS) != SD_OK ||
+        cudaMemset(c->stats.p, 0, sizeof(unsigned long long) * SD_N_STATS) != cudaSuccess) {
+        sd_destroy(c);
+        return SD_ERR_NOMEM;
+    }
     *out = c;
     return SD_OK;
 }
@@ -207,12 +212,20 @@ int sd_set_lines(sd_ctx *c, const sd_lines *ln) {
 }
 
 namespace {
+constexpr double ALPHA_COEFFICIENT = (sdm::PI * sdm::E_ESU * sdm::E_ESU) / (9.1093837015e-28 * sdm::C_CGS);  // plasma/base.py:35
+
+// count of non-finite line strengths (the reference raises ValueError for them, plasma/base.py:161-164, 293-296)
+__device__ __forceinline__ void flag_nonfinite(double a, unsigned long long *__restrict__ stats) {
+    const unsigned m = __ballot_sync(__activemask(), !(fabs(a) < INFINITY));
+    if (m && (threadIdx.x & 31) == (__ffs(m) - 1)) atomicAdd(&stats[11], (unsigned long long)__popc(m));
+}
+
 // one thread per (line, depth), depth fastest: coalesced (L, D) store, broadcast-friendly per-line loads
 __global__ void __launch_bounds__(256) k_alpha_line_vald(int64_t L, int D, const double *__restrict__ T,
                                                          const double *__restrict__ line_nu, const double *__restrict__ n_over_u,
                                                          const int64_t *__restrict__ ion_row, const double *__restrict__ gf,
                                                          const double *__restrict__ g_lo, const double *__restrict__ e_low,
-                                                         double *__restrict__ alpha) {
+                                                         double *__restrict__ alpha, unsigned long long *__restrict__ stats) {
     const int64_t g = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (g >= L * D) return;
     const int64_t l = g / D;
@@ -224,17 +237,53 @@ __global__ void __launch_bounds__(256) k_alpha_line_vald(int64_t L, int D, const
     if (g_lo) n_lower *= g_lo[l];
     // :272-281: 1 - exp((-h / k_B) * outer(nu, 1 / T))
     const double emis = 1.0 - exp((-sdm::H_CGS / sdm::KB_CGS) * (line_nu[l] * (1.0 / Td)));
-    constexpr double ALPHA_COEFFICIENT = (sdm::PI * sdm::E_ESU * sdm::E_ESU) / (9.1093837015e-28 * sdm::C_CGS);  // :35
-    alpha[g] = ALPHA_COEFFICIENT * n_lower * gf[l] * emis;  // :283-291, left to right
+    const double a = ALPHA_COEFFICIENT * n_lower * gf[l] * emis;  // :283-291, left to right
+    alpha[g] = a;
+    flag_nonfinite(a, stats);
+}
+
+// AlphaLine (plasma/base.py:130-175): alpha = ALPHA_COEFFICIENT * n_lower * stimulated_emission_factor * f_lu with
+// tardis' StimulatedEmissionFactor (third-party tardis release-2024.08.25, plasma/properties/radiative_properties.py;
+// source absent offline, restated from its published algorithm):
+//   sef = 1 - (g_lower n_upper) / (g_upper n_lower);  0 where n_lower == 0, where it is -inf, and where it is negative
+//   for a line whose upper level is metastable.
+__global__ void __launch_bounds__(256) k_alpha_line_levels(int64_t L, int D, const double *__restrict__ n_level,
+                                                           const double *__restrict__ g_level, const int64_t *__restrict__ lower,
+                                                           const int64_t *__restrict__ upper,
+                                                           const int64_t *__restrict__ metastable_upper,
+                                                           const double *__restrict__ f_lu, double *__restrict__ alpha,
+                                                           unsigned long long *__restrict__ stats) {
+    const int64_t g = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (g >= L * D) return;
+    const int64_t l = g / D;
+    const int d = (int)(g - l * D);
+    const int64_t lo = lower[l], up = upper[l];
+    const double n_lower = n_level[lo * D + d], n_upper = n_level[up * D + d];
+    double sef = 1.0 - ((g_level[lo] * n_upper) / (g_level[up] * n_lower));
+    if (n_lower == 0.0) sef = 0.0;
+    if (sef == -INFINITY) sef = 0.0;
+    if (metastable_upper && metastable_upper[l] != 0 && sef < 0.0) sef = 0.0;
+    const double a = ALPHA_COEFFICIENT * n_lower * sef * f_lu[l];
+    alpha[g] = a;
+    flag_nonfinite(a, stats);
+}
+
+int strength_prologue(sd_ctx *c, const char *who) {
+    SD_CHECK(c, c->D > 0, SD_ERR_STATE, "%s: no atmosphere", who);
+    SD_CUDA(c, cudaSetDevice(c->device));
+    SD_TRY(sd_ensure(c, c->stats, sizeof(unsigned long long) * SD_N_STATS));
+    SD_CUDA(c, cudaMemsetAsync(c->stats.as<unsigned long long>() + 11, 0, sizeof(unsigned long long), c->stream));
+    return SD_OK;
 }
 }  // namespace
 
 int sd_calc_alpha_line_vald(sd_ctx *c, int64_t n_ions, const double *n_over_u, const int64_t *ion_row, const double *gf,
                             const double *g_lo, const double *e_low_erg) {
     if (!c) return SD_ERR_ARG;
-    SD_CHECK(c, c->D > 0, SD_ERR_STATE, "sd_calc_alpha_line_vald: no atmosphere");
-    SD_CHECK(c, n_ions > 0 && n_over_u && ion_row && gf && e_low_erg, SD_ERR_ARG, "sd_calc_alpha_line_vald: missing input");
-    SD_CUDA(c, cudaSetDevice(c->device));
+    SD_CHECK(c, n_ions > 0 && n_over_u && ion_row && gf, SD_ERR_ARG, "sd_calc_alpha_line_vald: missing input");
+    SD_CHECK(c, e_low_erg || c->has_atomic_cols, SD_ERR_ARG,
+             "sd_calc_alpha_line_vald: e_low_erg == NULL needs the line table's level_energy_lower column");
+    SD_TRY(strength_prologue(c, "sd_calc_alpha_line_vald"));
     const int64_t L = c->L, n = L * c->D;
     if (n == 0) return SD_OK;
     // staged inputs: [n_over_u | ion_row | gf | e_low | g_lo]
@@ -244,15 +293,49 @@ int sd_calc_alpha_line_vald(sd_ctx *c, int64_t n_ions, const double *n_over_u, c
     SD_CUDA(c, cudaMemcpyAsync(base, n_over_u, b_tab, cudaMemcpyDefault, c->stream));
     SD_CUDA(c, cudaMemcpyAsync(base + b_tab, ion_row, b8, cudaMemcpyDefault, c->stream));
     SD_CUDA(c, cudaMemcpyAsync(base + b_tab + b8, gf, b8, cudaMemcpyDefault, c->stream));
-    SD_CUDA(c, cudaMemcpyAsync(base + b_tab + 2 * b8, e_low_erg, b8, cudaMemcpyDefault, c->stream));
+    if (e_low_erg) SD_CUDA(c, cudaMemcpyAsync(base + b_tab + 2 * b8, e_low_erg, b8, cudaMemcpyDefault, c->stream));
     if (g_lo) SD_CUDA(c, cudaMemcpyAsync(base + b_tab + 3 * b8, g_lo, b8, cudaMemcpyDefault, c->stream));
     sd_phase_begin(c, SD_PH_STRENGTH);
     k_alpha_line_vald<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(
         L, c->D, c->T.as<double>(), c->l_nu.as<double>(), reinterpret_cast<const double *>(base),
         reinterpret_cast<const int64_t *>(base + b_tab), reinterpret_cast<const double *>(base + b_tab + b8),
         g_lo ? reinterpret_cast<const double *>(base + b_tab + 3 * b8) : nullptr,
-        reinterpret_cast<const double *>(base + b_tab + 2 * b8), c->l_alpha.as<double>());
+        e_low_erg ? reinterpret_cast<const double *>(base + b_tab + 2 * b8) : c->l_elo.as<double>(), c->l_alpha.as<double>(),
+        c->stats.as<unsigned long long>());
     SD_TRY(sd_launch_check(c, "k_alpha_line_vald"));
+    sd_phase_end(c, SD_PH_STRENGTH);
+    c->have_alpha_line = true;
+    c->records_ready = false;
+    return SD_OK;
+}
+
+int sd_calc_alpha_line_levels(sd_ctx *c, int64_t n_levels, const double *level_number_density, const double *g,
+                              const int64_t *lower_level_index, const int64_t *upper_level_index,
+                              const int64_t *metastable_upper, const double *f_lu) {
+    if (!c) return SD_ERR_ARG;
+    SD_CHECK(c, n_levels > 0 && level_number_density && g && lower_level_index && upper_level_index && f_lu, SD_ERR_ARG,
+             "sd_calc_alpha_line_levels: missing input");
+    SD_TRY(strength_prologue(c, "sd_calc_alpha_line_levels"));
+    const int64_t L = c->L, n = L * c->D;
+    if (n == 0) return SD_OK;
+    // staged inputs: [level densities | g | lower | upper | f_lu | metastable]
+    const size_t b_tab = sizeof(double) * n_levels * c->D, b_g = sizeof(double) * n_levels, b8 = sizeof(double) * L;
+    SD_TRY(sd_ensure(c, c->vald_stage, b_tab + b_g + 4 * b8));
+    char *base = c->vald_stage.as<char>();
+    SD_CUDA(c, cudaMemcpyAsync(base, level_number_density, b_tab, cudaMemcpyDefault, c->stream));
+    SD_CUDA(c, cudaMemcpyAsync(base + b_tab, g, b_g, cudaMemcpyDefault, c->stream));
+    char *per_line = base + b_tab + b_g;
+    SD_CUDA(c, cudaMemcpyAsync(per_line, lower_level_index, b8, cudaMemcpyDefault, c->stream));
+    SD_CUDA(c, cudaMemcpyAsync(per_line + b8, upper_level_index, b8, cudaMemcpyDefault, c->stream));
+    SD_CUDA(c, cudaMemcpyAsync(per_line + 2 * b8, f_lu, b8, cudaMemcpyDefault, c->stream));
+    if (metastable_upper) SD_CUDA(c, cudaMemcpyAsync(per_line + 3 * b8, metastable_upper, b8, cudaMemcpyDefault, c->stream));
+    sd_phase_begin(c, SD_PH_STRENGTH);
+    k_alpha_line_levels<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(
+        L, c->D, reinterpret_cast<const double *>(base), reinterpret_cast<const double *>(base + b_tab),
+        reinterpret_cast<const int64_t *>(per_line), reinterpret_cast<const int64_t *>(per_line + b8),
+        metastable_upper ? reinterpret_cast<const int64_t *>(per_line + 3 * b8) : nullptr,
+        reinterpret_cast<const double *>(per_line + 2 * b8), c->l_alpha.as<double>(), c->stats.as<unsigned long long>());
+    SD_TRY(sd_launch_check(c, "k_alpha_line_levels"));
     sd_phase_end(c, SD_PH_STRENGTH);
     c->have_alpha_line = true;
     c->records_ready = false;

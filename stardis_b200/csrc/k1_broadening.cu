@@ -318,7 +318,7 @@ int sd_k2_prepare(sd_ctx *c) {
     int64_t L = c->L, n = c->L * c->D;
     int D = c->D;
     SD_TRY(sd_ensure(c, c->stats, sizeof(unsigned long long) * SD_N_STATS));
-    SD_CUDA(c, cudaMemsetAsync(c->stats.p, 0, sizeof(unsigned long long) * SD_N_STATS, c->stream));
+    SD_CUDA(c, cudaMemsetAsync(c->stats.p, 0, sizeof(unsigned long long) * 11, c->stream));  // [11] belongs to the strength producers
     sd_phase_begin(c, SD_PH_PREP);
     SD_TRY(sd_ensure(c, c->d_nu, sizeof(double)));
     SD_TRY(sd_ensure(c, c->cls_off, sizeof(int) * D * (SD_NCLS + 1)));

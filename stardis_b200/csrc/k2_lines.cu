@@ -731,7 +731,7 @@ int sd_k2_lines(sd_ctx *c, int slot) {
     }
     if (c->line_stats) {
         SD_CUDA(c, cudaMemsetAsync(c->stats.p, 0, 4 * sizeof(unsigned long long), c->stream));
-        SD_CUDA(c, cudaMemsetAsync(c->stats.as<unsigned long long>() + 8, 0, 8 * sizeof(unsigned long long), c->stream));
+        SD_CUDA(c, cudaMemsetAsync(c->stats.as<unsigned long long>() + 8, 0, 3 * sizeof(unsigned long long), c->stream));
     }
     static const int rcp = env_int("SD_K2_RCP", 2);
     const int P = c->k2_P, NW = c->k2_NW, tile = 32 * NW * P;

@@ -140,7 +140,29 @@ class DeviceContext:
         if rows.shape[0] != self.L or (rows.size and (rows.min() < 0 or rows.max() >= t.shape[0])):
             raise ValueError("ion_row must hold one valid row of n_over_u per line")
         self._ck(self.lib.sd_calc_alpha_line_vald(self.h, int(t.shape[0]), self._in(t), self._in(rows, integer=True),
-                                                  self._in(gf), self._in(g_lo), self._in(e_low_erg)))
+                                                  self._in(gf), self._in(g_lo), self._in(e_low_erg)))  # e_low None: E_lower column
+
+    def calc_alpha_line_levels(self, level_number_density, g, lower_level_index, upper_level_index, f_lu,
+                               metastable_upper=None):
+        """Line strengths (L, D) of the tardis line list on the device (AlphaLine, plasma/base.py:130-175, with tardis'
+        stimulated emission factor); see include/stardis_b200.h.  Needs ``set_atmosphere`` and ``set_lines(nu, None, ...)``."""
+        t = L.f64(level_number_density)
+        if t.ndim != 2 or t.shape[1] != self.D:
+            raise ValueError("level_number_density must have shape (n_levels, D)")
+        lo = np.ascontiguousarray(lower_level_index, dtype=np.int64)
+        up = np.ascontiguousarray(upper_level_index, dtype=np.int64)
+        for idx in (lo, up):
+            if idx.shape[0] != self.L or (idx.size and (idx.min() < 0 or idx.max() >= t.shape[0])):
+                raise ValueError("level indices must hold one valid row of level_number_density per line")
+        meta = None if metastable_upper is None else np.ascontiguousarray(metastable_upper, dtype=np.int64)
+        self._ck(self.lib.sd_calc_alpha_line_levels(self.h, int(t.shape[0]), self._in(t), self._in(g), self._in(lo, integer=True),
+                                                    self._in(up, integer=True), self._in(meta, integer=True), self._in(f_lu)))
+
+    def nonfinite_line_strengths(self):
+        """Number of NaN/inf values the last device line-strength producer wrote (synchronises)."""
+        out = np.zeros(16, dtype=np.int64)
+        self._ck(self.lib.sd_line_stats_ex(self.h, out.ctypes.data_as(C.POINTER(C.c_int64))))
+        return int(out[11])
 
     def set_farfield(self, on=True):
         """Far-field (Taylor) expansion of distant region-I wings per pixel tile; off = evaluate every pixel directly."""

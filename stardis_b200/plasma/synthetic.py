@@ -19,8 +19,8 @@ import types
 import numpy as np
 import pandas as pd
 
-from ..constants import AMU_CGS, EV_ERG, H_CGS, KB_CGS, ME_CGS
-from .columnar import ColumnarLines
+from ..constants import ALPHA_COEFFICIENT, AMU_CGS, EV_ERG, H_CGS, KB_CGS, ME_CGS
+from .columnar import ColumnarLines, LineStrength
 
 
 class SyntheticPlasma:
@@ -131,7 +131,7 @@ def saha_hydrogen(T, n_e):
 
 
 def synthetic_line_table(rng, n_lines, nu_min, nu_max, T, strong_fraction=0.005, vald=False, log_alpha=(-2.0, 8.0),
-                         log_alpha_strong=(9.0, 11.0)):
+                         log_alpha_strong=(9.0, 11.0), device_strengths=False):
     """Seeded synthetic line list following SURVEY.md 8(d): uniform in nu, iron-group-heavy Z distribution,
     E_lower ~ U[0, 0.8 E_ion], E_upper = E_lower + h nu (< E_ion enforced), A_ul = 10^U[6,9], alpha_line
     log-uniform with a Boltzmann depth trend exp(-E_lower / k T_d) normalised at the hottest depth, plus a strong
@@ -159,8 +159,22 @@ def synthetic_line_table(rng, n_lines, nu_min, nu_max, T, strong_fraction=0.005,
     a0 = 10.0 ** rng.uniform(log_alpha[0], log_alpha[1], L)
     strong = rng.random(L) < strong_fraction
     a0[strong] = 10.0 ** rng.uniform(log_alpha_strong[0], log_alpha_strong[1], int(strong.sum()))
-    boltz = np.exp(-e_lo[:, None] / KB_CGS * (1.0 / T[None, :] - 1.0 / T.max()))
-    alpha = np.ascontiguousarray(a0[:, None] * boltz)
+    strength = None
+    if device_strengths:
+        # the same recipe expressed through the O(L) inputs of the reference's VALD short-list producer
+        # (plasma/base.py:324-455): alpha = C (N/U)[ion, d] exp(-E_lo / k T_d) gf (1 - exp(-h nu / k T_d)) with a
+        # depth-independent N/U = 1 per ion and gf chosen so that alpha = a0 at the hottest depth -- the device fills the
+        # (L, D) array itself; the host copy below serves the CPU legs and the oracle only
+        ions = sorted({(int(z), int(i)) for z, i in zip(Z, ion)})
+        row_of = {zi: k for k, zi in enumerate(ions)}
+        ion_row = np.array([row_of[(int(z), int(i))] for z, i in zip(Z, ion)], dtype=np.int64)
+        t_hot = T.max()
+        gf = a0 / (ALPHA_COEFFICIENT * np.exp(-e_lo * (1.0 / (t_hot * KB_CGS))) * (1.0 - np.exp((-H_CGS / KB_CGS) * (nu * (1.0 / t_hot)))))
+        strength = LineStrength("vald", dict(ion_row=ion_row, gf=gf, g_lo=None), dict(n_over_u=np.ones((len(ions), D))))
+        alpha = strength.host_alpha(T, nu, e_lo)
+    else:
+        boltz = np.exp(-e_lo[:, None] / KB_CGS * (1.0 / T[None, :] - 1.0 / T.max()))
+        alpha = np.ascontiguousarray(a0[:, None] * boltz)
     stark = waals = None
     if vald:
         stark = np.where(rng.random(L) < 0.15, 0.0, -rng.uniform(4.5, 6.5, L))
@@ -168,7 +182,7 @@ def synthetic_line_table(rng, n_lines, nu_min, nu_max, T, strong_fraction=0.005,
         waals = np.where(kind == 0, -rng.uniform(7.0, 8.0, L), np.where(kind == 1, 0.0, np.where(
             kind == 2, rng.uniform(0.5, 3.0, L), rng.integers(150, 1500, L) + rng.uniform(0.15, 0.35, L))))
     return ColumnarLines(nu=nu, atomic_number=Z, ion_number=ion, ionization_energy=e_ion, level_energy_lower=e_lo,
-                         level_energy_upper=e_up, A_ul=A_ul, alpha_line=alpha, stark=stark, waals=waals)
+                         level_energy_upper=e_up, A_ul=A_ul, alpha_line=alpha, stark=stark, waals=waals, strength=strength)
 
 
 def attach_synthetic_molecules(plasma, T, n_lines, nu_min, nu_max, seed=0):
@@ -192,7 +206,7 @@ def attach_synthetic_molecules(plasma, T, n_lines, nu_min, nu_max, seed=0):
 
 
 def create_synthetic_plasma(atmosphere, n_lines, nu_min, nu_max, seed=0, strong_fraction=0.005, vald=False,
-                            n_h_levels=12, log_alpha=(-2.0, 8.0), log_alpha_strong=(9.0, 11.0)):
+                            n_h_levels=12, log_alpha=(-2.0, 8.0), log_alpha_strong=(9.0, 11.0), device_strengths=False):
     """atmosphere: dict with T, pe, pg (deepest -> surface, cgs)."""
     rng = np.random.default_rng(seed)
     T = np.asarray(atmosphere["T"], dtype=np.float64)
@@ -215,5 +229,6 @@ def create_synthetic_plasma(atmosphere, n_lines, nu_min, nu_max, seed=0, strong_
     g = 2.0 * n**2
     bz = g[:, None] * np.exp(-e_exc[:, None] / (KB_CGS * T[None, :]))
     n_lev = n_HI[None, :] * bz / bz.sum(0, keepdims=True)
-    lt = synthetic_line_table(rng, n_lines, nu_min, nu_max, T, strong_fraction, vald, log_alpha, log_alpha_strong)
+    lt = synthetic_line_table(rng, n_lines, nu_min, nu_max, T, strong_fraction, vald, log_alpha, log_alpha_strong,
+                              device_strengths=device_strengths)
     return SyntheticPlasma(T, n_e, n_HI, n_HII, n_HeI, h_minus, h2, h2_plus, lt, h_levels=(e_exc, n_lev))

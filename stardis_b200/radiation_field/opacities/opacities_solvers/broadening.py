@@ -90,6 +90,9 @@ def upload_lines_and_broaden(ctx, lines, alphas_array, masses, stellar_model, st
     then travel over PCIe once in total and reach the other ranks over NVLink (``distributed.upload_rows_striped``)."""
     get, has = _line_columns(lines)
     vald = bool(flags & L.VALD)
+    strength = getattr(lines, "strength", None)
+    if strength is not None:
+        alphas_array = None  # O(L) producer inputs travel instead of the (L, D) table; the device fills it (8f rank 1)
     if collective and alphas_array is not None:
         import torch
 
@@ -103,6 +106,8 @@ def upload_lines_and_broaden(ctx, lines, alphas_array, masses, stellar_model, st
                   level_energy_lower=get("level_energy_lower"), A_ul=get("A_ul"),
                   stark=get("stark") if vald and has("stark") else None,
                   waals=get("waals") if vald and has("waals") else None)
+    if strength is not None:
+        strength.run(ctx)
     ctx.calc_broadening(flags)
 
 

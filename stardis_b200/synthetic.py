@@ -68,7 +68,7 @@ WORKLOADS = {
 
 
 def make_workload(name="solar_full", seed=0, n_lines=None, strong_fraction=0.005, vald=False, lambda_range=None,
-                  step=None, log_alpha=(-2.0, 8.0)):
+                  step=None, log_alpha=(-2.0, 8.0), device_strengths=False):
     atm_name, t_scale, lam_rng, dstep, L, n_theta = WORKLOADS[name][:6]
     if len(WORKLOADS[name]) > 6:
         ov = WORKLOADS[name][6]
@@ -81,7 +81,7 @@ def make_workload(name="solar_full", seed=0, n_lines=None, strong_fraction=0.005
     model = stellar_model_from_atmosphere(atm)
     lam_q, nus = wavelength_grid(lam_rng[0], lam_rng[1], step)
     plasma = create_synthetic_plasma(atm, L, nus.min(), nus.max(), seed=seed, strong_fraction=strong_fraction, vald=vald,
-                                     log_alpha=log_alpha)
+                                     log_alpha=log_alpha, device_strengths=device_strengths)
     return dict(name=name, atmosphere=atm, model=model, plasma=plasma, lambdas=lam_q, nus=nus, no_of_thetas=n_theta)
 
 
