@@ -5,47 +5,134 @@
 // :659-732 (calculate_broadening: z_eff = ion_number + 1, linear Stark for hydrogen only), :1009-1085
 // (calc_vald_gamma), :32-71 (calc_doppler_width); opacities_solvers/base.py:522-575 (window rule).
 //
-// Roofline: HBM.  Per (line, depth): reads alpha_line 8 B (+ O(L) per-line columns), writes gamma 8 B,
-// doppler width 8 B, record 64 B, window 9 B.
+// K1 layout: every pow() of the formulae depends either on the line only (effective quantum numbers, C4^(2/3), C6^0.4,
+// 10^stark ...) or on the depth only (n_e^(2/3), T^(1/6), (8kT/pi m_p)^0.3 ...), never on both (the ABO van der Waals
+// code of VALD lists excepted).  k_line_pre / k_depth_pre evaluate them once per line / per depth; k_broadening then
+// multiplies the factors in the reference's order of association per (line, depth) pair -- the same numbers as the
+// unhoisted formula, bit for bit -- and is bound by its two (L, D) stores instead of by ~6 FP64 pow() per pair.
+//
+// Roofline: HBM.  Per (line, depth): K1 writes gamma 8 B + doppler width 8 B; the preparation pass reads those and
+// alpha_line (24 B) and writes window 32 B + class 1 B, and -- only for pairs whose window meets this context's extended
+// pixel range -- the 64-byte record and up to two 8-byte window-edge keys.
 #include "sd_internal.h"
 #include "sd_math.cuh"
 
 namespace {
 
-__global__ void __launch_bounds__(256) k_broadening(int64_t L, int D, const double *__restrict__ nu,
-                                                    const int64_t *__restrict__ Z, const int64_t *__restrict__ ion,
-                                                    const double *__restrict__ e_ion, const double *__restrict__ e_up,
-                                                    const double *__restrict__ e_lo, const double *__restrict__ A_ul,
-                                                    const double *__restrict__ mass, const double *__restrict__ stark,
-                                                    const double *__restrict__ waals, const double *__restrict__ T,
-                                                    const double *__restrict__ ne, const double *__restrict__ nH, double vmic,
-                                                    uint32_t flags, double *__restrict__ gammas, double *__restrict__ dws) {
-    int64_t g = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;  // (l, d), d fastest
+constexpr int LP_N = 8;    // doubles per line in line_pre
+constexpr int DP_N = 10;   // doubles per depth in depth_pre
+enum { LP_LS = 0, LP_QS = 1, LP_VDW = 2, LP_RAD = 3, LP_NUC = 4, LP_MASS = 5, LP_WAALS = 6, LP_STARK = 7 };
+enum { DP_NE23 = 0, DP_AQS = 1, DP_T16 = 2, DP_P17 = 3, DP_NH = 4, DP_2KT = 5, DP_NE = 6, DP_T16V = 7, DP_T038 = 8, DP_T = 9 };
+
+// per-line factors.  non-VALD (broadening.py:611-654): LS = 0.60 a1 (n_u^2 - n_l^2) [hydrogen only], QS = C4^(2/3),
+// VDW = C6^0.4.  VALD (:1039-1085): LS as above, QS = 10^stark, VDW = 10^waals (code < 0) or C6^0.4 (0 < code < 20).
+__global__ void __launch_bounds__(256) k_line_pre(int64_t L, uint32_t flags, const double *__restrict__ nu,
+                                                  const int64_t *__restrict__ Z, const int64_t *__restrict__ ion,
+                                                  const double *__restrict__ e_ion, const double *__restrict__ e_up,
+                                                  const double *__restrict__ e_lo, const double *__restrict__ A_ul,
+                                                  const double *__restrict__ mass, const double *__restrict__ stark,
+                                                  const double *__restrict__ waals, double *__restrict__ pre) {
+    const int64_t l = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (l >= L) return;
+    const double zeff = (double)(ion[l] + 1);
+    const double n_up = sdm::n_effective(zeff, e_ion[l], e_up[l]);
+    const double n_lo = sdm::n_effective(zeff, e_ion[l], e_lo[l]);
+    double *o = pre + l * LP_N;
+    // linear Stark, hydrogen lines only (broadening.py:614-620): 0.60 * a1 * (n_u^2 - n_l^2) [* n_e^(2/3)]
+    const bool ls = (flags & SD_LINEAR_STARK) && Z[l] == 1;
+    const double a1 = (n_up - n_lo < 1.5) ? 0.642 : 1.0;
+    o[LP_LS] = ls ? 0.60 * a1 * (n_up * n_up - n_lo * n_lo) : 0.0;
+    // C6^0.4 (broadening.py:420-472)
+    const double u2 = n_up * n_up, l2 = n_lo * n_lo;
+    const double c6 = 6.46e-34 * ((5.0 * u2 * u2 + u2) - (5.0 * l2 * l2 + l2)) / (2.0 * zeff * zeff);
+    const double c6_04 = pow(c6, 0.4);
+    if (flags & SD_VALD) {
+        const double w = waals[l];
+        o[LP_QS] = pow(10.0, stark[l]);
+        o[LP_VDW] = (w < 0) ? pow(10.0, w) : c6_04;
+        o[LP_WAALS] = w;
+        o[LP_STARK] = stark[l];
+    } else {
+        // C4^(2/3) (broadening.py:281-344)
+        const double eps0 = 1.0 / (4.0 * sdm::PI);
+        const double pref = (sdm::E_ESU * sdm::E_ESU * sdm::A0_CGS * sdm::A0_CGS * sdm::A0_CGS) /
+                            (36.0 * sdm::H_CGS * eps0 * zeff * zeff * zeff * zeff);
+        const double t1 = n_up * ((5.0 * n_up * n_up) + 1.0);
+        const double t2 = n_lo * ((5.0 * n_lo * n_lo) + 1.0);
+        const double c4 = pref * (t1 * t1 - t2 * t2);
+        o[LP_QS] = pow(c4, 2.0 / 3.0);
+        o[LP_VDW] = c6_04;
+        o[LP_WAALS] = 0.0;
+        o[LP_STARK] = 0.0;
+    }
+    o[LP_RAD] = A_ul[l];
+    o[LP_NUC] = nu[l] / sdm::C_CGS;
+    o[LP_MASS] = mass[l];
+}
+
+__global__ void k_depth_pre(int D, const double *__restrict__ T, const double *__restrict__ ne, const double *__restrict__ nH,
+                            double *__restrict__ pre) {
+    const int d = blockIdx.x * blockDim.x + threadIdx.x;
+    if (d >= D) return;
+    double *o = pre + d * DP_N;
+    const double Td = T[d], ned = ne[d];
+    o[DP_NE23] = pow(ned, 2.0 / 3.0);
+    o[DP_AQS] = 1e19 * sdm::KB_CGS * ned;
+    o[DP_T16] = pow(Td, 1.0 / 6.0);
+    o[DP_P17] = 17.0 * pow(8.0 * sdm::KB_CGS * Td / (sdm::PI * sdm::MP_CGS), 0.3);
+    o[DP_NH] = nH[d];
+    o[DP_2KT] = 2.0 * sdm::KB_CGS * Td;
+    o[DP_NE] = ned;
+    o[DP_T16V] = pow(Td / 1e4, 1.0 / 6.0);
+    o[DP_T038] = pow(Td / 1e4, 0.38);
+    o[DP_T] = Td;
+}
+
+// One thread per (line, depth), depth fastest: the 64-byte per-line block is a broadcast within a line, the per-depth
+// block comes from shared memory; two coalesced (L, D) stores.
+__global__ void __launch_bounds__(256) k_broadening(int64_t L, int D, const double *__restrict__ line_pre,
+                                                    const double *__restrict__ depth_pre, double vmic, uint32_t flags,
+                                                    double *__restrict__ gammas, double *__restrict__ dws) {
+    extern __shared__ double s_dp[];  // [D][DP_N]
+    for (int k = threadIdx.x; k < D * DP_N; k += blockDim.x) s_dp[k] = depth_pre[k];
+    __syncthreads();
+    const int64_t g = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;  // (l, d), d fastest
     if (g >= L * D) return;
-    int64_t l = g / D;
-    int d = (int)(g - l * D);
-    double zeff = (double)(ion[l] + 1);
-    double n_up = sdm::n_effective(zeff, e_ion[l], e_up[l]);
-    double n_lo = sdm::n_effective(zeff, e_ion[l], e_lo[l]);
-    double Td = T[d], ned = ne[d], nHd = nH[d];
+    const int64_t l = g / D;
+    const int d = (int)(g - l * D);
+    const double2 *lp2 = reinterpret_cast<const double2 *>(line_pre + l * LP_N);
+    const double2 p01 = __ldg(lp2), p23 = __ldg(lp2 + 1), p45 = __ldg(lp2 + 2), p67 = __ldg(lp2 + 3);
+    const double *dp = s_dp + d * DP_N;
     double gam;
     if (flags & SD_VALD) {  // broadening.py:1039-1085
         gam = 0.0;
-        if (flags & SD_RADIATION) gam += A_ul[l];
-        if ((flags & SD_LINEAR_STARK) && Z[l] == 1) gam += sdm::gamma_linear_stark(n_up, n_lo, ned);
-        if (flags & SD_QUADRATIC_STARK) gam += sdm::vald_stark(ned, stark[l], Td);
-        if (flags & SD_VAN_DER_WAALS) gam += sdm::vald_vdw_unit(waals[l], zeff, n_up, n_lo, Td, mass[l]) * nHd;
+        if (flags & SD_RADIATION) gam += p23.y;
+        if (flags & SD_LINEAR_STARK) gam += p01.x * dp[DP_NE23];  // 0 for non-hydrogen lines (finite densities)
+        if (flags & SD_QUADRATIC_STARK) {  // calc_vald_stark_gamma :880-890
+            const double gq = dp[DP_NE] * p01.y * dp[DP_T16V];
+            gam += (dp[DP_NE] * p67.y >= 0) ? 0.0 : gq;
+        }
+        if (flags & SD_VAN_DER_WAALS) {  // calc_vald_vdW :893-1006 (n_H = 1) * n_H
+            const double w = p67.x;
+            double unit;
+            if (w < 0) unit = p23.x * dp[DP_T038];
+            else if (w == 0.0) unit = 0.0;
+            else if (w < 20) unit = dp[DP_P17] * p23.x * 1.0 * w;
+            else if (!(w >= 20)) unit = 0.0;
+            else unit = sdm::vald_vdw_unit(w, 1.0, 1.0, 1.0, dp[DP_T], p45.y);  // ABO: T and the line mixed in one pow()
+            gam += unit * dp[DP_NH];
+        }
         gam /= 2.0;
     } else {  // broadening.py:611-654
         double g_ls = 0.0, g_qs = 0.0, g_vdw = 0.0, g_rad = 0.0;
-        if ((flags & SD_LINEAR_STARK) && Z[l] == 1) g_ls = sdm::gamma_linear_stark(n_up, n_lo, ned);
-        if (flags & SD_QUADRATIC_STARK) g_qs = sdm::gamma_quadratic_stark(zeff, n_up, n_lo, ned, Td);
-        if (flags & SD_VAN_DER_WAALS) g_vdw = sdm::gamma_van_der_waals(zeff, n_up, n_lo, Td, nHd);
-        if (flags & SD_RADIATION) g_rad = A_ul[l];
+        if (flags & SD_LINEAR_STARK) g_ls = p01.x * dp[DP_NE23];
+        if (flags & SD_QUADRATIC_STARK) g_qs = dp[DP_AQS] * p01.y * dp[DP_T16];
+        if (flags & SD_VAN_DER_WAALS) g_vdw = dp[DP_P17] * p23.x * dp[DP_NH];
+        if (flags & SD_RADIATION) g_rad = p23.y;
         gam = g_ls + g_qs + g_vdw + g_rad;
     }
     gammas[g] = gam;
-    dws[g] = sdm::doppler_width(nu[l], Td, mass[l], vmic);
+    dws[g] = p45.x * sqrt(dp[DP_2KT] / p45.y + vmic * vmic);  // calc_doppler_width :32-66
 }
 
 // d_nu = -max(diff(nus))  (opacities_solvers/base.py:524-526); one block.
@@ -111,6 +198,44 @@ __device__ __forceinline__ int hw_class(long long hw) {
     return k;
 }
 
+// Tiles [a_, b_) around the centre tile tc that are NOT far.  Farness is monotone in the distance from the centre (the
+// centre distance grows by 2 h per tile, the required distance by at most ~0.5 h), so each boundary is found from an
+// estimate (required distance / tile spacing at the centre tile) plus a short walk.  The three tiles around either
+// estimate are probed up front with INDEPENDENT loads (the walk then usually needs no further memory access: the
+// dependent load -> test -> load chain of a plain walk is what kept the first version of this kernel latency bound).
+__device__ __forceinline__ void near_interval(const double *__restrict__ geom, int n_tiles, int tc, double nu_l, double dw,
+                                              double y, int &a_out, int &b_out) {
+    const double h_c = geom[2 * tc + 1];
+    const double m_c = 15.0000001 - y;
+    const double need = fmax(SD_FAR_RHO_INV * h_c + 0.7071067811865476 * dw, h_c + (m_c > 0.0 ? m_c : 0.0) * dw);
+    const double est = need / (2.0 * h_c);
+    const int n_est = (est < (double)n_tiles) ? (int)est : n_tiles;  // NaN / inf -> the whole grid
+    int a_ = max(tc - n_est, 0), b_ = min(tc + n_est + 1, n_tiles);
+    // probes: tiles a_-1, a_, a_+1 and b_-2, b_-1, b_ (clamped; out-of-range probes are never consulted)
+    const int pa = a_ - 1, pb = b_ - 2;
+    bool fa[3], fb[3];
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        const int ta = min(max(pa + k, 0), n_tiles - 1), tb = min(max(pb + k, 0), n_tiles - 1);
+        fa[k] = tile_is_far(geom[2 * ta], geom[2 * ta + 1], nu_l, dw, y);
+        fb[k] = tile_is_far(geom[2 * tb], geom[2 * tb + 1], nu_l, dw, y);
+    }
+    auto far_a = [&](int t) {
+        const int k = t - pa;
+        return (k >= 0 && k < 3) ? (k == 0 ? fa[0] : (k == 1 ? fa[1] : fa[2])) : tile_is_far(geom[2 * t], geom[2 * t + 1], nu_l, dw, y);
+    };
+    auto far_b = [&](int t) {
+        const int k = t - pb;
+        return (k >= 0 && k < 3) ? (k == 0 ? fb[0] : (k == 1 ? fb[1] : fb[2])) : tile_is_far(geom[2 * t], geom[2 * t + 1], nu_l, dw, y);
+    };
+    while (a_ > 0 && !far_a(a_ - 1)) a_--;
+    while (a_ < tc && far_a(a_)) a_++;
+    while (b_ < n_tiles && !far_b(b_)) b_++;
+    while (b_ > tc + 1 && far_b(b_ - 1)) b_--;
+    a_out = a_;
+    b_out = b_;
+}
+
 // One thread per (line, depth), d fastest (coalesced reads of the (L,D) inputs).  Writes depth-major
 // records/windows (64-byte records are two full sectors, so the transposing write is not wasteful).
 __global__ void __launch_bounds__(256) k_build_records(int64_t L, int D, int64_t N, const double *__restrict__ line_nu,
@@ -126,6 +251,8 @@ __global__ void __launch_bounds__(256) k_build_records(int64_t L, int D, int64_t
     int rad_k[SD_FAR_LEVELS];
 #pragma unroll
     for (int k = 0; k < SD_FAR_LEVELS; k++) rad_k[k] = 0;
+    bool e_lo = false, e_hi = false;
+    unsigned long long key_lo = 0, key_hi = 0;
     if (active) {
         int64_t l = g / D;
         int d = (int)(g - l * D);
@@ -133,8 +260,9 @@ __global__ void __launch_bounds__(256) k_build_records(int64_t L, int D, int64_t
         double dw = dws[g];
         double a = alpha[g];
         double d_nu = d_nu_p[0];
+        const int idx = line_idx[l];
         long long lo, hi;
-        sdm::line_window(line_idx[l], N, gam, dw, a, d_nu, lo, hi);
+        sdm::line_window(idx, N, gam, dw, a, d_nu, lo, hi);
         // half-width as the reference computes it, for the class only
         double broad = ((gam + dw) * a) / d_nu * 20.0;
         double forced = (broad > 10.0) ? broad : 10.0;
@@ -152,7 +280,9 @@ __global__ void __launch_bounds__(256) k_build_records(int64_t L, int D, int64_t
         if (!(r.inv_dw > 0.0) || !(r.inv_dw < 1e300)) r.thr = NAN;  // dw <= 0, inf or NaN: exact path only
         r.pad0 = r.pad1 = 0.0;
         size_t o = (size_t)d * L + l;
-        rec[o] = r;
+        // The record is read only after a window test passed for a tile of this context: pairs whose window is empty
+        // or misses the extended pixel range never get that far (nu sharding: ~half of the record traffic per rank).
+        if (hi > lo && hi > fg.ext0 && lo < fg.ext1) rec[o] = r;
         PairWin pw;
         pw.lo = (int)lo;
         pw.hi = (int)hi;
@@ -160,7 +290,7 @@ __global__ void __launch_bounds__(256) k_build_records(int64_t L, int D, int64_t
         pw.pad0 = pw.pad1 = 0;
         // Far-capable pair: the window holds at least one level-0 tile and all parameters are finite.  Such pairs
         // form class 7; per hierarchy level they get the interval of tiles [nl, nh) around the line centre that are
-        // NOT far, and their window edges go to the two edge-sort key arrays.
+        // NOT far, and their window edges go to the edge list.
         const bool fc = fg.enabled && (hi - lo >= fg.tile[0]) && (r.thr == r.thr) && (a == a) && (fabs(a) < 1e300);
         if (fc) cls = SD_FC_CLASS;
         win_cls[o] = (uint8_t)cls;
@@ -172,23 +302,10 @@ __global__ void __launch_bounds__(256) k_build_records(int64_t L, int D, int64_t
                 int rad = 0;
                 const int tile = fg.tile[k], n_tiles = fg.n_tiles[k];
                 if (fc && hi - lo >= tile) {
-                    const double *__restrict__ geom = fg.geom[k];
-                    int tc = (int)(line_idx[l] / tile);
+                    int tc = idx / tile;
                     if (tc >= n_tiles) tc = n_tiles - 1;
-                    // [a_, b_): tiles around the line centre that are not far.  Farness is monotone in the distance from
-                    // the centre (the centre distance grows by 2 h per tile, the required distance by at most ~0.5 h), so
-                    // the two boundaries are found from an estimate (required distance / tile spacing at the centre
-                    // tile) plus a short walk in either direction instead of a walk from the centre.
-                    const double h_c = geom[2 * tc + 1];
-                    const double m_c = 15.0000001 - y;
-                    const double need = fmax(SD_FAR_RHO_INV * h_c + 0.7071067811865476 * dw, h_c + (m_c > 0.0 ? m_c : 0.0) * dw);
-                    const double est = need / (2.0 * h_c);
-                    const int n_est = (est < (double)n_tiles) ? (int)est : n_tiles;  // NaN / inf -> the whole grid
-                    int a_ = max(tc - n_est, 0), b_ = min(tc + n_est + 1, n_tiles);
-                    while (a_ > 0 && !tile_is_far(geom[2 * (a_ - 1)], geom[2 * (a_ - 1) + 1], r.nu, dw, y)) a_--;
-                    while (a_ < tc && tile_is_far(geom[2 * a_], geom[2 * a_ + 1], r.nu, dw, y)) a_++;
-                    while (b_ < n_tiles && !tile_is_far(geom[2 * b_], geom[2 * b_ + 1], r.nu, dw, y)) b_++;
-                    while (b_ > tc + 1 && tile_is_far(geom[2 * (b_ - 1)], geom[2 * (b_ - 1) + 1], r.nu, dw, y)) b_--;
+                    int a_, b_;
+                    near_interval(fg.geom[k], n_tiles, tc, r.nu, dw, y, a_, b_);
                     nl = (unsigned)a_;
                     nh = (unsigned)b_;
                     rad = max(tc - a_, b_ - 1 - tc);
@@ -196,10 +313,11 @@ __global__ void __launch_bounds__(256) k_build_records(int64_t L, int D, int64_t
                 pw.near[k] = nl | (nh << 16);
                 rad_k[k] = rad;
             }
-            const unsigned dkey = (unsigned)d << fg.key_shift, none = (1u << fg.key_shift) - 1u;
-            fg.lo_keys[o] = dkey | ((fc && lo > 0) ? (unsigned)lo : none);
-            fg.hi_keys[o] = dkey | ((fc && hi < N) ? (unsigned)hi : none);
-            fg.lo_l[o] = (int)l;
+            // window edges strictly inside the extended range (tiles only look for edges strictly inside themselves)
+            e_lo = fc && lo > fg.ext0 && lo < fg.ext1;
+            e_hi = fc && hi < N && hi > fg.ext0 && hi < fg.ext1;
+            key_lo = sd_edge_key(fg, 0, d, lo, (int)l);
+            key_hi = sd_edge_key(fg, 1, d, hi, (int)l);
         }
         win[o] = pw;
         nonempty = hi > lo;
@@ -207,12 +325,21 @@ __global__ void __launch_bounds__(256) k_build_records(int64_t L, int D, int64_t
         zero_dw = (hi > lo) && (dw == 0.0);
     }
     if (fg.enabled) {
+        const unsigned lane = threadIdx.x & 31, lt = (1u << lane) - 1u;
 #pragma unroll
         for (int k = 0; k < SD_FAR_LEVELS; k++) {
             int m = rad_k[k];
             for (int o2 = 16; o2; o2 >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o2));
-            if ((threadIdx.x & 31) == 0 && m > 0) atomicMax(&fg.near_rad[k], m);
+            if (lane == 0 && m > 0) atomicMax(&fg.near_rad[k], m);
         }
+        // warp-aggregated append of the edge keys (order irrelevant: the keys are sorted into a total order)
+        const unsigned m_lo = __ballot_sync(0xffffffffu, e_lo), m_hi = __ballot_sync(0xffffffffu, e_hi);
+        const int n_lo = __popc(m_lo), n_hi = __popc(m_hi);
+        unsigned long long base = 0;
+        if (lane == 0 && n_lo + n_hi) base = atomicAdd(fg.edge_count, (unsigned long long)(n_lo + n_hi));
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (e_lo) fg.edge_out[base + __popc(m_lo & lt)] = key_lo;
+        if (e_hi) fg.edge_out[base + n_lo + __popc(m_hi & lt)] = key_hi;
     }
     unsigned ne_w = __popc(__ballot_sync(0xffffffffu, nonempty));
     unsigned wd_w = __popc(__ballot_sync(0xffffffffu, wide));
@@ -306,11 +433,21 @@ int sd_k1_broadening(sd_ctx *c, uint32_t flags) {
     if (n == 0) return SD_OK;
     const double *stark = c->has_vald_cols ? c->l_stark.as<double>() : nullptr;
     const double *waals = c->has_vald_cols ? c->l_waals.as<double>() : nullptr;
-    k_broadening<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(
-        c->L, c->D, c->l_nu.as<double>(), c->l_Z.as<int64_t>(), c->l_ion.as<int64_t>(), c->l_eion.as<double>(),
+    SD_TRY(sd_ensure(c, c->line_pre, sizeof(double) * LP_N * c->L));
+    SD_TRY(sd_ensure(c, c->depth_pre, sizeof(double) * DP_N * c->D));
+    k_line_pre<<<(unsigned)((c->L + 255) / 256), 256, 0, c->stream>>>(
+        c->L, flags, c->l_nu.as<double>(), c->l_Z.as<int64_t>(), c->l_ion.as<int64_t>(), c->l_eion.as<double>(),
         c->l_eup.as<double>(), c->l_elo.as<double>(), c->l_A.as<double>(), c->l_mass.as<double>(), stark, waals,
-        c->T.as<double>(), c->ne.as<double>(), c->nH.as<double>(), c->vmic, flags, c->gammas.as<double>(),
-        c->dws.as<double>());
+        c->line_pre.as<double>());
+    SD_TRY(sd_launch_check(c, "k_line_pre"));
+    k_depth_pre<<<(c->D + 63) / 64, 64, 0, c->stream>>>(c->D, c->T.as<double>(), c->ne.as<double>(), c->nH.as<double>(),
+                                                       c->depth_pre.as<double>());
+    SD_TRY(sd_launch_check(c, "k_depth_pre"));
+    const size_t smem = sizeof(double) * DP_N * c->D;
+    SD_CHECK(c, smem <= 48 * 1024, SD_ERR_ARG, "sd_calc_broadening: too many depth points (%d)", c->D);
+    k_broadening<<<(unsigned)((n + 255) / 256), 256, smem, c->stream>>>(c->L, c->D, c->line_pre.as<double>(),
+                                                                       c->depth_pre.as<double>(), c->vmic, flags,
+                                                                       c->gammas.as<double>(), c->dws.as<double>());
     return sd_launch_check(c, "k_broadening");
 }
 
@@ -339,9 +476,16 @@ int sd_k2_prepare(sd_ctx *c) {
     }
     fg.near_rad = nullptr;
     fg.enabled = 0;
-    fg.key_shift = 0;
-    fg.lo_keys = fg.hi_keys = nullptr;
-    fg.lo_l = fg.hi_l = nullptr;
+    fg.edge_keys = nullptr;
+    fg.edge_off = nullptr;
+    fg.edge_out = nullptr;
+    fg.edge_count = nullptr;
+    fg.l_bits = fg.pix_bits = fg.depth_bits = 1;
+    // extended pixel range of this context: the top-level tiles its range [p0, p1) touches
+    const long long T_top = fg.tile[SD_FAR_LEVELS - 1];
+    fg.ext0 = (c->p0 / T_top) * T_top;
+    fg.ext1 = ((c->p1 + T_top - 1) / T_top) * T_top;
+    if (fg.ext1 > c->N) fg.ext1 = c->N;
     if (L == 0) {
         SD_CUDA(c, cudaMemsetAsync(c->cls_off.p, 0, sizeof(int) * D * (SD_NCLS + 1), c->stream));
         sd_phase_end(c, SD_PH_PREP);
@@ -355,26 +499,20 @@ int sd_k2_prepare(sd_ctx *c) {
     SD_TRY(sd_ensure(c, c->cls_list, sizeof(int) * n));
     if (c->farfield) {
         fg.enabled = 1;
-        int pix_bits = 1, depth_bits = 1;
-        while ((1LL << pix_bits) <= c->N) pix_bits++;
-        while ((1 << depth_bits) < D) depth_bits++;
-        SD_CHECK(c, pix_bits + depth_bits <= 32, SD_ERR_ARG,
-                 "far-field scheme: (depth, pixel) does not fit a 32-bit sort key (D = %d, N = %lld); use sd_set_farfield(ctx, 0)",
-                 D, (long long)c->N);
-        fg.key_shift = pix_bits;
+        while ((1LL << fg.pix_bits) <= c->N) fg.pix_bits++;
+        while ((1 << fg.depth_bits) < D) fg.depth_bits++;
+        while ((1LL << fg.l_bits) < L) fg.l_bits++;
+        SD_CHECK(c, 1 + fg.depth_bits + fg.pix_bits + fg.l_bits <= 64, SD_ERR_ARG,
+                 "far-field scheme: (depth, pixel, line) does not fit a 64-bit sort key (D = %d, N = %lld, L = %lld); use "
+                 "sd_set_farfield(ctx, 0)", D, (long long)c->N, (long long)L);
         SD_TRY(sd_ensure(c, c->near_rad, sizeof(int) * SD_FAR_LEVELS));
         SD_CUDA(c, cudaMemsetAsync(c->near_rad.p, 0, sizeof(int) * SD_FAR_LEVELS, c->stream));
         fg.near_rad = c->near_rad.as<int>();
-        // unsorted keys go to the temporaries (window starts) / to edge_keys[1] (window ends, sorted second)
-        SD_TRY(sd_ensure(c, c->edge_tmp_keys, sizeof(unsigned) * n));
-        SD_TRY(sd_ensure(c, c->edge_tmp_l, sizeof(int) * n));
-        for (int w = 0; w < 2; w++) {
-            SD_TRY(sd_ensure(c, c->edge_keys[w], sizeof(unsigned) * n));
-            SD_TRY(sd_ensure(c, c->edge_l[w], sizeof(int) * n));
-        }
-        fg.lo_keys = c->edge_tmp_keys.as<unsigned>();
-        fg.hi_keys = c->edge_keys[0].as<unsigned>();  // staging; overwritten by the first sort's output later
-        fg.lo_l = c->edge_tmp_l.as<int>();
+        SD_TRY(sd_ensure(c, c->edge_unsorted, sizeof(unsigned long long) * 2 * n));  // worst case: both edges of every pair
+        SD_TRY(sd_ensure(c, c->edge_count, sizeof(unsigned long long)));
+        SD_CUDA(c, cudaMemsetAsync(c->edge_count.p, 0, sizeof(unsigned long long), c->stream));
+        fg.edge_out = c->edge_unsorted.as<unsigned long long>();
+        fg.edge_count = c->edge_count.as<unsigned long long>();
     }
     int nchunks = (int)((L + CHUNK - 1) / CHUNK);
     SD_TRY(sd_ensure(c, c->chunk_cnt, sizeof(int) * (size_t)D * SD_NCLS * nchunks));
@@ -396,13 +534,7 @@ int sd_k2_prepare(sd_ctx *c) {
     sd_phase_end(c, SD_PH_PREP);
     if (c->farfield) {
         sd_phase_begin(c, SD_PH_SORT);
-        // window ends were staged in edge_keys[0]: sort them first (into edge_keys[1]/edge_l[1]), then the starts
-        SD_TRY(sd_sort_edges(c, 1, n));
-        SD_TRY(sd_sort_edges(c, 0, n));
-        fg.lo_keys = c->edge_keys[0].as<unsigned>();
-        fg.lo_l = c->edge_l[0].as<int>();
-        fg.hi_keys = c->edge_keys[1].as<unsigned>();
-        fg.hi_l = c->edge_l[1].as<int>();
+        SD_TRY(sd_sort_edges(c));
         sd_phase_end(c, SD_PH_SORT);
     }
     c->records_ready = true;

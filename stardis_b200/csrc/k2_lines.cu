@@ -127,7 +127,7 @@ __device__ __forceinline__ void class_range(const LineArgs &a, int d, int cls, i
 }
 
 // first j in [a, b) with keys[j] >= X (keys ascending), b if none.  Warp-cooperative 32-ary search.
-__device__ __forceinline__ int warp_lower_bound_u32(const unsigned *__restrict__ keys, int a, int b, unsigned X) {
+__device__ __forceinline__ int warp_lower_bound_u64(const unsigned long long *__restrict__ keys, int a, int b, unsigned long long X) {
     const int lane = threadIdx.x & 31;
     while (b > a) {
         int n = b - a;
@@ -158,11 +158,9 @@ __device__ __forceinline__ void fc_near_range(const LineArgs &a, int d, int lev,
 
 // Far-capable pairs of depth d with a window start (which = 0) or end (which = 1) strictly inside (t0, t1).
 __device__ __forceinline__ void fc_edge_range(const LineArgs &a, int d, int which, int64_t t0, int64_t t1, int &ja, int &jb) {
-    const unsigned *keys = (which ? a.fg.hi_keys : a.fg.lo_keys);
-    const unsigned dk = (unsigned)d << a.fg.key_shift;
-    const int lo = (int)((size_t)d * a.L), hi = lo + (int)a.L;
-    ja = warp_lower_bound_u32(keys, lo, hi, dk | (unsigned)(t0 + 1));
-    jb = warp_lower_bound_u32(keys, ja, hi, dk | (unsigned)t1);
+    const int lo = a.fg.edge_off[which * (a.D + 1) + d], hi = a.fg.edge_off[which * (a.D + 1) + d + 1];
+    ja = warp_lower_bound_u64(a.fg.edge_keys, lo, hi, sd_edge_key(a.fg, which, d, t0 + 1, 0));
+    jb = warp_lower_bound_u64(a.fg.edge_keys, ja, hi, sd_edge_key(a.fg, which, d, t1, 0));
 }
 
 // one 32-byte gather (two 16-byte loads of the same sector)
@@ -255,6 +253,7 @@ __global__ void __launch_bounds__(THREADS) k_far_coeffs(LineArgs a, int lev, int
     }
     const size_t drow = (size_t)d * a.L;
     const int *list_d = a.cls_list + drow;
+    const unsigned long long lmask = (1ull << a.fg.l_bits) - 1ull;  // line index = low bits of a window-edge key
     if (warp < 3) {
         int ja, jb;
         if (!has_parent) {
@@ -330,7 +329,7 @@ __global__ void __launch_bounds__(THREADS) k_far_coeffs(LineArgs a, int lev, int
                 const int idx = r * THREADS + tid, j = base + idx;
                 unsigned mask = 0;
                 if (j < jb) {
-                    const int l = (src == 0) ? list_d[j] : (src == 1 ? a.fg.lo_l[j] : a.fg.hi_l[j]);
+                    const int l = (src == 0) ? list_d[j] : (int)(a.fg.edge_keys[j] & lmask);
                     const PairWin pw = load_win(a.win + drow + l);
                     const int lo = pw.lo, hi = pw.hi;
                     bool okp = true;
@@ -454,6 +453,7 @@ __global__ void __launch_bounds__(32 * NW, MINB) k_lines(LineArgs a) {
     const int *list_d = a.cls_list + drow;
     const double *__restrict__ nus = a.nus;
     const bool use_far = a.fg.enabled != 0;
+    const unsigned long long lmask = (1ull << a.fg.l_bits) - 1ull;  // line index = low bits of a window-edge key
 
     // pixel frequencies and accumulators live in registers for the whole kernel
     double nu_i[P], acc[P];
@@ -519,7 +519,7 @@ __global__ void __launch_bounds__(32 * NW, MINB) k_lines(LineArgs a) {
                 int l;
                 if (src == 0) l = j;                                   // class 0: the nu-sorted line list itself
                 else if (src <= SD_FC_CLASS) l = list_d[j];            // class lists (7 = far-capable pairs near the tile)
-                else l = (src == SD_NCLS) ? a.fg.lo_l[j] : a.fg.hi_l[j];  // far-capable pairs with an edge inside the tile
+                else l = (int)(a.fg.edge_keys[j] & lmask);             // far-capable pairs with an edge inside the tile
                 o = drow + l;
                 const PairWin pw = load_win(a.win + o);
                 lo = pw.lo;
@@ -600,6 +600,10 @@ __global__ void __launch_bounds__(32 * NW, MINB) k_lines(LineArgs a) {
                             }
                         }
                     }
+                    // the next entry's pass may update the same pixel from another lane: order the shared read-modify-
+                    // writes of the warp (independent thread scheduling gives no lock-step guarantee after the divergent
+                    // exact path; compute-sanitizer racecheck flagged exactly this line)
+                    __syncwarp();
                 } else {
                     // long overlap (a near-field pair whose core or window edge lies in this span): register slots
                     const int lo2 = e2.lo, hi2 = e2.hi;

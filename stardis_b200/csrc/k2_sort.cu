@@ -1,29 +1,61 @@
-// k2_sort.cu -- ordering of the far-capable (line, depth) pairs by the pixel position of their window edges.
+// k2_sort.cu -- ordering of the window edges of the far-capable (line, depth) pairs.
 //
 // Part of the K2 PREPARATION pass of the far-field scheme (not of the per-pixel hot loop): the pairs whose window
-// starts (ends) strictly inside a given tile are found by two binary searches in these sorted arrays instead of by
-// scanning whole class lists per tile.  Keys are 32-bit (depth << key_shift | edge pixel), values the line index; a stable
-// LSD radix sort keeps equal keys in line order, so everything downstream stays deterministic.  This is the one place
-// where a CUDA toolkit utility (CUB, header-only, compiled here for sm_100a) is used instead of a hand-written kernel.
+// starts (ends) strictly inside a given tile are found by two binary searches in ONE sorted array instead of by
+// scanning whole class lists per tile.  k_build_records appends a 64-bit key
+//     kind (0 start / 1 end) | depth | edge pixel | line index
+// only for edges that exist (inside the grid) and can matter to this context (inside its extended pixel range), so a
+// nu shard sorts ~1/R of what a whole-grid run sorts.  The key is a total order: the sorted array -- and every
+// summation order derived from it -- is independent of the (atomic) append order.  The radix sort itself is the one
+// CUDA toolkit utility in the library (CUB, header-only, compiled here for sm_100a); it needs the number of keys on the
+// host, which costs one 8-byte device->host copy and stream synchronisation per preparation pass.
 #include <cub/device/device_radix_sort.cuh>
 
 #include "sd_internal.h"
 
-// which == 1: window ENDS   (unsorted keys staged in edge_keys[0])  -> edge_keys[1], edge_l[1]
-// which == 0: window STARTS (unsorted keys in edge_tmp_keys)        -> edge_keys[0], edge_l[0]
-int sd_sort_edges(sd_ctx *c, int which, int64_t n) {
-    const unsigned *keys_in = which ? c->edge_keys[0].as<unsigned>() : c->edge_tmp_keys.as<unsigned>();
-    unsigned *keys_out = c->edge_keys[which].as<unsigned>();
-    const int *vals_in = c->edge_tmp_l.as<int>();
-    int *vals_out = c->edge_l[which].as<int>();
-    int depth_bits = 1;
-    while ((1 << depth_bits) < c->D) depth_bits++;
-    const int end_bit = c->far_geom.key_shift + depth_bits;
-    size_t bytes = 0;
-    SD_CUDA(c, cub::DeviceRadixSort::SortPairs(nullptr, bytes, keys_in, keys_out, vals_in, vals_out, (int)n, 0, end_bit, c->stream));
-    SD_TRY(sd_ensure(c, c->edge_sort_tmp, bytes));
-    SD_CUDA(c, cub::DeviceRadixSort::SortPairs(c->edge_sort_tmp.p, bytes, keys_in, keys_out, vals_in, vals_out, (int)n, 0, end_bit,
-                                               c->stream));
-    c->launches += 6;  // histogram + one-sweep passes of the radix sort (approximate; library kernels)
-    return SD_OK;
+namespace {
+// off[kind * (D + 1) + d] = first sorted key of (kind, d); the entry d == D closes the kind's range
+__global__ void k_edge_offsets(FarGeom fg, const unsigned long long *__restrict__ keys, const unsigned long long *__restrict__ count,
+                               int D, int *__restrict__ off) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= 2 * (D + 1)) return;
+    const int kind = i / (D + 1), d = i - kind * (D + 1);
+    const long long M = (long long)count[0];
+    long long lo = 0, hi = M;
+    if (kind == 1 && d == D) lo = M;
+    else {
+        const unsigned long long X = (d == D) ? sd_edge_key(fg, kind + 1, 0, 0, 0) : sd_edge_key(fg, kind, d, 0, 0);
+        while (lo < hi) {
+            const long long mid = lo + ((hi - lo) >> 1);
+            if (keys[mid] < X) lo = mid + 1; else hi = mid;
+        }
+    }
+    off[i] = (int)lo;
+}
+}  // namespace
+
+int sd_sort_edges(sd_ctx *c) {
+    FarGeom &fg = c->far_geom;
+    if (!c->h_edge_count) SD_CUDA(c, cudaHostAlloc((void **)&c->h_edge_count, sizeof(unsigned long long), cudaHostAllocDefault));
+    SD_CUDA(c, cudaMemcpyAsync(c->h_edge_count, c->edge_count.p, sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
+    SD_CUDA(c, cudaStreamSynchronize(c->stream));
+    const long long M = (long long)*c->h_edge_count;
+    SD_CHECK(c, M >= 0 && M < 2147483647LL, SD_ERR_STATE, "window-edge list too long (%lld entries)", M);
+    SD_TRY(sd_ensure(c, c->edge_keys, sizeof(unsigned long long) * (size_t)(M > 0 ? M : 1)));
+    SD_TRY(sd_ensure(c, c->edge_off, sizeof(int) * 2 * (c->D + 1)));
+    if (M > 0) {
+        const int end_bit = 1 + fg.depth_bits + fg.pix_bits + fg.l_bits;
+        const unsigned long long *in = c->edge_unsorted.as<unsigned long long>();
+        unsigned long long *out = c->edge_keys.as<unsigned long long>();
+        size_t bytes = 0;
+        SD_CUDA(c, cub::DeviceRadixSort::SortKeys(nullptr, bytes, in, out, (int)M, 0, end_bit, c->stream));
+        SD_TRY(sd_ensure(c, c->edge_sort_tmp, bytes));
+        SD_CUDA(c, cub::DeviceRadixSort::SortKeys(c->edge_sort_tmp.p, bytes, in, out, (int)M, 0, end_bit, c->stream));
+        c->launches += 2 + (end_bit + 7) / 8;  // histogram + scan + one-sweep passes (library kernels, approximate)
+    }
+    fg.edge_keys = c->edge_keys.as<unsigned long long>();
+    fg.edge_off = c->edge_off.as<int>();
+    k_edge_offsets<<<(2 * (c->D + 1) + 127) / 128, 128, 0, c->stream>>>(fg, fg.edge_keys, c->edge_count.as<unsigned long long>(), c->D,
+                                                                      c->edge_off.as<int>());
+    return sd_launch_check(c, "k_edge_offsets");
 }

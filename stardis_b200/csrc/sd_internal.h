@@ -49,13 +49,23 @@ struct FarGeom {
     const double *geom[SD_FAR_LEVELS];  // {centre frequency, half-width} per tile
     int enabled;                        // far field on (PairWin::near is filled, edge lists exist)
     int *near_rad;                      // [SD_FAR_LEVELS] largest half-extent (in tiles) of any near interval
-    // far-capable pairs sorted by the position of their window edges (per depth: entries [d L, (d+1) L)); keys are
-    // 32-bit (depth << key_shift | pixel), 2^key_shift > N, pixel = 2^key_shift - 1 when the pair has no such edge
-    // inside the grid (as few key bits as possible: the radix sort of the preparation pass is priced per byte)
-    unsigned *lo_keys, *hi_keys;
-    int key_shift;
-    int *lo_l, *hi_l;
+    // Window edges of the far-capable pairs that lie inside the grid AND inside this context's extended pixel range
+    // (the top-level tiles its range touches), as ONE sorted array of 64-bit keys
+    //   kind (0 = window start, 1 = window end) | depth | edge pixel | line index      (see sd_edge_key)
+    // -- a total order, so the result does not depend on the order in which k_build_records appended them.
+    // edge_off[kind * (D + 1) + d] = first entry of (kind, d); [.. + D] = end of the kind's entries.
+    const unsigned long long *edge_keys;
+    const int *edge_off;
+    int l_bits, pix_bits, depth_bits;
+    unsigned long long *edge_out;        // unsorted append buffer (k_build_records)
+    unsigned long long *edge_count;      // [1] number of appended keys
+    long long ext0, ext1;                // extended pixel range [ext0, ext1): pairs whose window misses it get no LineRec
 };
+
+__host__ __device__ __forceinline__ unsigned long long sd_edge_key(const FarGeom &fg, int kind, int d, long long pixel, int l) {
+    return ((((unsigned long long)kind << fg.depth_bits | (unsigned long long)d) << fg.pix_bits | (unsigned long long)pixel)
+            << fg.l_bits) | (unsigned long long)(unsigned)l;
+}
 
 struct DevBuf {
     void *p = nullptr;
@@ -111,8 +121,10 @@ struct sd_ctx {
     DevBuf chunk_cnt;  // int32 [D * nchunks * NCLS]
     DevBuf stats;      // uint64 [8]
     DevBuf near_rad;                   // int [SD_FAR_LEVELS]
-    DevBuf edge_keys[2], edge_l[2];    // sorted (depth, edge pixel) keys / line indices: [0] window starts, [1] window ends
-    DevBuf edge_tmp_keys, edge_tmp_l, edge_sort_tmp;
+    DevBuf edge_keys, edge_unsorted;   // 64-bit window-edge keys (sorted / as appended), see FarGeom
+    DevBuf edge_off, edge_count, edge_sort_tmp;
+    DevBuf line_pre, depth_pre;        // K1: per-line / per-depth factors of the broadening formulae (pow() hoisted)
+    unsigned long long *h_edge_count = nullptr;  // pinned host copy of the edge counter
     DevBuf tile_geom[SD_FAR_LEVELS];   // double [2 * n_tiles]: centre frequency and half-width of every global tile
     DevBuf far_coef[SD_FAR_LEVELS];    // double [D * n_tiles_shard * (SD_FAR_K + 1)]
     DevBuf far_part;                   // partial top-level coefficient sets (8 slices of the pair list per tile)
@@ -176,7 +188,7 @@ int sd_k1_broadening(sd_ctx *c, uint32_t flags);
 int sd_k2_prepare(sd_ctx *c);
 int sd_k2_lines(sd_ctx *c, int slot);
 int sd_k2_choose_P(sd_ctx *c);
-int sd_sort_edges(sd_ctx *c, int which, int64_t n);  // k2_sort.cu (CUB radix sort of the edge keys)
+int sd_sort_edges(sd_ctx *c);  // k2_sort.cu (CUB radix sort of the appended window-edge keys + segment offsets)
 int sd_k3_continuum(sd_ctx *c, const sd_continuum *desc, uint32_t store_mask);
 int sd_k4_raytrace(sd_ctx *c, int n_theta, const double *ray_ds, const double *weights, int inward, double scale,
                    int track);
