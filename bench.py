@@ -57,6 +57,8 @@ def parse_args():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="solar_full")
     ap.add_argument("--lines", type=int, default=None, help="override the number of synthetic lines")
+    ap.add_argument("--partition", default="depth", choices=["depth", "nu"],
+                    help="multi-GPU decomposition of the opacity stages (the formal solution is always sharded by nu)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-direct", action="store_true", help="skip the direct-mode (far field off) comparison run")
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="target CPU time of one reference sample")
@@ -92,11 +94,15 @@ def build_workload(args, name=None):
     return w, cfg, desc
 
 
-def config_block(desc, n_lines, D, cells, world, bounds):
+def config_block(desc, n_lines, D, cells, world, bounds, partition="depth"):
+    if world > 1 and partition == "depth":
+        part = (f"opacity stages: depth points r, r+{world}, ... of the whole grid on rank r; one NCCL all-to-all of the total "
+                f"opacity; formal solution: {world} equal-width nu ranges; all-gather of the spectrum")
+    else:
+        part = f"{world} contiguous nu range(s), global windows, cut at equal (pixels + 10 x lines inside)"
     return {"workload": desc,
             "l2": "inputs larger than L2 (line records %.2f GB, outputs %.2f GB per array)" % (n_lines * D * 64 / 1e9, cells * 8 / 1e9),
-            "partition": f"{world} contiguous nu range(s), global windows, cut at equal (pixels + 10 x lines inside)",
-            "ranges": [list(b) for b in bounds]}
+            "partition": part, "ranges": [list(b) for b in bounds]}
 
 
 # ----------------------------------------------------------------------------------------------- clocks
@@ -196,68 +202,101 @@ def rel_err(a, b):
 
 
 class HotPath:
-    """Resident inputs of one workload on one context + the device step (pointers into the C ABI)."""
+    """Resident inputs of one workload on one rank + the device step (pointers into the C ABI).
 
-    def __init__(self, ctx, w, cfg, rank, world, torch):
+    world == 1: one context, all depth points, whole grid.  world > 1 (``partition`` "depth"): the opacity stages
+    (K1, preparation, K2, K3) run on ``ctx_op`` for the depth points rank, rank + world, ... of the WHOLE grid, one
+    all-to-all moves the total opacity to the equal-width pixel ranges, the formal solution runs on ``ctx`` for all
+    depth points of this rank's range, the emergent spectrum is all-gathered.  ``partition`` "nu": everything on this
+    rank's cost-balanced pixel range (no exchange; the per-(line, depth) preparation is repeated on every rank)."""
+
+    def __init__(self, ctx, w, cfg, rank, world, torch, partition="depth", stream=None):
         from stardis_b200 import _lib as L
         from stardis_b200 import units as u
-        from stardis_b200.distributed import line_balanced_bounds
+        from stardis_b200.device import DeviceContext
+        from stardis_b200.distributed import all_shards, depth_indices, line_balanced_bounds
         from stardis_b200.radiation_field import RadiationField
         from stardis_b200.radiation_field.opacities.opacities_solvers import base as ob
-        from stardis_b200.radiation_field.opacities.opacities_solvers.broadening import set_device_atmosphere
         from stardis_b200.radiation_field.radiation_field_solvers.base import ray_distances
 
-        self.L_, self.ctx, self.torch, self.world = L, ctx, torch, world
+        self.L_, self.ctx, self.torch, self.world, self.rank = L, ctx, torch, world, rank
         model, plasma, nus = w["model"], w["plasma"], w["nus"]
         self.model, self.plasma, self.nus, self.cfg = model, plasma, nus, cfg
         self.N, self.D = len(nus), model.no_of_depth_points
+        self.depth_mode = world > 1 and partition == "depth"
         line_cfg = cfg.opacity.line
         self.nus_q = u.Quantity(nus, u.Hz)
         self.lines = ob.select_lines(plasma, model, self.nus_q, line_cfg)
-        # cost-balanced contiguous nu ranges (pixels + 10 x lines inside): the blue end of the grid holds ~10x more
-        # lines per pixel than the red end, so equal-width ranges would leave rank 0 with several times the core work
-        self.bounds = line_balanced_bounds(nus, self.lines.nu, world)
+        if self.depth_mode:
+            self.bounds = all_shards(self.N, world)
+            self.didx = depth_indices(self.D, rank, world)
+            self.ctx_op = DeviceContext(ctx.device, stream=stream)
+        else:
+            # cost-balanced contiguous nu ranges (pixels + 10 x lines inside): the blue end of the grid holds ~10x more
+            # lines per pixel than the red end, so equal-width ranges would leave rank 0 with several times the core work
+            self.bounds = line_balanced_bounds(nus, self.lines.nu, world)
+            self.didx = np.arange(self.D)
+            self.ctx_op = ctx
         self.p0, self.p1 = self.bounds[rank]
         self.W = self.p1 - self.p0
         self.flags = ob._line_flags(line_cfg)
-        self.tables, _ = ob.file_tables(plasma, model, cfg.opacity.file)
-        self.bf_cut, self.bf_prefix = ob.bf_descriptor(plasma, cfg.opacity.bf)
-        self.ff_coef = ob.ff_descriptor(plasma, model, cfg.opacity.ff)
-        self.rayleigh = ob.rayleigh_descriptor(plasma, model, cfg.opacity.rayleigh)
-        self.electron = ob.electron_descriptor(plasma)
+        didx = self.didx
+        tables, _ = ob.file_tables(plasma, model, cfg.opacity.file)
+        self.tables = [dict(t, depth_scale=np.ascontiguousarray(t["depth_scale"][didx]),
+                            depth_y=None if t.get("depth_y") is None else np.ascontiguousarray(t["depth_y"][didx])) for t in tables]
+        self.bf_cut, bf_prefix = ob.bf_descriptor(plasma, cfg.opacity.bf)
+        self.bf_prefix = np.ascontiguousarray(bf_prefix[:, didx])
+        self.ff_coef = np.ascontiguousarray(ob.ff_descriptor(plasma, model, cfg.opacity.ff)[didx])
+        self.rayleigh = tuple(np.ascontiguousarray(c[didx]) for c in ob.rayleigh_descriptor(plasma, model, cfg.opacity.rayleigh))
+        self.electron = np.ascontiguousarray(ob.electron_descriptor(plasma)[didx])
         self.srf0 = RadiationField(self.nus_q, None, model, cfg.no_of_thetas)
         self.ds, self.inward = ray_distances(model, self.srf0.thetas)
-        self.set_atmosphere = lambda: set_device_atmosphere(ctx, model, plasma)
-        self.set_atmosphere()
+        T = u.values_of(model.temperatures)
+        n_e = np.asarray(plasma.electron_densities.values, dtype=np.float64)
+        n_H = np.asarray(plasma.ion_number_density.loc[1, 0].values, dtype=np.float64)
+        self.model_vmic = float(u.cgs_values_of(model.microturbulence))
+        self.ctx_op.set_atmosphere(T[didx], n_e[didx], n_H[didx], self.model_vmic)
+        if self.depth_mode:
+            self.ctx_op.set_grid(nus)
+            ctx.set_atmosphere(T, n_e, n_H, self.model_vmic)
+            self.t_local = torch.empty((len(didx), self.N), dtype=torch.float64, device="cuda")
         ctx.set_grid(nus, self.p0, self.p1)
-        self.d_lines = {k: torch.from_numpy(np.ascontiguousarray(getattr(self.lines, k))).cuda() for k in
-                        ("nu", "alpha_line", "mass", "atomic_number", "ion_number", "ionization_energy", "level_energy_upper",
-                         "level_energy_lower", "A_ul")}
+        cols = {k: np.ascontiguousarray(getattr(self.lines, k)) for k in
+                ("nu", "mass", "atomic_number", "ion_number", "ionization_energy", "level_energy_upper", "level_energy_lower", "A_ul")}
+        cols["alpha_line"] = np.ascontiguousarray(self.lines.alpha_line[:, didx])
+        self.d_lines = {k: torch.from_numpy(v).cuda() for k, v in cols.items()}
         self.d_spec = torch.empty(self.W, dtype=torch.float64, device="cuda")
+
+    N_EVENTS = 7
+    PHASES = ("K1_broadening", "K2_prepare_and_lines", "K3_continuum", "depth_to_nu_exchange", "K4_raytrace", "spectrum_gather")
 
     def step(self, ev=None, stream=None, gather=True):
         """One pass of the hot path on resident inputs."""
-        from stardis_b200.distributed import allgather_spectrum
+        from stardis_b200.distributed import allgather_spectrum, exchange_depth_to_nu
 
-        ctx, d, L = self.ctx, self.d_lines, self.L_
+        ctx, op, d, L = self.ctx, self.ctx_op, self.d_lines, self.L_
         rec = (lambda i: ev[i].record(stream)) if ev is not None else (lambda i: None)
         rec(0)
-        ctx.set_lines(d["nu"], d["alpha_line"], mass=d["mass"], atomic_number=d["atomic_number"], ion_number=d["ion_number"],
-                      ionization_energy=d["ionization_energy"], level_energy_upper=d["level_energy_upper"],
-                      level_energy_lower=d["level_energy_lower"], A_ul=d["A_ul"])
-        ctx.calc_broadening(self.flags)                       # K1
+        op.set_lines(d["nu"], d["alpha_line"], mass=d["mass"], atomic_number=d["atomic_number"], ion_number=d["ion_number"],
+                     ionization_energy=d["ionization_energy"], level_energy_upper=d["level_energy_upper"],
+                     level_energy_lower=d["level_energy_lower"], A_ul=d["A_ul"])
+        op.calc_broadening(self.flags)                       # K1
         rec(1)
-        ctx.calc_alpha_line(0)                                # K2 (+ window/record preparation)
+        op.calc_alpha_line(0)                                # K2 (+ window/record preparation)
         rec(2)
-        ctx.calc_continuum(bf_nu_cut=self.bf_cut, bf_prefix=self.bf_prefix, ff_coef=self.ff_coef, rayleigh=self.rayleigh,
-                           electron=self.electron, tables=self.tables, store_mask=0)  # K3
+        op.calc_continuum(bf_nu_cut=self.bf_cut, bf_prefix=self.bf_prefix, ff_coef=self.ff_coef, rayleigh=self.rayleigh,
+                          electron=self.electron, tables=self.tables, store_mask=0)  # K3
         rec(3)
-        ctx.raytrace(self.ds, self.srf0.I_nus_weights, inward_rays=self.inward)  # K4
+        if self.depth_mode:                                  # (D/R, N) depth rows -> (D, N/R) pixel range, NCCL all-to-all
+            op.get(L.BUF_TOTAL, out=self.t_local)
+            ctx.set_total(exchange_depth_to_nu(self.t_local, self.D, self.N, bounds=self.bounds))
         rec(4)
+        ctx.raytrace(self.ds, self.srf0.I_nus_weights, inward_rays=self.inward)  # K4
+        rec(5)
         ctx.get_row(L.BUF_F_NU, -1, out=self.d_spec)
         if self.world > 1 and gather:
             allgather_spectrum(self.d_spec, (self.p0, self.p1), self.N, bounds=self.bounds)
-        rec(5)
+        rec(6)
 
 
 def run_b200_arm(args):
@@ -299,10 +338,11 @@ def run_b200_arm(args):
         return run_grid_sweep(args, ctx, stream, rank, world, local_rank, barrier, max_over_ranks)
 
     w, cfg, desc = build_workload(args)
-    hp = HotPath(ctx, w, cfg, rank, world, torch)
+    hp = HotPath(ctx, w, cfg, rank, world, torch, partition=args.partition, stream=stream)
     model, plasma, nus, N, D, W, p0, p1, bounds = hp.model, hp.plasma, hp.nus, hp.N, hp.D, hp.W, hp.p0, hp.p1, hp.bounds
+    op = hp.ctx_op   # context of the opacity stages (== ctx unless the multi-GPU run shards them by depth)
     line_cfg = cfg.opacity.line
-    ev = [torch.cuda.Event(enable_timing=True) for _ in range(6)]
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(hp.N_EVENTS)]
 
     sampler = ClockSampler(local_rank)  # sampled from the warm-up on: the timed region itself may last < 1 s
     sampler.start()
@@ -310,7 +350,7 @@ def run_b200_arm(args):
         hp.step()
     barrier()
     launches0 = ctx.launch_count()
-    phase = np.zeros(5)
+    phase = np.zeros(hp.N_EVENTS - 1)
     kern = {}
     t_start = torch.cuda.Event(enable_timing=True)
     t_end = torch.cuda.Event(enable_timing=True)
@@ -318,10 +358,13 @@ def run_b200_arm(args):
     t_start.record(stream)
     for _ in range(args.steps):
         hp.step(ev, stream)
-        ev[5].synchronize()
+        ev[-1].synchronize()
         ctx._keep.clear()
-        phase += [ev[i].elapsed_time(ev[i + 1]) for i in range(5)]
-        for k, v in ctx.phase_times().items():  # per-kernel device times of this step (events inside the library)
+        op._keep.clear()
+        phase += [ev[i].elapsed_time(ev[i + 1]) for i in range(hp.N_EVENTS - 1)]
+        pt = dict(op.phase_times())  # per-kernel device times of this step (events inside the library)
+        pt["K4_raytrace"] = ctx.phase_times()["K4_raytrace"]
+        for k, v in pt.items():
             kern[k] = kern.get(k, 0.0) + max(v, 0.0)
     t_end.record(stream)
     barrier()
@@ -333,11 +376,11 @@ def run_b200_arm(args):
     value = N / (ms_per_step * 1e-3)
 
     # ---- K2 statistics (untimed): executed work of the default mode + reference-equivalent evaluation counts
-    ctx.set_line_stats(True)
-    ctx.calc_alpha_line(0)
-    stats = ctx.line_stats()
-    ex = ctx.line_stats_ex()
-    ctx.set_line_stats(False)
+    op.set_line_stats(True)
+    op.calc_alpha_line(0)
+    stats = op.line_stats()
+    ex = op.line_stats_ex()
+    op.set_line_stats(False)
     reg = torch.tensor(stats["region_evals"].astype(np.float64), device="cuda")
     if world > 1:
         dist.all_reduce(reg)
@@ -345,13 +388,13 @@ def run_b200_arm(args):
 
     def time_k2(reps):
         """Device time of the Voigt accumulation alone (k_far_coeffs + k_lines; records already prepared)."""
-        ctx.calc_alpha_line(0)
+        op.calc_alpha_line(0)
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ms = []
         for _ in range(reps):
             e0.record(stream)
-            ctx.lib.sd_calc_alpha_line(ctx.h, 0)
+            op.lib.sd_calc_alpha_line(op.h, 0)
             e1.record(stream)
             e1.synchronize()
             ms.append(e0.elapsed_time(e1))
@@ -364,9 +407,9 @@ def run_b200_arm(args):
     # directly, like the reference's loop ("roofline_direct").
     direct = None
     if not args.no_direct:
-        a_far = torch.empty((D, W), dtype=torch.float64, device="cuda")
-        ctx.get(L.BUF_ALPHA_LINE, out=a_far)
-        ctx.set_farfield(False)
+        a_far = torch.empty((len(hp.didx), op.W), dtype=torch.float64, device="cuda")
+        op.get(L.BUF_ALPHA_LINE, out=a_far)
+        op.set_farfield(False)
         hp.step()
         barrier()
         n_direct = max(1, args.steps // 3)
@@ -378,12 +421,12 @@ def run_b200_arm(args):
         barrier()
         ms_direct = max_over_ranks(td0.elapsed_time(td1) / n_direct)
         k2_kernel_ms = time_k2(max(1, n_direct))
-        a_dir = torch.empty((D, W), dtype=torch.float64, device="cuda")
-        ctx.get(L.BUF_ALPHA_LINE, out=a_dir)
+        a_dir = torch.empty_like(a_far)
+        op.get(L.BUF_ALPHA_LINE, out=a_dir)
         torch.cuda.synchronize()
-        far_dev = float(((a_far - a_dir).abs() / a_dir.abs().clamp_min(1e-300)).max().item())
+        far_dev = max_over_ranks(float(((a_far - a_dir).abs() / a_dir.abs().clamp_min(1e-300)).max().item()))
         del a_far, a_dir
-        ctx.set_farfield(True)
+        op.set_farfield(True)
         flops_direct = float((stats["region_evals"] * FLOPS_PER_EVAL).sum())  # this rank's launch
         direct = dict(ms_per_step=ms_direct, k2_ms=k2_kernel_ms, far_dev=far_dev,
                       tflops=flops_direct / (k2_kernel_ms * 1e-3) / 1e12)
@@ -434,6 +477,8 @@ def run_b200_arm(args):
     # (sd_calc_alpha_line_vald fills the (L, D) table in HBM; without producer inputs the table itself travels, striped
     # over the ranks and exchanged over NVLink: distributed.upload_rows_striped)
     r0, r1, _ = stripe_rows(len(sel), rank, world)
+    if hp.depth_mode and sel.strength is None:
+        r0, r1 = 0, -(-len(sel) * len(hp.didx) // D)  # this rank's depth columns of the (L, D) table
     h2d = int(pinned_nus.numel() * 8 + sum(np.asarray(getattr(sel, k)).nbytes for k in
               ("nu", "mass", "atomic_number", "ion_number", "ionization_energy", "level_energy_upper",
                "level_energy_lower", "A_ul")) + 3 * D * 8 +
@@ -442,7 +487,7 @@ def run_b200_arm(args):
 
     def api_step():
         srf = RadiationField(nus_host, None, model, cfg.no_of_thetas, device_context=ctx, shard=(p0, p1) if world > 1 else None,
-                             shard_bounds=bounds)
+                             shard_bounds=bounds, depth_shard=(rank, world) if hp.depth_mode else None)
         ob.calc_alphas(plasma, model, srf, cfg.opacity, store_components=False)
         raytrace(model, srf)
         ctx.get_row(L.BUF_F_NU, -1, out=h_spec)
@@ -486,7 +531,7 @@ def run_b200_arm(args):
             if (t.get("N"), t.get("D"), t.get("L")) == (N, D, len(sel)):
                 traffic = t.get("bytes_per_launch", {})
         # executed work of this rank's launches in the default (far-field) mode
-        flops_lines = float((ex["direct_region_evals"] * FLOPS_PER_EVAL).sum()) + FLOPS_HORNER * 3.0 * cells
+        flops_lines = float((ex["direct_region_evals"] * FLOPS_PER_EVAL).sum()) + FLOPS_HORNER * 3.0 * len(hp.didx) * op.W
         flops_far = FLOPS_FAR_SETUP * ex["far_expansions"] + FLOPS_FAR_TERM * ex["far_terms"]
         t_lines, t_far = kern.get("K2_lines", 0.0), kern.get("K2_far_coeffs", 0.0)
         tf_lines = flops_lines / max(t_lines * 1e-3, 1e-12) / 1e12
@@ -496,7 +541,7 @@ def run_b200_arm(args):
             "metric": METRIC, "value": value, "unit": "nu-points/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": config_block(desc, len(sel), D, cells, world, bounds),
+            "config": config_block(desc, len(sel), D, cells, world, bounds, args.partition),
             "roofline": {"kernel": "k_lines, default (far-field) mode: the dominant kernel of the timed step", "bound": "fp64",
                          "achieved": tf_lines, "peak": dfma_peak, "unit": "TFLOP/s", "frac": tf_lines / dfma_peak,
                          "traffic": traffic.get("k_lines"),
@@ -520,8 +565,7 @@ def run_b200_arm(args):
                                  "tile on a 3-level tile hierarchy (k_far_coeffs) instead of per pixel",
                          "k2_ms": k2_far_ms, "reference_equivalent_region_evals_all_ranks": region_evals.tolist(),
                          "far_replaced_evals": ex["far_replaced_evals"]},
-            "phase_ms": {"K1_broadening": phase[0], "K2_prepare_and_lines": phase[1], "K3_continuum": phase[2],
-                         "K4_raytrace": phase[3], "spectrum_gather": phase[4]},
+            "phase_ms": {name: phase[i] for i, name in enumerate(hp.PHASES)},
             "kernel_ms": kern,
             "parity": parity,
             "cpu_baseline": cpu,

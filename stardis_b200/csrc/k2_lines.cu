@@ -43,6 +43,7 @@ constexpr int THREADS = 256;
 constexpr int WARPS = THREADS / 32;
 constexpr int FAR_CH = 1024;                // candidates per cooperative scan chunk of k_far_coeffs
 struct __align__(16) FarRec { double nu, dw, y, K; };  // = the first 32 bytes of LineRec
+static_assert((SD_FAR_K + 1) % 3 == 0, "the series length is tested every third term");
 static_assert(WARPS == (1 << SD_FAR_SHIFT), "k_far_coeffs maps the warps of a CTA to the children of a tile");
 constexpr size_t FAR_SMEM = (size_t)(FAR_CH + WARPS * 64) * sizeof(FarRec) + FAR_CH;
 
@@ -291,10 +292,10 @@ __global__ void __launch_bounds__(THREADS) k_far_coeffs(LineArgs a, int lev, int
             const double q1 = sdm::rcp_fast(fma(D1, D1, g * g)), q2 = sdm::rcp_fast(fma(D2, D2, g * g));
             const double i1 = -h * q1, i2 = -h * q2;
             w1r = D1 * i1; w1i = g * i1; w2r = D2 * i2; w2i = g * i2;
-            // terms needed: (n + 1) rho^n <= 22 * 4^-21 (the bound of the full series at the far criterion rho = 1/4)
-            // <=>  n >= ~42 / log2(1 / rho);  rho^2 = h^2 max(q1, q2)
+            // terms needed: (n + 1) rho^n <= (K1 + 1) rho_far^K1 (the bound of the full series at the far criterion)
+            // <=>  n >= ~K1 log2(1 / rho_far) / log2(1 / rho);  rho^2 = h^2 max(q1, q2)
             const float lg = -0.5f * __log2f((float)(h * h * fmax(q1, q2)));
-            nterms = (lg > 2.0f) ? min(K1, (int)(__fdividef(42.0f, lg) + 1.02f)) : K1;
+            nterms = (lg > SD_FAR_LOG2_RHO_INV) ? min(K1, (int)(__fdividef((float)K1 * SD_FAR_LOG2_RHO_INV, lg) + 1.02f)) : K1;
             n_far++;
         }
         // queue neighbours are neighbours in frequency, at similar distances from the tile: warp-uniform series length

@@ -35,8 +35,13 @@ constexpr int SD_NCLS = 8;          // half-width classes
 constexpr int SD_CLS0_HW = 64;      // class 0: hw <= 64; class k: hw <= 64 * 4^k; last class: everything wider
 constexpr int SD_MAX_SOURCES = 4 + SD_MAX_TABLES;
 // far-field (Taylor) expansion of region-I wings per pixel tile: order and convergence radius
-constexpr int SD_FAR_K = 20;            // polynomial degree (21 coefficients)
-constexpr double SD_FAR_RHO_INV = 4.0;  // a (line, depth) pair is expanded only if |nu_c - pole| >= 4 h
+// Convergence radius 1/3 with 27 coefficients has the truncation error of the round-1 choice (1/4, 21 coefficients:
+// worst case of one expansion ~5e-12, tests/test_farfield_model.py) but admits the tiles at index distance 2 for every
+// pair: the directly evaluated near field is 3 tiles instead of 5 on average and a pair is expanded at ~21 instead of
+// ~42 tiles per level.
+constexpr int SD_FAR_K = 26;            // polynomial degree (27 coefficients)
+constexpr double SD_FAR_RHO_INV = 3.0;  // a (line, depth) pair is expanded only if |nu_c - pole| >= 3 h
+constexpr float SD_FAR_LOG2_RHO_INV = 1.5849625f;  // log2(SD_FAR_RHO_INV)
 constexpr int SD_FAR_LEVELS = 3;        // tile hierarchy: level k tiles hold 256 * P * 8^k pixels
 constexpr int SD_FAR_SHIFT = 3;         // log2 of the branching factor
 static_assert(SD_FAR_LEVELS == 3, "PairWin::near holds three levels");

@@ -157,3 +157,155 @@ def upload_rows_striped(host_array, device):
     full = torch.empty((rows * world, d), dtype=torch.float64, device=device)
     dist.all_gather_into_tensor(full, local)
     return full[:n]
+
+
+# ------------------------------------------------------------------------------------------------- depth sharding
+# Under nu sharding every rank repeats the per-(line, depth) preparation of the line kernel for the whole line list
+# (windows, near-tile intervals, class lists, edge sort: independent of the rank's pixel range for the ~40 % of the pairs
+# whose window spans the whole grid), which caps the 8-GPU efficiency near 0.5.  All opacity stages (K1, preparation, K2,
+# K3) are independent per DEPTH POINT, so the multi-GPU driver shards those by depth instead -- rank r evaluates depth
+# points r, r + R, r + 2R, ... on the WHOLE grid (interleaved: neighbouring depths cost the same, so the ranks are
+# balanced) -- and the formal solution, which couples all depths of one frequency, by nu.  Between the two sits the only
+# real exchange step of the path: one all-to-all of the total opacity (every rank sends (D/R, N/R) blocks, 34 MB per
+# rank at the flagship size), NCCL over NVLink.  Every depth row is computed exactly as in a single-GPU run, so the
+# result is bitwise identical for every R.
+
+def depth_indices(n_depth, rank, world_size):
+    """Depth points of rank ``rank``: rank, rank + world, ... (interleaved)."""
+    return np.arange(int(rank), int(n_depth), int(world_size))
+
+
+def exchange_depth_to_nu(local, n_depth, n_total, bounds=None):
+    """All-to-all between the two decompositions: ``local`` (D_r, N) holds this rank's depth rows (``depth_indices``) over
+    the whole grid; returns (D, W_r), all depth rows over this rank's pixel range ``bounds[rank]`` (default: equal
+    widths).  torch tensors (CUDA -> NCCL ``all_to_all_single``; CPU/gloo -> point-to-point sends, used by the tests);
+    returns a tensor on the same device.  Without a process group the input is returned unchanged."""
+    import torch
+
+    dist, rank, world = dist_info()
+    if dist is None or world == 1:
+        return local
+    bounds = _checked_bounds(bounds, n_total, world)
+    d_pad = -(-int(n_depth) // world)
+    w_pad = max(b - a for a, b in bounds)
+    send = torch.zeros((world, d_pad, w_pad), dtype=torch.float64, device=local.device)
+    for j, (a, b) in enumerate(bounds):
+        send[j, : local.shape[0], : b - a] = local[:, a:b]
+    recv = torch.empty_like(send)
+    if local.is_cuda:
+        dist.all_to_all_single(recv, send)
+    else:  # gloo has no all-to-all: pairwise exchange
+        reqs = []
+        for j in range(world):
+            if j == rank:
+                recv[j] = send[j]
+            else:
+                reqs.append(dist.isend(send[j].contiguous(), j))
+                reqs.append(dist.irecv(recv[j], j))
+        for r in reqs:
+            r.wait()
+    a, b = bounds[rank]
+    out = torch.empty((int(n_depth), b - a), dtype=torch.float64, device=local.device)
+    for s in range(world):
+        rows = depth_indices(n_depth, s, world)
+        out[s::world] = recv[s, : len(rows), : b - a]
+    return out
+
+
+def allgather_depth_columns(local, n_depth):
+    """(L, D_r) columns of this rank's depth points -> (L, D) on every rank (gammas / Doppler widths when the caller asked
+    for the whole radiation field)."""
+    import torch
+
+    dist, rank, world = dist_info()
+    if dist is None or world == 1:
+        return local
+    d_pad = -(-int(n_depth) // world)
+    padded = torch.zeros((local.shape[0], d_pad), dtype=torch.float64, device=local.device)
+    padded[:, : local.shape[1]] = local
+    pieces = [torch.empty_like(padded) for _ in range(world)]
+    dist.all_gather(pieces, padded)
+    out = torch.empty((local.shape[0], int(n_depth)), dtype=torch.float64, device=local.device)
+    for s in range(world):
+        rows = depth_indices(n_depth, s, world)
+        out[:, s::world] = pieces[s][:, : len(rows)]
+    return out
+
+
+class DepthSlicedModel:
+    """View of a stellar model restricted to some depth points (what the opacity stages read: temperatures, composition,
+    microturbulence; the geometry belongs to the formal solution and is not sliced)."""
+
+    def __init__(self, stellar_model, idx):
+        self._m = stellar_model
+        self.temperatures = stellar_model.temperatures[idx]
+        self.no_of_depth_points = len(idx)
+
+    def __getattr__(self, name):
+        return getattr(self._m, name)
+
+
+class DepthSlicedPlasma:
+    """View of a plasma restricted to some depth points: every per-depth table the opacity stages read is
+    sliced, everything else passes through.  Cached per plasma and depth selection (the columnar line table of the view
+    is built once)."""
+
+    _SERIES = ("electron_densities", "h_minus_density", "h2_density", "h2_plus_density")
+    _FRAMES = ("ion_number_density", "level_number_density", "partition_function")
+    _WITH_NU = ("alpha_line", "alpha_line_from_linelist", "molecule_alpha_line_from_linelist")
+
+    def __init__(self, stellar_plasma, idx):
+        self._p = stellar_plasma
+        self._idx = np.asarray(idx)
+        self._cache = {}
+
+    @classmethod
+    def of(cls, stellar_plasma, idx):
+        key = tuple(int(i) for i in idx)
+        try:
+            views = stellar_plasma.__dict__.setdefault("_stardis_b200_depth_views", {})
+        except AttributeError:
+            return cls(stellar_plasma, idx)
+        if key not in views:
+            views[key] = cls(stellar_plasma, idx)
+        return views[key]
+
+    def __getattr__(self, name):
+        if name.startswith("_"):
+            raise AttributeError(name)
+        cache = self.__dict__["_cache"]
+        if name in cache:
+            return cache[name]
+        v = getattr(self._p, name)
+        idx = self._idx
+        if v is None:
+            out = None
+        elif name in self._SERIES:
+            out = v.iloc[idx]
+        elif name in self._FRAMES:
+            out = v.iloc[:, idx]
+        elif name in self._WITH_NU:  # (L, D) + a trailing "nu" column
+            cols = list(v.columns)
+            out = v[[cols[i] for i in idx] + ["nu"]]
+        elif name == "line_table":
+            out = _slice_line_table(v, idx)
+        else:
+            out = v
+        cache[name] = out
+        return out
+
+
+def _slice_line_table(table, idx):
+    """ColumnarLines with the depth columns ``idx`` of alpha_line and of the line-strength producer tables."""
+    from .plasma.columnar import ColumnarLines, LineStrength
+
+    if table is None:
+        return None
+    strength = table.strength
+    if strength is not None:
+        strength = LineStrength(strength.kind, strength.per_line,
+                                {k: (np.ascontiguousarray(v[:, idx]) if np.ndim(v) == 2 else v) for k, v in strength.tables.items()})
+    cols = {k: getattr(table, k) for k in ColumnarLines._data_fields()}
+    if cols["alpha_line"] is not None:
+        cols["alpha_line"] = np.ascontiguousarray(cols["alpha_line"][:, idx])
+    return ColumnarLines(**cols, strength=strength)

@@ -25,12 +25,14 @@ class RadiationField:
 
     B200 additions: ``device_context`` (None = the process-wide context of cuda:0) and ``shard`` = (p0, p1), the
     pixel range of the global grid this rank evaluates (None = everything); ``shard_bounds`` = the partition of all
-    ranks when it is not the equal-width one (``distributed.line_balanced_bounds``)."""
+    ranks when it is not the equal-width one (``distributed.line_balanced_bounds``); ``depth_shard`` = (rank, world):
+    the opacity stages of this rank cover the depth points rank, rank + world, ... of the whole grid and are
+    redistributed to the pixel ranges by one all-to-all before the formal solution (``stardis_b200.distributed``)."""
 
     hdf_properties = ["frequencies", "opacities", "F_nu"]
 
     def __init__(self, frequencies, source_function, stellar_model, num_of_thetas, track_individual_intensities=False,
-                 device_context=None, shard=None, shard_bounds=None):
+                 device_context=None, shard=None, shard_bounds=None, depth_shard=None):
         self.frequencies = frequencies
         self.source_function = source_function
         self.opacities = Opacities(frequencies, stellar_model)
@@ -46,6 +48,7 @@ class RadiationField:
         self.device_context = device_context
         self.shard = shard
         self.shard_bounds = shard_bounds
+        self.depth_shard = depth_shard
         self.token = next(_tokens)
 
     @property
@@ -74,17 +77,24 @@ class RadiationField:
 def create_stellar_radiation_field(tracing_nus, stellar_model, stellar_plasma, config, device_context=None, shard=None):
     """radiation_field/base.py:71-117: RadiationField -> calc_alphas -> raytrace.
 
-    ``shard="auto"``: inside an initialised torch.distributed job every rank takes its range of the cost-balanced
-    partition (``distributed.line_balanced_bounds`` over the lines the run uses)."""
-    shard_bounds = None
+    Inside an initialised torch.distributed job, ``shard="auto"`` gives every rank the depth points rank, rank + world,
+    ... for the opacity stages and an equal-width pixel range for the formal solution (one all-to-all in between, see
+    ``stardis_b200.distributed``); ``shard="auto-nu"`` shards everything by frequency instead (cost-balanced ranges,
+    ``distributed.line_balanced_bounds``; no exchange, but the per-(line, depth) preparation is repeated on every rank)."""
+    shard_bounds, depth_shard = None, None
     if isinstance(shard, str):
-        if shard != "auto":
-            raise ValueError("shard must be None, (p0, p1) or 'auto'")
-        from ..distributed import dist_info, line_balanced_bounds
+        if shard not in ("auto", "auto-nu"):
+            raise ValueError("shard must be None, (p0, p1), 'auto' or 'auto-nu'")
+        from ..distributed import all_shards, dist_info, line_balanced_bounds
 
+        mode = shard
         _, rank, world = dist_info()
         shard = None
-        if world > 1:
+        if world > 1 and mode == "auto":
+            shard_bounds = all_shards(len(tracing_nus), world)
+            shard = shard_bounds[rank]
+            depth_shard = (rank, world)
+        elif world > 1:
             from .opacities.opacities_solvers.base import select_lines
 
             line_nus = ([] if config.opacity.line.disable
@@ -94,7 +104,7 @@ def create_stellar_radiation_field(tracing_nus, stellar_model, stellar_plasma, c
     stellar_radiation_field = RadiationField(
         tracing_nus, blackbody_flux_at_nu, stellar_model, config.no_of_thetas,
         track_individual_intensities=config.result_options.return_radiation_field,
-        device_context=device_context, shard=shard, shard_bounds=shard_bounds)
+        device_context=device_context, shard=shard, shard_bounds=shard_bounds, depth_shard=depth_shard)
     logger.info("Calculating alphas")
     calc_alphas(stellar_plasma=stellar_plasma, stellar_model=stellar_model,
                 stellar_radiation_field=stellar_radiation_field, opacity_config=config.opacity,

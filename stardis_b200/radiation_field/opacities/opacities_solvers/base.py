@@ -316,14 +316,32 @@ def _calc_alan_entries(delta_nus, doppler_widths_at_depth_point, gammas_at_depth
 
 
 # ------------------------------------------------------------------------------------------ driver
+def opacity_context_of(ctx):
+    """Second context on the same device for the depth-sharded opacity stages of a multi-GPU run (the formal solution
+    keeps ``ctx``, which holds all depth points of this rank's pixel range)."""
+    from ....device import DeviceContext
+
+    if getattr(ctx, "_opacity_ctx", None) is None:
+        ctx._opacity_ctx = DeviceContext(ctx.device)
+    return ctx._opacity_ctx
+
+
 def calc_alphas(stellar_plasma, stellar_model, stellar_radiation_field, opacity_config, store_components=True):
     """Calculates every opacity term, stores them in the radiation field and returns the total (base.py:630-740).
 
     One pass on the device: K1 -> K2 (atomic, then molecular lines) -> K3 (all continuum terms + total).  The
     entries of ``opacities_dict`` keep the reference's keys and order; they are ``DeviceArray`` objects that turn
     into numpy arrays when touched.  With ``store_components=False`` the per-term arrays are not kept in HBM (only the
-    total is); touching one then recomputes that single term."""
+    total is); touching one then recomputes that single term.
+
+    Multi-GPU: ``stellar_radiation_field.shard`` = (p0, p1) alone evaluates that pixel range of the global grid (nu
+    sharding, no exchange); with ``depth_shard`` = (rank, world) as well, the opacity stages run for the depth points
+    rank, rank + world, ... on the WHOLE grid and one all-to-all redistributes the result to the pixel ranges (see
+    ``stardis_b200.distributed``)."""
     srf = stellar_radiation_field
+    depth_shard = getattr(srf, "depth_shard", None)
+    if depth_shard is not None and int(depth_shard[1]) > 1:
+        return _calc_alphas_depth_sharded(stellar_plasma, stellar_model, srf, opacity_config, store_components)
     ctx = _ctx_of(srf)
     ctx.evict()
     nus_q = srf.frequencies
@@ -332,7 +350,6 @@ def calc_alphas(stellar_plasma, stellar_model, stellar_radiation_field, opacity_
     D = stellar_model.no_of_depth_points
     p0, p1 = _shard_of(srf, N)
     W = p1 - p0
-    od = srf.opacities.opacities_dict
 
     if (nus > RAYLEIGH_UPPER_BOUND_HZ).any():
         raise NotImplementedError(
@@ -340,73 +357,178 @@ def calc_alphas(stellar_plasma, stellar_model, stellar_radiation_field, opacity_
             "zeroing (base.py:98-99), after which its own line and formal-solver steps are ill-defined; not supported")
     set_device_atmosphere(ctx, stellar_model, stellar_plasma)
     ctx.set_grid(nus, p0, p1)
+    n_lines, mol = _device_opacity_pass(ctx, stellar_plasma, stellar_model, nus_q, opacity_config, store_components,
+                                        collective=getattr(srf, "shard", None) is not None)
+    ctx.owner = getattr(srf, "token", None)
 
-    # ---- continuum descriptors (host, O(D)); evaluation order and dict keys follow base.py:655-700
-    tables, table_names = file_tables(stellar_plasma, stellar_model, opacity_config.file)
+    def shard_array(which):
+        return ctx.track(DeviceArray(ctx, which, (D, W)))
+
+    def line_table_array(which):
+        return ctx.track(DeviceArray(ctx, which, (n_lines, D)))
+
+    _publish(srf, stellar_plasma, stellar_model, nus_q, opacity_config, store_components, n_lines, mol, (D, W), (p0, p1),
+             shard_array, line_table_array)
+    # ---- total (Opacities.calc_total_alphas accumulates into the existing array, opacities/base.py:24-28)
+    previous = srf.opacities._total
+    total = shard_array(L.BUF_TOTAL)
+    if previous is not None and np.any(np.asarray(previous) != 0):
+        total = np.asarray(previous) + total.numpy()
+        ctx.set_total(total)
+    srf.opacities.total_alphas = total
+    return total
+
+
+def _device_opacity_pass(ctx, stellar_plasma, stellar_model, nus_q, opacity_config, store_components, collective=False):
+    """K1 + K2 (atomic, molecular) + K3 on a prepared context (atmosphere and grid set).  Continuum descriptors are
+    assembled on the host (O(D)); evaluation order follows base.py:655-736.  Returns (n_lines or None, molecular
+    (gammas, doppler_widths) or None)."""
+    tables, _ = file_tables(stellar_plasma, stellar_model, opacity_config.file)
     bf_cut, bf_prefix = bf_descriptor(stellar_plasma, opacity_config.bf)
     ff_coef = ff_descriptor(stellar_plasma, stellar_model, opacity_config.ff)
     rayleigh = rayleigh_descriptor(stellar_plasma, stellar_model, opacity_config.rayleigh)
     electron = None if opacity_config.disable_electron_scattering else electron_descriptor(stellar_plasma)
-    def shard_array(which):
-        return ctx.track(DeviceArray(ctx, which, (D, W)))
-
-    # ---- lines (K1 + K2), base.py:702-736
     line_cfg = opacity_config.line
-    n_lines = None
+    n_lines, mol = None, None
     if not line_cfg.disable:
-        # sharded run (every rank of the job is here with the same line table): stripe the big upload
-        n_lines = _device_line_opacity(ctx, stellar_plasma, stellar_model, nus_q, line_cfg,
-                                       collective=getattr(srf, "shard", None) is not None)
-        mol = None
+        # nu-sharded run (every rank of the job is here with the same line table): stripe the big upload
+        n_lines = _device_line_opacity(ctx, stellar_plasma, stellar_model, nus_q, line_cfg, collective=collective)
         if line_cfg.include_molecules:
             mol = _device_molecular_opacity(ctx, stellar_plasma, stellar_model, nus_q, line_cfg)
-
-    # ---- K3: continuum terms + total in one pass
-    store_mask = 0xFFFF if store_components else 0
     ctx.calc_continuum(bf_nu_cut=bf_cut, bf_prefix=bf_prefix, ff_coef=ff_coef, rayleigh=rayleigh, electron=electron,
-                       tables=tables, store_mask=store_mask)
-    ctx.owner = getattr(srf, "token", None)
+                       tables=tables, store_mask=0xFFFF if store_components else 0)
+    return n_lines, mol
+
+
+def _publish(srf, stellar_plasma, stellar_model, nus_q, opacity_config, store_components, n_lines, mol, shape, pixel_range,
+             shard_array, line_table_array):
+    """Fill ``opacities_dict`` with the reference's keys in the reference's order (base.py:655-736).  ``shard_array(which)``
+    / ``line_table_array(which)`` wrap a stored device result; terms that were not stored are recomputed when touched."""
+    od = srf.opacities.opacities_dict
+    D, W = shape
+    p0, p1 = pixel_range
+    line_cfg = opacity_config.line
+    have_bf = len(opacity_config.bf) > 0
+    have_ff = len(opacity_config.ff) > 0
 
     def term(source_index, recompute):
         if store_components:
             return shard_array(L.BUF_SOURCE0 + source_index)
         return DeviceArray(None, None, (D, W), fetch=lambda: recompute()[:, p0:p1])
 
-    for k, name in enumerate(table_names):
-        src, fpath = list(opacity_config.file.items())[k]
-        od[name] = term(L.SRC_TABLE0 + k, lambda src=src, fpath=fpath: calc_alpha_file(stellar_plasma, stellar_model, nus_q, src, fpath))
+    for k, (src, fpath) in enumerate(list(opacity_config.file.items())):
+        od[f"alpha_file_{src}"] = term(L.SRC_TABLE0 + k, lambda src=src, fpath=fpath: calc_alpha_file(
+            stellar_plasma, stellar_model, nus_q, src, fpath))
     od["alpha_bf"] = (term(L.SRC_BF, lambda: calc_alpha_bf(stellar_plasma, stellar_model, nus_q, opacity_config.bf))
-                      if bf_cut is not None else _zeros_lazy((D, W)))
+                      if have_bf else _zeros_lazy((D, W)))
     od["alpha_ff"] = (term(L.SRC_FF, lambda: calc_alpha_ff(stellar_plasma, stellar_model, nus_q, opacity_config.ff))
-                      if ff_coef is not None else _zeros_lazy((D, W)))
+                      if have_ff else _zeros_lazy((D, W)))
     od["alpha_rayleigh"] = term(L.SRC_RAYLEIGH, lambda: calc_alpha_rayleigh(stellar_plasma, stellar_model, nus_q, opacity_config.rayleigh))
-    od["alpha_electron"] = (0 if electron is None else
+    od["alpha_electron"] = (0 if opacity_config.disable_electron_scattering else
                             term(L.SRC_ELECTRON, lambda: calc_alpha_electron(stellar_plasma, stellar_model, nus_q)))
     if line_cfg.disable:
         od["alpha_line_at_nu"] = 0
         od["alpha_line_at_nu_gammas"] = 0
         od["alpha_line_at_nu_doppler_widths"] = 0
-    else:
-        od["alpha_line_at_nu"] = shard_array(L.BUF_ALPHA_LINE)
-        if n_lines:
-            if line_cfg.include_molecules:
-                # the molecular pass re-used the line-table buffers: atomic gammas are recomputed when asked for
-                def _atomic(which):
-                    return lambda: calc_alpha_line_at_nu(stellar_plasma, stellar_model, nus_q, line_cfg)[which]
-                od["alpha_line_at_nu_gammas"] = DeviceArray(None, None, (n_lines, D), fetch=_atomic(1))
-                od["alpha_line_at_nu_doppler_widths"] = DeviceArray(None, None, (n_lines, D), fetch=_atomic(2))
-            else:
-                od["alpha_line_at_nu_gammas"] = ctx.track(DeviceArray(ctx, L.BUF_GAMMAS, (n_lines, D)))
-                od["alpha_line_at_nu_doppler_widths"] = ctx.track(DeviceArray(ctx, L.BUF_DOPPLER, (n_lines, D)))
-        else:
-            od["alpha_line_at_nu_gammas"] = np.zeros((0, D))
-            od["alpha_line_at_nu_doppler_widths"] = np.zeros((0, D))
-        if line_cfg.include_molecules:
-            od["molecule_alpha_line_at_nu"] = shard_array(L.BUF_ALPHA_MOLECULE)
-            od["molecule_alpha_line_at_nu_gammas"] = mol[0]
-            od["molecule_alpha_line_at_nu_doppler_widths"] = mol[1]
+        return
 
-    # ---- total (Opacities.calc_total_alphas accumulates into the existing array, opacities/base.py:24-28)
+    def _atomic(which):  # recomputed on demand (whole grid, this GPU alone)
+        return lambda: calc_alpha_line_at_nu(stellar_plasma, stellar_model, nus_q, line_cfg)[which]
+
+    alpha_line = shard_array(L.BUF_ALPHA_LINE)
+    od["alpha_line_at_nu"] = (alpha_line if alpha_line is not None
+                              else DeviceArray(None, None, (D, W), fetch=lambda: _atomic(0)()[:, p0:p1]))
+    if n_lines:
+        stored = None if line_cfg.include_molecules else (line_table_array(L.BUF_GAMMAS), line_table_array(L.BUF_DOPPLER))
+        if stored is None or stored[0] is None:
+            # the molecular pass re-used the line-table buffers (or the tables live on another decomposition): atomic
+            # gammas are recomputed when asked for
+            od["alpha_line_at_nu_gammas"] = DeviceArray(None, None, (n_lines, D), fetch=_atomic(1))
+            od["alpha_line_at_nu_doppler_widths"] = DeviceArray(None, None, (n_lines, D), fetch=_atomic(2))
+        else:
+            od["alpha_line_at_nu_gammas"], od["alpha_line_at_nu_doppler_widths"] = stored
+    else:
+        od["alpha_line_at_nu_gammas"] = np.zeros((0, D))
+        od["alpha_line_at_nu_doppler_widths"] = np.zeros((0, D))
+    if line_cfg.include_molecules:
+        mol_alpha = shard_array(L.BUF_ALPHA_MOLECULE)
+        od["molecule_alpha_line_at_nu"] = (mol_alpha if mol_alpha is not None else DeviceArray(
+            None, None, (D, W), fetch=lambda: calc_molecular_alpha_line_at_nu(stellar_plasma, stellar_model, nus_q, line_cfg)[0][:, p0:p1]))
+        od["molecule_alpha_line_at_nu_gammas"] = mol[0]
+        od["molecule_alpha_line_at_nu_doppler_widths"] = mol[1]
+
+
+def _calc_alphas_depth_sharded(stellar_plasma, stellar_model, srf, opacity_config, store_components):
+    """calc_alphas of a multi-GPU run: opacity stages for this rank's depth points on the whole grid (second context),
+    all-to-all of the total opacity into this rank's pixel range, where the formal solution finds it.  Per-term arrays
+    are redistributed as well when ``store_components`` is set; otherwise they are recomputed on demand."""
+    import torch
+
+    from ....distributed import (DepthSlicedModel, DepthSlicedPlasma, all_shards, allgather_depth_columns, depth_indices,
+                                 exchange_depth_to_nu)
+
+    rank, world = int(srf.depth_shard[0]), int(srf.depth_shard[1])
+    ctx = _ctx_of(srf)
+    ctx_op = opacity_context_of(ctx)
+    ctx.evict()
+    ctx_op.evict()
+    nus_q = srf.frequencies
+    nus = u.values_of(nus_q)
+    N = nus.shape[0]
+    D = stellar_model.no_of_depth_points
+    if (nus > RAYLEIGH_UPPER_BOUND_HZ).any():
+        raise NotImplementedError("frequency grids reaching above 2.3e15 Hz are not supported (see calc_alphas)")
+    bounds = getattr(srf, "shard_bounds", None) or all_shards(N, world)
+    p0, p1 = _shard_of(srf, N)
+    if (p0, p1) != tuple(bounds[rank]):
+        raise ValueError(f"rank {rank}: pixel range {(p0, p1)} is not entry {rank} of the partition {bounds}")
+    W = p1 - p0
+    idx = depth_indices(D, rank, world)
+    model_r = DepthSlicedModel(stellar_model, idx)
+    plasma_r = DepthSlicedPlasma.of(stellar_plasma, idx)
+    set_device_atmosphere(ctx_op, model_r, plasma_r)
+    ctx_op.set_grid(nus)
+    n_lines, mol = _device_opacity_pass(ctx_op, plasma_r, model_r, nus_q, opacity_config, store_components)
+    dev = torch.device("cuda", ctx.device)
+    stream = torch.cuda.current_stream(dev)
+
+    def to_pixel_range(which):
+        """(D_r, N) result of the opacity context -> (D, W) tensor on this rank's pixel range (collective)."""
+        t = torch.empty((len(idx), N), dtype=torch.float64, device=dev)
+        ctx_op.get(which, out=t)
+        ctx_op.synchronize()            # the copy ran on the context's stream, the collective runs on torch's
+        out = exchange_depth_to_nu(t, D, N, bounds=bounds)
+        stream.synchronize()
+        return out
+
+    total_t = to_pixel_range(L.BUF_TOTAL)
+    set_device_atmosphere(ctx, stellar_model, stellar_plasma)
+    ctx.set_grid(nus, p0, p1)
+    ctx.set_total(total_t)
+    ctx.owner = getattr(srf, "token", None)
+
+    def tensor_array(t):
+        return DeviceArray(None, None, tuple(t.shape), fetch=lambda: t.cpu().numpy())
+
+    def shard_array(which):
+        if which == L.BUF_TOTAL:
+            return ctx.track(DeviceArray(ctx, which, (D, W)))
+        return tensor_array(to_pixel_range(which)) if store_components else None
+
+    def line_table_array(which):
+        if not store_components:
+            return None
+        t = torch.empty((n_lines, len(idx)), dtype=torch.float64, device=dev)
+        ctx_op.get(which, out=t)
+        ctx_op.synchronize()
+        out = allgather_depth_columns(t, D)
+        stream.synchronize()
+        return tensor_array(out)
+
+    if mol is not None and store_components:  # molecular (gammas, Doppler widths): (L, 1) gammas are depth independent
+        mol = (mol[0], allgather_depth_columns(torch.from_numpy(np.ascontiguousarray(mol[1])).to(dev), D).cpu().numpy())
+    _publish(srf, stellar_plasma, stellar_model, nus_q, opacity_config, store_components, n_lines, mol, (D, W), (p0, p1),
+             shard_array, line_table_array)
     previous = srf.opacities._total
     total = shard_array(L.BUF_TOTAL)
     if previous is not None and np.any(np.asarray(previous) != 0):

@@ -4,13 +4,14 @@ and its three-term recurrence for Im(w^k), against the closed form.  Pins the er
 (a few 1e-12 relative, all terms positive) independently of the GPU."""
 import numpy as np
 
-K1 = 21                 # SD_FAR_K + 1
-RHO_INV = 4.0           # SD_FAR_RHO_INV
+K1 = 27                 # SD_FAR_K + 1
+RHO_INV = 3.0           # SD_FAR_RHO_INV
+LOG2_RHO_INV = np.float32(1.5849625)
 
 
 def _terms_needed(rho2):
     lg = -0.5 * np.log2(rho2.astype(np.float32)).astype(np.float32)
-    n = np.where(lg > 2.0, np.minimum(K1, (np.float32(42.0) / lg + np.float32(1.02)).astype(np.int64)), K1)
+    n = np.where(lg > LOG2_RHO_INV, np.minimum(K1, (np.float32(K1) * LOG2_RHO_INV / lg + np.float32(1.02)).astype(np.int64)), K1)
     return ((n + 2) // 3) * 3  # the kernel tests the length every third term
 
 
@@ -73,9 +74,9 @@ def test_series_matches_region_one_profile_at_the_far_criterion_and_beyond():
     assert min(lengths) <= 9 and max(lengths) == K1   # the rule really shortens distant expansions
 
 
-def test_series_length_rule_is_monotone_and_covers_the_full_series_at_one_quarter():
-    rho = np.array([0.25, 0.2, 0.125, 1 / 16, 1 / 32, 1 / 64, 1e-3])
+def test_series_length_rule_is_monotone_and_covers_the_full_series_at_the_far_criterion():
+    rho = np.array([1 / RHO_INV, 0.25, 0.2, 0.125, 1 / 16, 1 / 32, 1 / 64, 1e-3])
     n = _terms_needed(rho * rho)
     assert n[0] == K1 and (np.diff(n) <= 0).all() and n[-1] >= 3
-    # (n + 1) rho^n stays below the bound of the full series at rho = 1/4
-    assert ((n + 1) * rho ** n <= 22 * 4.0 ** -21 * 1.0000001).all()
+    # (n + 1) rho^n stays below the bound of the full series at the far criterion
+    assert ((n + 1) * rho ** n <= (K1 + 1) * RHO_INV ** -float(K1) * 1.0000001).all()
