@@ -570,63 +570,96 @@ __global__ void __launch_bounds__(32 * NW, MINB) k_lines(LineArgs a) {
                 far_eval(w.xl, w.inv_dw, w.b, w.c, w.Kc, w.Kf);
             }
             if (STATS) h0 += (unsigned long long)n_far * nvalid;
-            // ---- mixed entries: window edge inside the span and/or pixels near the line core.  Lanes take CONSECUTIVE
-            // pixels of the in-window part of the span (a 20-pixel window keeps 20 lanes busy in one pass); entries are
-            // processed one after the other and a pass touches distinct pixels, so the shared accumulators need no
-            // atomics and the summation order stays fixed.
+            // ---- mixed entries: a window edge inside the span and/or pixels near the line core.  An entry is handled in
+            // two steps.  (1) CLASSIFY + region I: one sweep over the in-window pixels evaluates the region-I formula where
+            // the pixel is certainly in region I (q > thr; branch-free) and finds, with ballots, the contiguous pixel range
+            // [za, zb) that is not, and inside it the range [ca, cb) with |x| + y <= 5.5 (regions III/IV).  Overlaps longer
+            // than 64 pixels sweep the register slots (no loads), shorter ones put lanes on consecutive pixels (a 20-pixel
+            // window keeps 20 lanes busy).  (2) ZONES: the line core is evaluated region by region with lanes on
+            // consecutive pixels -- first [ca, cb), then the two flanks of [za, zb) as one list -- so that a pass executes
+            // ONE Humlicek branch with (nearly) all lanes instead of two or three branches with a few lanes each.  The
+            // evaluator itself re-classifies every pixel exactly (the ranges are a packing hint, never a decision).
+            // Entries are processed one after the other and a pass touches distinct pixels, so the shared accumulators
+            // need no atomics and the summation order stays fixed.
             for (int m = 0; m < n_mix; m++) {
                 const WEntry &e2 = my[31 - m];
                 const int64_t pa = e2.lo > ws ? e2.lo : ws, pb = e2.hi < we ? e2.hi : we;
                 const double thr = e2.thr, xl = e2.xl, inv_dw = e2.inv_dw, eb = e2.b, ec = e2.c, Kc = e2.Kc, Kf = e2.Kf;
-                if (pb - pa <= 64) {
-                    for (int64_t c0 = pa; c0 < pb; c0 += 32) {
-                        const int64_t pix = c0 + lane;
-                        if (pix < pb) {
-                            const int k = (int)(pix - ws);
-                            const double nu = nus[pix];
-                            double x = fma(nu, inv_dw, -xl);
-                            double q = x * x;
-                            double v;
-                            if (q > thr) {
-                                double den = fma(q, q + eb, ec);
-                                double num = fma(Kf, q, Kc);
-                                v = num * (RCP == 2 ? sdm::rcp_fast2(den) : sdm::rcp_fast(den));
-                            } else {
-                                v = exact_contribution(nu, e2.nu, e2.dw, inv_dw, thr, e2.y, e2.K);
-                            }
-                            s_acc[warp][k] += v;
-                            if (STATS && pix >= p0 && pix < p1) {
+                const double xcut = 5.5 - e2.y;                  // |x| <= xcut  <=>  |x| + y <= 5.5
+                const int oa = (int)(pa - ws), ob = (int)(pb - ws);  // in-window pixels as offsets into the span
+                int za = ob, zb = oa, ca = ob, cb = oa;           // zone bounds (offsets); empty while za >= zb
+                auto note = [&](unsigned mn, unsigned mc, int base) {
+                    if (mn) { za = min(za, base + __ffs(mn) - 1); zb = max(zb, base + 32 - __clz(mn)); }
+                    if (mc) { ca = min(ca, base + __ffs(mc) - 1); cb = max(cb, base + 32 - __clz(mc)); }
+                };
+                if (ob - oa > 64) {
+#pragma unroll
+                    for (int p = 0; p < P; p++) {
+                        const int k = p * 32 + lane;
+                        const bool inwin = (k >= oa) && (k < ob);
+                        if (!__any_sync(0xffffffffu, inwin)) continue;
+                        const double x = fma(nu_i[p], inv_dw, -xl);
+                        const double q = x * x;
+                        const bool fast = inwin && (q > thr);
+                        const bool slow = inwin && !(q > thr);
+                        note(__ballot_sync(0xffffffffu, slow), __ballot_sync(0xffffffffu, slow && (fabs(x) <= xcut)), p * 32);
+                        const double den = fma(q, q + eb, ec);
+                        const double num = fma(Kf, q, Kc);
+                        const double v = num * (RCP == 2 ? sdm::rcp_fast2(den) : sdm::rcp_fast(den));
+                        if (fast) acc[p] += v;
+                        if (STATS && fast && ws + k >= p0 && ws + k < p1) {
+                            int r = sdm::humlicek_region((nu_i[p] - e2.nu) / e2.dw, e2.y);
+                            h0 += (r == 0); h1 += (r == 1); h2 += (r == 2); h3 += (r == 3);
+                        }
+                    }
+                } else {
+                    for (int c0 = oa; c0 < ob; c0 += 32) {
+                        const int k = c0 + lane;
+                        const bool inwin = k < ob;
+                        const double nu = nus[ws + (inwin ? k : ob - 1)];
+                        const double x = fma(nu, inv_dw, -xl);
+                        const double q = x * x;
+                        const bool fast = inwin && (q > thr);
+                        const bool slow = inwin && !(q > thr);
+                        note(__ballot_sync(0xffffffffu, slow), __ballot_sync(0xffffffffu, slow && (fabs(x) <= xcut)), c0);
+                        if (fast) {
+                            const double den = fma(q, q + eb, ec);
+                            const double num = fma(Kf, q, Kc);
+                            s_acc[warp][k] += num * (RCP == 2 ? sdm::rcp_fast2(den) : sdm::rcp_fast(den));
+                            if (STATS && ws + k >= p0 && ws + k < p1) {
                                 int r = sdm::humlicek_region((nu - e2.nu) / e2.dw, e2.y);
                                 h0 += (r == 0); h1 += (r == 1); h2 += (r == 2); h3 += (r == 3);
                             }
                         }
                     }
-                    // the next entry's pass may update the same pixel from another lane: order the shared read-modify-
-                    // writes of the warp (independent thread scheduling gives no lock-step guarantee after the divergent
-                    // exact path; compute-sanitizer racecheck flagged exactly this line)
-                    __syncwarp();
-                } else {
-                    // long overlap (a near-field pair whose core or window edge lies in this span): register slots
-                    const int lo2 = e2.lo, hi2 = e2.hi;
-#pragma unroll
-                    for (int p = 0; p < P; p++) {
-                        int64_t pix = ws + p * 32 + lane;
-                        bool inwin = (pix >= lo2) && (pix < hi2) && (pix < t1);
-                        if (!__any_sync(0xffffffffu, inwin)) continue;
-                        double x = fma(nu_i[p], inv_dw, -xl);
-                        double q = x * x;
-                        bool fast = inwin && (q > thr);
-                        double den = fma(q, q + eb, ec);
-                        double num = fma(Kf, q, Kc);
-                        double v = num * (RCP == 2 ? sdm::rcp_fast2(den) : sdm::rcp_fast(den));
-                        if (fast) acc[p] += v;
-                        if (inwin && !fast) acc[p] += exact_contribution(nu_i[p], e2.nu, e2.dw, inv_dw, thr, e2.y, e2.K);
-                        if (STATS && inwin && pix >= p0 && pix < p1) {
-                            int r = sdm::humlicek_region((nu_i[p] - e2.nu) / e2.dw, e2.y);
-                            h0 += (r == 0); h1 += (r == 1); h2 += (r == 2); h3 += (r == 3);
+                }
+                if (za < zb) {
+                    // zone lists: [ca, cb) first, then [za, ca) + [cb, zb) (one list; the whole zone when there is no core)
+                    const bool has_core = ca < cb;
+                    const int n_core = has_core ? cb - ca : 0;
+                    const int n_left = has_core ? ca - za : zb - za, n_right = has_core ? zb - cb : 0;
+                    for (int pass = 0; pass < 2; pass++) {
+                        const int n_items = pass == 0 ? n_core : n_left + n_right;
+                        for (int i0 = 0; i0 < n_items; i0 += 32) {
+                            const int i = i0 + lane;
+                            if (i < n_items) {
+                                const int k = pass == 0 ? ca + i : (i < n_left ? za + i : cb + (i - n_left));
+                                const double nu = nus[ws + k];
+                                const double x = fma(nu, inv_dw, -xl);
+                                if (!(x * x > thr)) {  // (always true for a monotone grid: the zone is exactly this set)
+                                    s_acc[warp][k] += exact_contribution(nu, e2.nu, e2.dw, inv_dw, thr, e2.y, e2.K);
+                                    if (STATS && ws + k >= p0 && ws + k < p1) {
+                                        int r = sdm::humlicek_region((nu - e2.nu) / e2.dw, e2.y);
+                                        h0 += (r == 0); h1 += (r == 1); h2 += (r == 2); h3 += (r == 3);
+                                    }
+                                }
+                            }
                         }
                     }
                 }
+                // the next entry may update the same pixels from other lanes: order the shared read-modify-writes of the
+                // warp (independent thread scheduling gives no lock-step guarantee after the divergent exact path)
+                __syncwarp();
             }
             __syncwarp();
             }

@@ -383,11 +383,6 @@ def _device_opacity_pass(ctx, stellar_plasma, stellar_model, nus_q, opacity_conf
     """K1 + K2 (atomic, molecular) + K3 on a prepared context (atmosphere and grid set).  Continuum descriptors are
     assembled on the host (O(D)); evaluation order follows base.py:655-736.  Returns (n_lines or None, molecular
     (gammas, doppler_widths) or None)."""
-    tables, _ = file_tables(stellar_plasma, stellar_model, opacity_config.file)
-    bf_cut, bf_prefix = bf_descriptor(stellar_plasma, opacity_config.bf)
-    ff_coef = ff_descriptor(stellar_plasma, stellar_model, opacity_config.ff)
-    rayleigh = rayleigh_descriptor(stellar_plasma, stellar_model, opacity_config.rayleigh)
-    electron = None if opacity_config.disable_electron_scattering else electron_descriptor(stellar_plasma)
     line_cfg = opacity_config.line
     n_lines, mol = None, None
     if not line_cfg.disable:
@@ -395,6 +390,12 @@ def _device_opacity_pass(ctx, stellar_plasma, stellar_model, nus_q, opacity_conf
         n_lines = _device_line_opacity(ctx, stellar_plasma, stellar_model, nus_q, line_cfg, collective=collective)
         if line_cfg.include_molecules:
             mol = _device_molecular_opacity(ctx, stellar_plasma, stellar_model, nus_q, line_cfg)
+    # the line kernels are running now: the host assembles the O(D) continuum descriptors (pandas) in their shadow
+    tables, _ = file_tables(stellar_plasma, stellar_model, opacity_config.file)
+    bf_cut, bf_prefix = bf_descriptor(stellar_plasma, opacity_config.bf)
+    ff_coef = ff_descriptor(stellar_plasma, stellar_model, opacity_config.ff)
+    rayleigh = rayleigh_descriptor(stellar_plasma, stellar_model, opacity_config.rayleigh)
+    electron = None if opacity_config.disable_electron_scattering else electron_descriptor(stellar_plasma)
     ctx.calc_continuum(bf_nu_cut=bf_cut, bf_prefix=bf_prefix, ff_coef=ff_coef, rayleigh=rayleigh, electron=electron,
                        tables=tables, store_mask=0xFFFF if store_components else 0)
     return n_lines, mol
