@@ -32,8 +32,9 @@ def run_stardis(config_fname, tracing_lambdas_or_nus, add_config_dict=None, devi
 
 
 def create_stellar_plasma(stellar_model, adata, config, tracing_nus):
-    """The LTE plasma is tardis' job (stardis/plasma/base.py:491-569).  With a tardis AtomData the reference's own
-    ``create_stellar_plasma`` is used; the synthetic provider stands in otherwise."""
+    """The LTE plasma is tardis' job (stardis/plasma/base.py:491-569) and outside this package: ``run_stardis`` covers the
+    seeded synthetic provider (``atom_data: synthetic:<n_lines>``); real atomic data is refused in
+    ``io.base.parse_config_to_model`` with a pointer to the integration route."""
     if isinstance(adata, dict) and adata.get("synthetic"):
         from .plasma.synthetic import create_synthetic_plasma
 
@@ -43,9 +44,7 @@ def create_stellar_plasma(stellar_model, adata, config, tracing_nus):
         nus = u.values_of(tracing_nus)
         return create_synthetic_plasma(atm, adata["n_lines"], nus.min(), nus.max(), seed=adata["seed"],
                                        vald=config.opacity.line.vald_linelist.use_linelist)
-    from stardis.plasma import create_stellar_plasma as reference_create_stellar_plasma  # needs tardis + stardis
-
-    return reference_create_stellar_plasma(stellar_model, adata, config)
+    raise NotImplementedError("only the synthetic plasma provider is available (see io.base.parse_config_to_model)")
 
 
 def set_num_threads(n_threads):

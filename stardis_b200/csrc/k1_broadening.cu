@@ -404,9 +404,7 @@ __global__ void __launch_bounds__(256) k_cls_scan(int nchunks, int *__restrict__
 }
 
 __global__ void __launch_bounds__(CHUNK) k_cls_scatter(int64_t L, const uint8_t *__restrict__ win_cls, int nchunks,
-                                                       const int *__restrict__ chunk_off, int *__restrict__ cls_list,
-                                                       const PairWin *__restrict__ win, const LineRec *__restrict__ rec,
-                                                       FcRec *__restrict__ fcrec) {
+                                                       const int *__restrict__ chunk_off, int *__restrict__ cls_list) {
     __shared__ int warp_cnt[SD_NCLS][CHUNK / 32];
     int d = blockIdx.y, ch = blockIdx.x;
     int64_t l = (int64_t)ch * CHUNK + threadIdx.x;
@@ -423,12 +421,6 @@ __global__ void __launch_bounds__(CHUNK) k_cls_scatter(int64_t L, const uint8_t 
         int off = chunk_off[((size_t)d * SD_NCLS + cls) * nchunks + ch];
         for (int ww = 0; ww < w; ww++) off += warp_cnt[cls][ww];
         cls_list[(size_t)d * L + off + my_rank] = (int)l;
-        if (cls == SD_FC_CLASS && fcrec) {  // compact, streamable copy of the far-capable pair at its list position
-            const int4 *w = reinterpret_cast<const int4 *>(win + (size_t)d * L + l);
-            const int4 *r = reinterpret_cast<const int4 *>(rec + (size_t)d * L + l);
-            int4 *o = reinterpret_cast<int4 *>(fcrec + (size_t)d * L + off + my_rank);
-            o[0] = __ldg(w); o[1] = __ldg(w + 1); o[2] = __ldg(r); o[3] = __ldg(r + 1);
-        }
     }
 }
 
@@ -536,10 +528,8 @@ int sd_k2_prepare(sd_ctx *c) {
     SD_TRY(sd_launch_check(c, "k_cls_count"));
     k_cls_scan<<<D, 256, 0, c->stream>>>(nchunks, c->chunk_cnt.as<int>(), c->cls_off.as<int>());
     SD_TRY(sd_launch_check(c, "k_cls_scan"));
-    if (c->farfield) SD_TRY(sd_ensure(c, c->fcrec, sizeof(FcRec) * n));
     k_cls_scatter<<<dim3(nchunks, D), CHUNK, 0, c->stream>>>(L, c->win_cls.as<uint8_t>(), nchunks, c->chunk_cnt.as<int>(),
-                                                           c->cls_list.as<int>(), c->win.as<PairWin>(), c->rec.as<LineRec>(),
-                                                           c->farfield ? c->fcrec.as<FcRec>() : nullptr);
+                                                           c->cls_list.as<int>());
     SD_TRY(sd_launch_check(c, "k_cls_scatter"));
     sd_phase_end(c, SD_PH_PREP);
     if (c->farfield) {

@@ -40,13 +40,12 @@
 namespace {
 
 constexpr int THREADS = 256;
-constexpr int K1_MAX_LANES = 32;            // coefficient k of a tile is reduced into lane k
 constexpr int WARPS = THREADS / 32;
-constexpr int FAR_CH = 512;                 // candidates per chunk of k_far_coeffs (two chunk stages in shared memory)
+constexpr int FAR_CH = 1024;                // candidates per cooperative scan chunk of k_far_coeffs
+struct __align__(16) FarRec { double nu, dw, y, K; };  // = the first 32 bytes of LineRec
 static_assert((SD_FAR_K + 1) % 3 == 0, "the series length is tested every third term");
 static_assert(WARPS == (1 << SD_FAR_SHIFT), "k_far_coeffs maps the warps of a CTA to the children of a tile");
-constexpr size_t FAR_SMEM = (size_t)2 * FAR_CH * sizeof(FcRec) + (size_t)WARPS * 128 * sizeof(double2);
-static_assert(FAR_CH % THREADS == 0 && K1_MAX_LANES >= SD_FAR_K + 1, "chunk / coefficient layout");
+constexpr size_t FAR_SMEM = (size_t)(FAR_CH + WARPS * 64) * sizeof(FarRec) + FAR_CH;
 
 struct __align__(16) WEntry {
     // far-wing path (48 B)
@@ -73,7 +72,6 @@ struct LineArgs {
     const int *line_idx;
     const LineRec *rec;
     const PairWin *win;   // (depth, line) window records
-    const FcRec *fcrec;   // per depth: the far-capable (class 7) pairs in class-list order, window + expansion record
     const int *cls_list, *cls_off;
     FarGeom fg;                  // tile hierarchy; fg.near[0] == nullptr: far field disabled
     double *far_coef[SD_FAR_LEVELS];   // per level: (D, n_tiles_launch[k], SD_FAR_K + 1)
@@ -223,21 +221,13 @@ __device__ __forceinline__ bool pair_is_far(int lo, int hi, unsigned near, int64
 // (`nsplit` CTAs per group; k_far_reduce adds the partial sums in slice order).  Groups, slices, chunking and queue order
 // depend on the global tile index and the candidate lists only, never on the shard, so the summation order -- and the
 // result, bit for bit -- is the same for every partition of the grid.
-__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src) {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src)
-                 : "memory");
-}
-
 __global__ void __launch_bounds__(THREADS) k_far_coeffs(LineArgs a, int lev, int count_stats, int nsplit, double *part) {
     constexpr int K1 = SD_FAR_K + 1;
-    constexpr int GROUPS = FAR_CH / 32;
     __shared__ int s_ja[3], s_jb[3];
-    __shared__ unsigned s_bits[GROUPS][WARPS];  // per 32 candidates of the chunk and child: acceptance bits
     extern __shared__ __align__(16) unsigned char far_smem[];
-    // chunk buffers, two stages, one array per 16-byte quarter of a candidate record (conflict-free 16-byte accesses):
-    // quarter 0 = {lo, hi, near[0], near[1]}, 1 = {near[2], cls, -, -}, 2 = {nu, dw}, 3 = {y, K}
-    int4 *const s_q = reinterpret_cast<int4 *>(far_smem);                               // [2][4][FAR_CH]
-    double2 *const s_queue = reinterpret_cast<double2 *>(s_q + 2 * 4 * FAR_CH);         // [WARPS][2][64] per-warp queues
+    FarRec *const s_rec = reinterpret_cast<FarRec *>(far_smem);                        // [FAR_CH] staged records of the chunk
+    FarRec *const s_queue = s_rec + FAR_CH;                                            // [WARPS][64] per-warp queues
+    unsigned char *const s_mask = reinterpret_cast<unsigned char *>(s_queue + WARPS * 64);  // [FAR_CH] child masks
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int d = blockIdx.y;
     const int tile_px = a.fg.tile[lev];
@@ -263,6 +253,7 @@ __global__ void __launch_bounds__(THREADS) k_far_coeffs(LineArgs a, int lev, int
         if (tc >= a.far_tile0[lev] && tc < a.far_tile0[lev] + a.far_ntl[lev]) valid |= 1u << cc;
     }
     const size_t drow = (size_t)d * a.L;
+    const int *list_d = a.cls_list + drow;
     const unsigned long long lmask = (1ull << a.fg.l_bits) - 1ull;  // line index = low bits of a window-edge key
     if (warp < 3) {
         int ja, jb;
@@ -287,18 +278,17 @@ __global__ void __launch_bounds__(THREADS) k_far_coeffs(LineArgs a, int lev, int
     const double inv_h = 1.0 / h;
     const unsigned lt_mask = (1u << lane) - 1u;
 
-    // One accepted pair: Taylor coefficients of its two poles about the tile centre.  Called with a dense batch of
+    // One accepted pair: 21 Taylor coefficients of its two poles about the tile centre.  Called with a dense batch of
     // pairs (one per lane); `have` is false only in the last, partial batch.
-    auto expand = [&](bool have, const double2 r01, const double2 r23) {
+    auto expand = [&](bool have, const FarRec &r) {
         double Wn = 0.0, w1r = 0.0, w1i = 0.0, w2r = 0.0, w2i = 0.0;
         int nterms = 0;
         if (have) {
-            const double r_nu = r01.x, r_dw = r01.y, r_y = r23.x, r_K = r23.y;
-            const double g = r_y * r_dw;                                // Lorentz half-width in Hz
-            Wn = -r_K * r_dw * (0.5 * sdm::INV_SQRT_PI) * inv_h;        // -W
-            const double adw = 0.7071067811865476 * r_dw;
+            const double g = r.y * r.dw;                                // Lorentz half-width in Hz
+            Wn = -r.K * r.dw * (0.5 * sdm::INV_SQRT_PI) * inv_h;        // -W
+            const double adw = 0.7071067811865476 * r.dw;
             // w = -h / (D - i g) = -h (D + i g) / (D^2 + g^2) for the two poles
-            const double D1 = nu_c - (r_nu + adw), D2 = nu_c - (r_nu - adw);
+            const double D1 = nu_c - (r.nu + adw), D2 = nu_c - (r.nu - adw);
             const double q1 = sdm::rcp_fast(fma(D1, D1, g * g)), q2 = sdm::rcp_fast(fma(D2, D2, g * g));
             const double i1 = -h * q1, i2 = -h * q2;
             w1r = D1 * i1; w1i = g * i1; w2r = D2 * i2; w2i = g * i2;
@@ -314,7 +304,7 @@ __global__ void __launch_bounds__(THREADS) k_far_coeffs(LineArgs a, int lev, int
         // Im(w^(k+1)) by the real three-term recurrence of the powers of a complex number,
         //   s_(k+1) = 2 Re(w) s_k - |w|^2 s_(k-1),  s_0 = 0, s_1 = Im w,
         // two instructions per pole and term instead of the four of a complex product (the recurrence loses about one
-        // bit per step relative to |w|^k, i.e. < 1e-13 over the series).
+        // bit per step relative to |w|^k, i.e. < 1e-13 over 21 terms).
         const double a1 = w1r + w1r, b1 = fma(w1r, w1r, w1i * w1i), a2 = w2r + w2r, b2 = fma(w2r, w2r, w2i * w2i);
         double s1 = w1i, s1p = 0.0, s2 = w2i, s2p = 0.0;
 #pragma unroll
@@ -329,140 +319,77 @@ __global__ void __launch_bounds__(THREADS) k_far_coeffs(LineArgs a, int lev, int
         }
     };
 
-    // acceptance mask of one candidate over the eight children (integer compares on its window record)
-    auto child_mask = [&](int src, int lo, int hi, unsigned near_p, unsigned near_l) -> unsigned {
-        bool okp = true;
-        if (has_parent) {
-            const bool covers_parent = (lo <= pt0) && (hi >= pt1);
-            if (src == 0) okp = covers_parent && !pair_is_far(lo, hi, near_p, pt0, pt1, ptile);  // (A)
-            else okp = !covers_parent && !(src == 2 && lo > pt0 && lo < pt1);  // (B); both edges inside: via its start
-        }
-        unsigned mask = 0;
-        if (okp) {
-#pragma unroll
-            for (int cc = 0; cc < WARPS; cc++) {
-                const int64_t c0 = (int64_t)(child0 + cc) * tile_px;
-                const int64_t c1 = (c0 + tile_px < a.N) ? c0 + tile_px : a.N;
-                if (pair_is_far(lo, hi, near_l, c0, c1, child0 + cc)) mask |= 1u << cc;
-            }
-            mask &= valid;
-        }
-        return mask;
-    };
-    // the acceptance bits of the 32 candidates a warp just tested, transposed: one 32-bit word per child
-    auto publish_bits = [&](int grp, unsigned mask) {
-        unsigned mine = 0;
-#pragma unroll
-        for (int cc = 0; cc < WARPS; cc++) {
-            const unsigned b = __ballot_sync(0xffffffffu, (mask >> cc) & 1u);
-            if (lane == cc) mine = b;
-        }
-        if (lane < WARPS) s_bits[grp][lane] = mine;
-    };
-
-    double2 *const qa = s_queue + warp * 128, *const qb = qa + 64;  // this warp's queue: {nu, dw} and {y, K}
-    int qn = 0;                                                     // its length
-    // this warp's child: accepted records of chunk stage `st` in list order -> queue -> dense batches of 32 expansions
-    auto drain_chunk = [&](int st, int n_here) {
-        const int4 *const q2 = s_q + (st * 4 + 2) * FAR_CH, *const q3 = s_q + (st * 4 + 3) * FAR_CH;
-        for (int g = 0; g * 32 < n_here && tile_ok; g++) {
-            const unsigned m = s_bits[g][warp];
-            if (!m) continue;
-            if ((m >> lane) & 1u) {
-                const int pos = qn + __popc(m & lt_mask);
-                qa[pos] = *reinterpret_cast<const double2 *>(q2 + g * 32 + lane);
-                qb[pos] = *reinterpret_cast<const double2 *>(q3 + g * 32 + lane);
-            }
-            qn += __popc(m);
-            __syncwarp();
-            if (qn >= 32) {
-                expand(true, qa[lane], qb[lane]);
-                const int rem = qn - 32;
-                double2 va, vb;
-                if (lane < rem) { va = qa[32 + lane]; vb = qb[32 + lane]; }
-                __syncwarp();
-                if (lane < rem) { qa[lane] = va; qb[lane] = vb; }
-                qn = rem;
-                __syncwarp();
-            }
-        }
-    };
-
-    // ---- source 0: contiguous range of the depth's compact class-7 records (64 bytes each): streamed through a two-stage
-    // cp.async pipeline -- the copy of chunk c + 1 runs while chunk c is tested and expanded
-    {
-        const int ja = s_ja[0], jb = s_jb[0];
-        const FcRec *const row = a.fcrec + drow;
-        const int n_chunks = (jb - ja + FAR_CH - 1) / FAR_CH;
-        auto issue = [&](int c) {
-            const int base = ja + c * FAR_CH, st = c & 1;
-            const int n_here = min(FAR_CH, jb - base);
-            const int4 *src = reinterpret_cast<const int4 *>(row + base);  // n_here * 4 consecutive 16-byte granules
-#pragma unroll
-            for (int r = 0; r < 4 * FAR_CH / THREADS; r++) {
-                const int gi = r * THREADS + tid;
-                if (gi < 4 * n_here) cp_async16(s_q + (st * 4 + (gi & 3)) * FAR_CH + (gi >> 2), src + gi);
-            }
-            asm volatile("cp.async.commit_group;" ::: "memory");
-        };
-        if (n_chunks > 0) issue(0);
-        for (int c = 0; c < n_chunks; c++) {
-            const int st = c & 1, base = ja + c * FAR_CH;
-            const int n_here = min(FAR_CH, jb - base);
-            if (c + 1 < n_chunks) {
-                issue(c + 1);
-                asm volatile("cp.async.wait_group 1;" ::: "memory");
-            } else {
-                asm volatile("cp.async.wait_group 0;" ::: "memory");
-            }
-            __syncthreads();  // chunk c is in shared memory
-#pragma unroll
-            for (int r = 0; r < FAR_CH / THREADS; r++) {
-                const int idx = r * THREADS + tid;
-                unsigned mask = 0;
-                if (idx < n_here) {
-                    const int4 w0 = s_q[(st * 4 + 0) * FAR_CH + idx];
-                    const int w1x = s_q[(st * 4 + 1) * FAR_CH + idx].x;
-                    const unsigned nr[3] = {(unsigned)w0.z, (unsigned)w0.w, (unsigned)w1x};
-                    mask = child_mask(0, w0.x, w0.y, plev == 0 ? nr[0] : (plev == 1 ? nr[1] : nr[2]),
-                                      lev == 0 ? nr[0] : (lev == 1 ? nr[1] : nr[2]));
-                }
-                publish_bits(r * WARPS + warp, mask);
-            }
-            __syncthreads();  // acceptance bits complete
-            drain_chunk(st, n_here);
-            __syncthreads();  // stage st may be overwritten by the copy of chunk c + 2
-        }
-    }
-    // ---- sources 1, 2: pairs with a window edge strictly inside the parent (edge-sorted lists): gathered
-    for (int src = 1; src < 3 && has_parent; src++) {
+    FarRec *const q = s_queue + warp * 64;
+    int qn = 0;  // queue length of this warp
+    for (int src = 0; src < 3; src++) {
         const int ja = s_ja[src], jb = s_jb[src];
         for (int base = ja; base < jb; base += FAR_CH) {
-            const int n_here = min(FAR_CH, jb - base);
+            // ---- scan: one gather per candidate, acceptance mask over the eight children
 #pragma unroll
             for (int r = 0; r < FAR_CH / THREADS; r++) {
-                const int idx = r * THREADS + tid;
+                const int idx = r * THREADS + tid, j = base + idx;
                 unsigned mask = 0;
-                if (idx < n_here) {
-                    const int l = (int)(a.fg.edge_keys[base + idx] & lmask);
+                if (j < jb) {
+                    const int l = (src == 0) ? list_d[j] : (int)(a.fg.edge_keys[j] & lmask);
                     const PairWin pw = load_win(a.win + drow + l);
-                    mask = child_mask(src, pw.lo, pw.hi, near_of(pw, plev), near_of(pw, lev));
+                    const int lo = pw.lo, hi = pw.hi;
+                    bool okp = true;
+                    if (has_parent) {
+                        const bool covers_parent = (lo <= pt0) && (hi >= pt1);
+                        if (src == 0) {  // (A): covers the parent, parent inside the near interval
+                            okp = covers_parent && !pair_is_far(lo, hi, near_of(pw, plev), pt0, pt1, ptile);
+                        } else {         // (B): an edge strictly inside the parent; both edges inside: via its start
+                            okp = !covers_parent && !(src == 2 && lo > pt0 && lo < pt1);
+                        }
+                    }
+                    if (okp) {
+                        const unsigned near = near_of(pw, lev);
+#pragma unroll
+                        for (int cc = 0; cc < WARPS; cc++) {
+                            const int64_t c0 = (int64_t)(child0 + cc) * tile_px;
+                            const int64_t c1 = (c0 + tile_px < a.N) ? c0 + tile_px : a.N;
+                            if (pair_is_far(lo, hi, near, c0, c1, child0 + cc)) mask |= 1u << cc;
+                        }
+                        mask &= valid;
+                    }
                     if (mask) {
-                        const int4 *srcp = reinterpret_cast<const int4 *>(a.rec + drow + l);
-                        cp_async16(s_q + 2 * FAR_CH + idx, srcp);
-                        cp_async16(s_q + 3 * FAR_CH + idx, srcp + 1);
+                        const unsigned dst = (unsigned)__cvta_generic_to_shared(s_rec + idx);
+                        const LineRec *srcp = a.rec + drow + l;
+                        asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(srcp) : "memory");
+                        asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst + 16u),
+                                     "l"(reinterpret_cast<const char *>(srcp) + 16) : "memory");
                     }
                 }
-                publish_bits(r * WARPS + warp, mask);
+                s_mask[idx] = (unsigned char)mask;
             }
             asm volatile("cp.async.commit_group;" ::: "memory");
             asm volatile("cp.async.wait_group 0;" ::: "memory");
             __syncthreads();
-            drain_chunk(0, n_here);
-            __syncthreads();
+            // ---- expand: this warp's child, in list order
+            const int n_here = (jb - base < FAR_CH) ? jb - base : FAR_CH;
+            for (int i0 = 0; i0 < n_here && tile_ok; i0 += 32) {
+                const int idx = i0 + lane;
+                const bool acc = (idx < n_here) && ((s_mask[idx] >> warp) & 1u);
+                const unsigned m = __ballot_sync(0xffffffffu, acc);
+                if (!m) continue;
+                if (acc) q[qn + __popc(m & lt_mask)] = s_rec[idx];
+                qn += __popc(m);
+                __syncwarp();
+                if (qn >= 32) {
+                    expand(true, q[lane]);
+                    const int rem = qn - 32;
+                    FarRec v;
+                    if (lane < rem) v = q[32 + lane];
+                    __syncwarp();
+                    if (lane < rem) q[lane] = v;
+                    qn = rem;
+                    __syncwarp();
+                }
+            }
+            __syncthreads();  // the chunk buffers are overwritten by the next scan
         }
     }
-    if (qn > 0) expand(lane < qn, qa[lane < qn ? lane : 0], qb[lane < qn ? lane : 0]);
+    if (qn > 0) expand(lane < qn, q[lane < qn ? lane : 0]);
     // deterministic reduction: lanes by shuffle (every lane ends up with the sum; lane k keeps coefficient k)
     double mine = 0.0;
 #pragma unroll
@@ -647,84 +574,59 @@ __global__ void __launch_bounds__(32 * NW, MINB) k_lines(LineArgs a) {
             // pixels of the in-window part of the span (a 20-pixel window keeps 20 lanes busy in one pass); entries are
             // processed one after the other and a pass touches distinct pixels, so the shared accumulators need no
             // atomics and the summation order stays fixed.
-            // Sweeps run on a 32-pixel grid CENTRED ON THE LINE (block k = pixels [c - 16 + 32 k, c + 16 + 32 k), c = middle
-            // of the window): the Humlicek regions are nested rings around the centre, so a centred block holds one region
-            // (the innermost ~+-16 pixels: III/IV) or two instead of the three a window-aligned block typically straddles,
-            // and the expensive region-IV branch is executed once per line instead of twice.
             for (int m = 0; m < n_mix; m++) {
                 const WEntry &e2 = my[31 - m];
                 const int64_t pa = e2.lo > ws ? e2.lo : ws, pb = e2.hi < we ? e2.hi : we;
                 const double thr = e2.thr, xl = e2.xl, inv_dw = e2.inv_dw, eb = e2.b, ec = e2.c, Kc = e2.Kc, Kf = e2.Kf;
-                const int64_t cen = ((int64_t)e2.lo + (int64_t)e2.hi) >> 1;  // the line centre unless the grid end clipped the window
-                // one block: pixels [b0, b0 + 32) of the overlap, lanes on consecutive pixels; returns whether any of them
-                // was NOT certainly in region I
-                auto sweep = [&](int64_t b0) -> bool {
-                    const int64_t pix = b0 + lane;
-                    bool slow = false;
-                    if (pix >= pa && pix < pb) {
-                        const int k = (int)(pix - ws);
-                        const double nu = nus[pix];
-                        const double x = fma(nu, inv_dw, -xl);
-                        const double q = x * x;
-                        double v;
-                        if (q > thr) {
-                            const double den = fma(q, q + eb, ec);
-                            const double num = fma(Kf, q, Kc);
-                            v = num * (RCP == 2 ? sdm::rcp_fast2(den) : sdm::rcp_fast(den));
-                        } else {
-                            v = exact_contribution(nu, e2.nu, e2.dw, inv_dw, thr, e2.y, e2.K);
-                            slow = true;
-                        }
-                        s_acc[warp][k] += v;
-                        if (STATS && pix >= p0 && pix < p1) {
-                            int r = sdm::humlicek_region((nu - e2.nu) / e2.dw, e2.y);
-                            h0 += (r == 0); h1 += (r == 1); h2 += (r == 2); h3 += (r == 3);
+                if (pb - pa <= 64) {
+                    for (int64_t c0 = pa; c0 < pb; c0 += 32) {
+                        const int64_t pix = c0 + lane;
+                        if (pix < pb) {
+                            const int k = (int)(pix - ws);
+                            const double nu = nus[pix];
+                            double x = fma(nu, inv_dw, -xl);
+                            double q = x * x;
+                            double v;
+                            if (q > thr) {
+                                double den = fma(q, q + eb, ec);
+                                double num = fma(Kf, q, Kc);
+                                v = num * (RCP == 2 ? sdm::rcp_fast2(den) : sdm::rcp_fast(den));
+                            } else {
+                                v = exact_contribution(nu, e2.nu, e2.dw, inv_dw, thr, e2.y, e2.K);
+                            }
+                            s_acc[warp][k] += v;
+                            if (STATS && pix >= p0 && pix < p1) {
+                                int r = sdm::humlicek_region((nu - e2.nu) / e2.dw, e2.y);
+                                h0 += (r == 0); h1 += (r == 1); h2 += (r == 2); h3 += (r == 3);
+                            }
                         }
                     }
-                    return __any_sync(0xffffffffu, slow);
-                };
-                if (pb - pa <= 64) {
-                    // short overlap: every block of the centred grid that meets it
-                    int off = (int)((pa - (cen - 16)) % 32);
-                    if (off < 0) off += 32;
-                    for (int64_t c0 = pa - off; c0 < pb; c0 += 32) sweep(c0);
+                    // the next entry's pass may update the same pixel from another lane: order the shared read-modify-
+                    // writes of the warp (independent thread scheduling gives no lock-step guarantee after the divergent
+                    // exact path; compute-sanitizer racecheck flagged exactly this line)
+                    __syncwarp();
                 } else {
-                    // long overlap (a near-field pair whose core or window edge lies in this span): centred blocks from the
-                    // (clamped) centre outwards as far as pixels outside region I reach, register slots for the rest
-                    const int64_t cc = cen < pa ? pa : (cen >= pb ? pb - 1 : cen);
-                    int off = (int)((cc - (cen - 16)) % 32);
-                    if (off < 0) off += 32;
-                    int64_t sa = cc - off, sb = sa + 32;  // swept so far: [sa, sb)
-                    const bool core = sweep(sa);
-                    for (bool more = core; more && sa > pa;) { sa -= 32; more = sweep(sa); }
-                    for (bool more = core; more && sb < pb;) { more = sweep(sb); sb += 32; }
-                    const int oa = (int)(pa - ws), ob = (int)(pb - ws);
-                    const int ka = (int)((sa > pa ? sa : pa) - ws), kb = (int)((sb < pb ? sb : pb) - ws);
+                    // long overlap (a near-field pair whose core or window edge lies in this span): register slots
+                    const int lo2 = e2.lo, hi2 = e2.hi;
 #pragma unroll
                     for (int p = 0; p < P; p++) {
-                        const int k = p * 32 + lane;
-                        const bool in = (k >= oa) && (k < ob) && (k < ka || k >= kb);
-                        if (!__any_sync(0xffffffffu, in)) continue;
-                        const double x = fma(nu_i[p], inv_dw, -xl);
-                        const double q = x * x;
-                        const bool fast = in && (q > thr);
-                        const double den = fma(q, q + eb, ec);
-                        const double num = fma(Kf, q, Kc);
-                        const double v = num * (RCP == 2 ? sdm::rcp_fast2(den) : sdm::rcp_fast(den));
+                        int64_t pix = ws + p * 32 + lane;
+                        bool inwin = (pix >= lo2) && (pix < hi2) && (pix < t1);
+                        if (!__any_sync(0xffffffffu, inwin)) continue;
+                        double x = fma(nu_i[p], inv_dw, -xl);
+                        double q = x * x;
+                        bool fast = inwin && (q > thr);
+                        double den = fma(q, q + eb, ec);
+                        double num = fma(Kf, q, Kc);
+                        double v = num * (RCP == 2 ? sdm::rcp_fast2(den) : sdm::rcp_fast(den));
                         if (fast) acc[p] += v;
-                        if (__any_sync(0xffffffffu, in && !fast)) {  // grids that are not monotone only
-                            if (in && !fast) acc[p] += exact_contribution(nu_i[p], e2.nu, e2.dw, inv_dw, thr, e2.y, e2.K);
-                        }
-                        if (STATS && in && ws + k >= p0 && ws + k < p1) {
+                        if (inwin && !fast) acc[p] += exact_contribution(nu_i[p], e2.nu, e2.dw, inv_dw, thr, e2.y, e2.K);
+                        if (STATS && inwin && pix >= p0 && pix < p1) {
                             int r = sdm::humlicek_region((nu_i[p] - e2.nu) / e2.dw, e2.y);
                             h0 += (r == 0); h1 += (r == 1); h2 += (r == 2); h3 += (r == 3);
                         }
                     }
                 }
-                // the next entry's blocks may update the same pixels from other lanes: order the shared read-modify-writes
-                // of the warp (independent thread scheduling gives no lock-step guarantee after the divergent exact path;
-                // compute-sanitizer racecheck flagged exactly this)
-                __syncwarp();
             }
             __syncwarp();
             }
@@ -845,7 +747,6 @@ int sd_k2_lines(sd_ctx *c, int slot) {
     const int n_launch = (int)((c->p1 + tile - 1) / tile) - a.tile0;
     a.nus = c->nus.as<double>(); a.line_idx = c->line_idx.as<int>(); a.rec = c->rec.as<LineRec>();
     a.win = c->win.as<PairWin>();
-    a.fcrec = c->fcrec.as<FcRec>();
     a.cls_list = c->cls_list.as<int>(); a.cls_off = c->cls_off.as<int>();
     a.fg = c->far_geom;
     a.out = c->alpha_line[slot].as<double>();

@@ -31,16 +31,6 @@ struct __align__(16) PairWin {
 };
 static_assert(sizeof(PairWin) == 32, "PairWin must be 32 bytes");
 
-// ---- compact record of a far-capable (class 7) pair: window + the 32 bytes the far-field expansion needs, stored per
-// depth in class-list order (= by window centre) so that k_far_coeffs STREAMS its candidates (contiguous 64-byte
-// records, cp.async pipeline) instead of gathering index -> window -> record
-struct __align__(16) FarRec { double nu, dw, y, K; };  // = the first 32 bytes of LineRec
-struct __align__(16) FcRec {
-    PairWin win;
-    FarRec rec;
-};
-static_assert(sizeof(FcRec) == 64, "FcRec must be 64 bytes");
-
 constexpr int SD_NCLS = 8;          // half-width classes
 constexpr int SD_CLS0_HW = 64;      // class 0: hw <= 64; class k: hw <= 64 * 4^k; last class: everything wider
 constexpr int SD_MAX_SOURCES = 4 + SD_MAX_TABLES;
@@ -132,7 +122,6 @@ struct sd_ctx {
     DevBuf win;        // PairWin [D*L]
     DevBuf win_cls;    // uint8 [D*L]
     DevBuf cls_list;   // int32 [D*L]   per depth: lines of class 1.. concatenated by class (stable in l)
-    DevBuf fcrec;      // FcRec [D*L]   per depth: compact records of the class-7 pairs at their cls_list positions
     DevBuf cls_off;    // int32 [D*(NCLS+1)] offsets into cls_list row d (class 0 is not listed)
     DevBuf chunk_cnt;  // int32 [D * nchunks * NCLS]
     DevBuf stats;      // uint64 [8]

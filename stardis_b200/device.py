@@ -62,10 +62,14 @@ class DeviceContext:
         self._ck(self.lib.sd_synchronize(self.h))
         self._keep.clear()
 
+    KEEP_LIMIT = 4096  # host buffers kept alive for in-flight copies before a synchronisation point is forced
+
     def _in(self, a, integer=False):
         if a is None:
             return None
         a = L.i64(a) if integer else L.f64(a)
+        if len(self._keep) >= self.KEEP_LIMIT:  # callers that never synchronise (device-to-device result reads) must
+            self.synchronize()                   # not grow the list without bound
         self._keep.append(a)
         return L.ptr(a)
 

@@ -46,11 +46,16 @@ def line_balanced_bounds(tracing_nus, line_nus, world_size, line_weight=10.0, al
     cuts = np.append(cuts, n)  # candidate cut positions (aligned) and the end of the grid
     lines_below = np.searchsorted(np.sort(pos), cuts, side="left")
     cost = cuts.astype(np.float64) + float(line_weight) * lines_below
+    if n < world_size:
+        raise ValueError(f"cannot split {n} pixels into {world_size} non-empty ranges")
+    step = align if n >= world_size * align else 1  # smallest admissible range (one aligned block; pixels on tiny grids)
     bounds, prev = [], 0
     for r in range(1, world_size):
         k = int(np.searchsorted(cost, cost[-1] * r / world_size, side="left"))
         cut = int(cuts[min(max(k, 0), len(cuts) - 1)])
-        cut = min(max(cut, prev), n)
+        # every rank gets at least one block (sd_set_grid needs p0 < p1; an empty range would leave its rank out of the
+        # collectives): not before prev + step, and room for the ranks still to come
+        cut = min(max(cut, prev + step), n - (world_size - r) * step)
         bounds.append((prev, cut))
         prev = cut
     bounds.append((prev, n))

@@ -3,15 +3,18 @@
 Atomic data and the LTE plasma live in the third-party ``tardis`` package (not available offline, out of the hot-path
 scope).  ``atom_data`` therefore accepts
 
-* ``*.h5``  -- a carsus/tardis atomic data file: needs ``tardis`` (and the reference's plasma layer) importable;
-  the call is delegated to them and only the opacity + formal-solution path runs here;
+* ``*.h5``  -- a carsus/tardis atomic data file: NOT handled here.  Turning it into the hot path's inputs is the job of
+  tardis' LTE plasma and of the reference's ``create_stellar_plasma`` (upstream of the path, third-party, absent
+  offline).  A user with tardis + stardis installed builds ``stellar_model`` / ``stellar_plasma`` with the reference's
+  own ``parse_config_to_model`` / ``create_stellar_plasma`` and hands them to
+  ``stardis_b200.radiation_field.create_stellar_radiation_field`` (INTEGRATION.md); ``run_stardis`` raises
+  ``NotImplementedError`` for such a config instead of pretending to be a drop-in for that part;
 * ``synthetic:<n_lines>[:<seed>]`` -- the seeded synthetic plasma state of ``stardis_b200.plasma.synthetic`` (the
   attribute surface the hot path reads), used by the benchmarks and tests.
 """
 from __future__ import annotations
 
 import logging
-import os
 from pathlib import Path
 
 from .. import units as u
@@ -42,6 +45,10 @@ def parse_config_to_model(config_fname, add_config_dict=None):
 
     base = Path(config_fname).resolve().parent
     adata = _load_atom_data(config.atom_data, base)
+    if config.input_model.get("nuclide_rescaling_dict"):
+        raise NotImplementedError(
+            "input_model.nuclide_rescaling_dict rescales the tardis composition before the plasma solve (stardis/io/base.py:"
+            "103-117), which is upstream of the hot path and not part of this package; it would be silently ignored here")
 
     logger.info("Reading model")
     if config.input_model.type == "marcs":
@@ -69,12 +76,9 @@ def _load_atom_data(spec, base):
     if spec.startswith("synthetic:"):
         parts = spec.split(":")
         return {"synthetic": True, "n_lines": int(parts[1]), "seed": int(parts[2]) if len(parts) > 2 else 0}
-    path = spec if os.path.isabs(spec) or os.path.exists(spec) else str(base / spec)
-    try:
-        from tardis.io.atom_data import AtomData
-    except ImportError as e:
-        raise ImportError(
-            f"atom_data={spec!r} is a tardis/carsus HDF5 file, but tardis is not installed; the LTE plasma that turns it "
-            "into the hot path's inputs is part of tardis (outside this package's scope). Use 'synthetic:<n_lines>' or "
-            "install tardis + stardis for real atomic data.") from e
-    return AtomData.from_hdf(path)
+    raise NotImplementedError(
+        f"atom_data={spec!r}: carsus/tardis atomic data files feed tardis' LTE plasma (stardis/plasma/base.py:491-569), "
+        "which is upstream of the hot path and not part of this package.  With tardis + stardis installed, build "
+        "stellar_model and stellar_plasma with the reference's own parse_config_to_model / create_stellar_plasma and pass "
+        "them to stardis_b200.radiation_field.create_stellar_radiation_field (INTEGRATION.md); for benchmarks and tests use "
+        "atom_data: 'synthetic:<n_lines>[:<seed>]'.")

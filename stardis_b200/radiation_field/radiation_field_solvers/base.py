@@ -92,6 +92,9 @@ def raytrace(stellar_model, stellar_radiation_field):
         arr = as_host(previous)  # materialises a device-backed F_nu BEFORE its buffer is overwritten
         if np.any(arr != 0):
             prev_host = arr
+    held = getattr(srf, "_I_nus", None)
+    if isinstance(held, DeviceArray):
+        held.detach_to_host()  # intensities of an earlier raytrace() on this field: materialise before the buffer is reused
     ctx.raytrace(ds, np.asarray(srf.I_nus_weights, dtype=np.float64), inward_rays=inward, scale=scale, track=track)
     F = ctx.track(DeviceArray(ctx, L.BUF_F_NU, (D, W)))
     if prev_host is not None:
