@@ -233,6 +233,12 @@ int sd_ew_gamma_van_der_waals(sd_ctx *ctx, int64_t n, const double *z_eff, const
 int sd_ew_blackbody(sd_ctx *ctx, int32_t n_depth, int64_t n_nu, const double *nus, const double *T, double *out);
 int sd_ew_calc_weights(sd_ctx *ctx, int64_t n, const double *tau, double *w0, double *w1, double *w2);
 
+/* ---- spectrum post-processing: rotation_broadening (broadening.py:824-877) ----------------------------------- */
+/* out[i] = sum_j weights[j] x[reflect(i - j + m/2)], m odd: scipy.ndimage.convolve1d(x, weights) with its default
+ * "reflect" boundary, the convolution rotation_broadening applies to the flux (the O(m) rotational profile itself is
+ * formed by the caller).  x / out: n doubles, host or device. */
+int sd_convolve1d_reflect(sd_ctx *ctx, int64_t n, const double *x, int32_t m, const double *weights, double *out);
+
 /* ---- measurement helpers (bench.py roofline denominators) --------------------------------------- */
 /* Dependent-chain-free DFMA loop on every SM; returns achieved FP64 TFLOP/s (2 flops per FMA). */
 int sd_bench_dfma(sd_ctx *ctx, int32_t iters, double *tflops);

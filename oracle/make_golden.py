@@ -16,6 +16,7 @@ Fixtures
 from __future__ import annotations
 
 import os
+import sys
 import types
 
 import numpy as np
@@ -240,13 +241,35 @@ def gen_raytrace(R, rng):
     np.savez_compressed(os.path.join(OUT, "raytrace_golden.npz"), **out)
 
 
+def gen_rotation(R, rng):
+    """rotation_broadening (broadening.py:824-877) on a synthetic spectrum with absorption lines, three rotational
+    velocities (one below the 1e-5 km/s cut: returned unchanged)."""
+    from oracle.ref_shim import UQ, Unit
+
+    n = 4000
+    lam = 5000.0 * np.exp(np.arange(n) * 2.0 / 2.99792458e5)  # constant 2 km/s per pixel
+    flux = 1.0e6 * (1.0 + 0.05 * np.sin(np.arange(n) / 300.0))
+    for c in rng.integers(50, n - 50, 40):
+        flux *= 1.0 - rng.uniform(0.1, 0.9) * np.exp(-0.5 * ((np.arange(n) - c) / rng.uniform(1.5, 6.0)) ** 2)
+    out = dict(lam=lam, flux=flux, velocity_per_pix=2.0)
+    kms = Unit("km/s")
+    for tag, v, eps in (("a", 17.0, 0.6), ("b", 60.5, 0.3), ("c", 0.0, 0.6)):
+        _, f = R.broadening.rotation_broadening(UQ(2.0, kms), lam, flux, v_rot=UQ(v, kms), limb_darkening=eps)
+        out[f"v_{tag}"], out[f"eps_{tag}"], out[f"out_{tag}"] = v, eps, np.asarray(getattr(f, "value", f), dtype=np.float64)
+    np.savez_compressed(os.path.join(OUT, "rotation_golden.npz"), **out)
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     R = load_reference()
+    if "rotation" in sys.argv[1:]:
+        gen_rotation(R, np.random.default_rng(105))
+        return
     gen_kernels(R, np.random.default_rng(101))
     gen_broadening(R, np.random.default_rng(102))
     gen_alan(R, np.random.default_rng(103))
     gen_raytrace(R, np.random.default_rng(104))
+    gen_rotation(R, np.random.default_rng(105))
     from oracle import make_golden_pipeline
 
     make_golden_pipeline.main(R)

@@ -440,3 +440,71 @@ def alpha_line_vald(atomic_number, ion_charge, wavelength_aa, log_gf, e_low_ev, 
         alphas = alphas[valid]
         lines = {k: v[valid] for k, v in lines.items()}
     return alphas, lines
+
+
+# ------------------------------------------------------------------ tardis line strengths (upstream of K1/K2)
+def stimulated_emission_factor(level_number_density, g, lower_level_index, upper_level_index, metastable_upper):
+    """tardis ``StimulatedEmissionFactor.calculate`` (third-party tardis release-2024.08.25,
+    tardis/plasma/properties/radiative_properties.py; source absent offline -- restated from its published algorithm, PARITY
+    UNPINNED for this factor): 1 - (g_lower n_upper) / (g_upper n_lower); 0 where n_lower == 0, where the factor is -inf, and
+    where it is negative for a line whose upper level is metastable."""
+    n = np.asarray(level_number_density, dtype=np.float64)
+    g = np.asarray(g, dtype=np.float64)
+    n_lower, n_upper = n[lower_level_index], n[upper_level_index]
+    with np.errstate(divide="ignore", invalid="ignore"):
+        sef = 1.0 - ((g[lower_level_index][:, None] * n_upper) / (g[upper_level_index][:, None] * n_lower))
+    sef[n_lower == 0.0] = 0.0
+    sef[np.isneginf(sef)] = 0.0
+    sef[np.asarray(metastable_upper, dtype=bool)[:, None] & (sef < 0)] = 0.0
+    return sef
+
+
+def alpha_line(level_number_density, lower_level_index, stimulated_emission_factor_, f_lu):
+    """``AlphaLine.calculate`` (stardis/plasma/base.py:143-158): ALPHA_COEFFICIENT * n_lower * sef * f_lu, left to right."""
+    ALPHA_COEFFICIENT = (np.pi * 4.803204712570263e-10 ** 2) / (9.1093837015e-28 * 2.99792458e10)  # :35
+    n_lower = np.asarray(level_number_density, dtype=np.float64)[lower_level_index]
+    return ALPHA_COEFFICIENT * n_lower * stimulated_emission_factor_ * np.asarray(f_lu, dtype=np.float64)[:, None]
+
+
+# ------------------------------------------------------------------ molecules (stardis/plasma/molecules.py)
+_SYMBOLS = ("H He Li Be B C N O F Ne Na Mg Al Si P S Cl Ar K Ca Sc Ti V Cr Mn Fe Co Ni Cu Zn").split()
+
+
+def split_ion(s):
+    """'C+' -> (6, 1), 'H-' -> (1, -1) (molecules.py:145-159: symbol, count of '+' minus count of '-')."""
+    import re
+
+    m = re.match(r"([A-Z][a-z]?)(\+*)(\-*)", s)
+    return _SYMBOLS.index(m.group(1)) + 1, len(m.group(2)) - len(m.group(3))
+
+
+def molecule_number_density(ion1, ion2, equilibrium_constants, t_grid, ion_index, ion_number_density, t_electrons):
+    """``MoleculeIonNumberDensity.calculate`` (molecules.py:35-143): Barklem & Collet 2016 pressure equilibrium constants
+    (log10, SI) splined in T, converted to number-density constants with the ideal gas law, then the closed-form solution of
+    the dissociation equilibrium (homonuclear / heteronuclear); negative ions and absent elements give 0."""
+    from scipy.interpolate import CubicSpline
+
+    T = np.asarray(t_electrons, dtype=np.float64)
+    nd = {tuple(int(v) for v in k): np.asarray(r, dtype=np.float64) for k, r in zip(ion_index, ion_number_density)}
+    included = {k[0] for k in nd}
+    out = np.zeros((len(ion1), T.size))
+    ion_map = np.zeros((len(ion1), 2), dtype=np.int64)
+    for i, (a, b) in enumerate(zip(ion1, ion2)):
+        (z1, c1), (z2, c2) = split_ion(str(a)), split_ion(str(b))
+        ion_map[i] = (z1, z2)
+        if c1 == -1 or c2 == -1 or z1 not in included or z2 not in included:
+            continue
+        n1, n2 = nd[(z1, c1)], nd[(z2, c2)]
+        logk = CubicSpline(t_grid, equilibrium_constants[i], extrapolate=True)(T)
+        k = (10.0 ** logk) * 10.0 / (1.380649e-16 * T)  # Pa -> dyn cm^-2, / k_B T -> cm^-3
+        if z1 == z2 and c1 == c2:
+            n = (1 / 8) * ((-((k * (k + 8 * n1)) ** 0.5)) + k + 4 * n1)
+        else:
+            n = 0.5 * (-np.sqrt(k ** 2 + 2 * k * (n1 + n2) + (n1 - n2) ** 2) + k + n1 + n2)
+        out[i] = np.maximum(n, 0)
+    return out, ion_map
+
+
+def molecule_partition_function(partition_functions, t_grid, t_electrons):
+    """``MoleculePartitionFunction.calculate`` (molecules.py:176-191): np.interp per molecule."""
+    return np.array([np.interp(t_electrons, t_grid, row) for row in partition_functions])

@@ -100,6 +100,7 @@ def load_plasma_module():
                      m_e=Const(9.1093837015e-28), m_p=Const(1.67262192369e-24), u=Const(1.66053906660e-24))
     units = _module("astropy.units", eV=ScaleUnit(EV_ERG), K=ScaleUnit(1.0), AA=ScaleUnit(1e-8), Angstrom=ScaleUnit(1e-8),
                     Hz=ScaleUnit(1.0), cm=ScaleUnit(1.0), erg=ScaleUnit(1.0), s=ScaleUnit(1.0), km=ScaleUnit(1e5),
+                    Pa=ScaleUnit(10.0),
                     spectral=lambda: "spectral")
     _module("astropy", constants=consts, units=units)
 
@@ -109,7 +110,9 @@ def load_plasma_module():
 
     _module("tardis")
     _module("tardis.util")
-    _module("tardis.util.base", element_symbol2atomic_number=lambda s: 0, species_string_to_tuple=lambda s: (0, 0))
+    symbols = ("H He Li Be B C N O F Ne Na Mg Al Si P S Cl Ar K Ca Sc Ti V Cr Mn Fe Co Ni Cu Zn").split()
+    _module("tardis.util.base", element_symbol2atomic_number=lambda s: symbols.index(s) + 1,
+            species_string_to_tuple=lambda s: (0, 0))
     _module("tardis.plasma")
     _module("tardis.plasma.base", BasePlasma=_Base)
     _module("tardis.plasma.properties")

@@ -83,6 +83,7 @@ SIGNATURES = {
     "sd_ew_gamma_van_der_waals": (C.c_int, [_V, C.c_int64, _V, _V, _V, _V, _V, _V]),
     "sd_ew_blackbody": (C.c_int, [_V, C.c_int32, C.c_int64, _V, _V, _V]),
     "sd_ew_calc_weights": (C.c_int, [_V, C.c_int64, _V, _V, _V, _V]),
+    "sd_convolve1d_reflect": (C.c_int, [_V, C.c_int64, _V, C.c_int32, _V, _V]),
     "sd_bench_dfma": (C.c_int, [_V, C.c_int32, _dp]),
     "sd_bench_fp64": (C.c_int, [_V, C.c_int32, C.c_int32, _dp]),
     "sd_bench_fareval": (C.c_int, [_V, C.c_int32, C.c_int32, _dp]),

@@ -698,6 +698,44 @@ int sd_ew_blackbody(sd_ctx *c, int32_t D, int64_t N, const double *nus, const do
 
 }  // extern "C"
 
+// ------------------------------------------------------------------------------- spectrum convolution
+namespace {
+// out[i] = sum_j w[j] x[reflect(i - j + m/2)], m odd: scipy.ndimage.convolve1d(x, w) with its default mode "reflect"
+// (half-sample symmetric: d c b a | a b c d | d c b a), as rotation_broadening calls it (broadening.py:866-874)
+__global__ void __launch_bounds__(256) k_convolve1d_reflect(int64_t n, const double *__restrict__ x, int m,
+                                                            const double *__restrict__ w, double *__restrict__ out) {
+    extern __shared__ double s_w[];
+    for (int k = threadIdx.x; k < m; k += blockDim.x) s_w[k] = w[k];
+    __syncthreads();
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int h = m / 2;
+    double acc = 0.0;
+    for (int j = 0; j < m; j++) {
+        int64_t k = i - j + h;
+        while (k < 0 || k >= n) k = (k < 0) ? -k - 1 : 2 * n - k - 1;
+        acc += s_w[j] * x[k];  // scipy accumulates in kernel order as well; agreement ~1e-16 relative
+    }
+    out[i] = acc;
+}
+}  // namespace
+
+extern "C" int sd_convolve1d_reflect(sd_ctx *c, int64_t n, const double *x, int32_t m, const double *weights, double *out) {
+    if (!c) return SD_ERR_ARG;
+    SD_CHECK(c, n > 0 && x && weights && out && m > 0 && (m & 1) && m <= 6000, SD_ERR_ARG,
+             "sd_convolve1d_reflect: need n > 0 and an odd kernel length <= 6000");
+    SD_CUDA(c, cudaSetDevice(c->device));
+    Staged st{c};
+    SD_TRY(sd_upload(c, st.in[0], x, sizeof(double) * n));
+    SD_TRY(sd_upload(c, st.in[1], weights, sizeof(double) * m));
+    SD_TRY(sd_ensure(c, st.out[0], sizeof(double) * n));
+    k_convolve1d_reflect<<<nblk(n), 256, sizeof(double) * m, c->stream>>>(n, st.in[0].as<double>(), m, st.in[1].as<double>(),
+                                                                          st.out[0].as<double>());
+    SD_TRY(sd_launch_check(c, "k_convolve1d_reflect"));
+    SD_CUDA(c, cudaMemcpyAsync(out, st.out[0].p, sizeof(double) * n, cudaMemcpyDefault, c->stream));
+    return SD_OK;
+}
+
 // ------------------------------------------------------------------------------- measurement helpers
 namespace {
 // 8 independent FMA chains per thread, no memory traffic: the FP64 FMA-pipe ceiling of the chip.

@@ -323,6 +323,15 @@ class DeviceContext:
         self.synchronize()
         return out
 
+    def convolve1d_reflect(self, x, weights):
+        """scipy.ndimage.convolve1d(x, weights) (mode "reflect", odd kernel) on the device."""
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        w = np.ascontiguousarray(weights, dtype=np.float64)
+        out = np.empty_like(x)
+        self._ck(self.lib.sd_convolve1d_reflect(self.h, int(x.size), L.ptr(x), int(w.size), L.ptr(w), L.ptr(out)))
+        self.synchronize()
+        return out
+
     # ------------------------------------------------------------------ measurement
     def bench_dfma(self, iters=4096):
         t = C.c_double()

@@ -489,7 +489,7 @@ def _calc_alphas_depth_sharded(stellar_plasma, stellar_model, srf, opacity_confi
     plasma_r = DepthSlicedPlasma.of(stellar_plasma, idx)
     set_device_atmosphere(ctx_op, model_r, plasma_r)
     ctx_op.set_grid(nus)
-    n_lines, mol = _device_opacity_pass(ctx_op, plasma_r, model_r, nus_q, opacity_config, store_components)
+    n_lines, mol = _device_opacity_pass(ctx_op, plasma_r, model_r, nus_q, opacity_config, store_components, collective=True)
     dev = torch.device("cuda", ctx.device)
     stream = torch.cuda.current_stream(dev)
 

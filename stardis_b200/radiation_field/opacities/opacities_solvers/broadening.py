@@ -101,11 +101,22 @@ def upload_lines_and_broaden(ctx, lines, alphas_array, masses, stellar_model, st
         alphas_array = upload_rows_striped(alphas_array, torch.device("cuda", ctx.device))
         if hasattr(alphas_array, "data_ptr"):
             torch.cuda.current_stream(ctx.device).synchronize()  # the gather ran on torch's stream, K1 runs on ctx's
-    ctx.set_lines(get("nu"), alphas_array, mass=masses, atomic_number=get("atomic_number"), ion_number=get("ion_number"),
-                  ionization_energy=get("ionization_energy"), level_energy_upper=get("level_energy_upper"),
-                  level_energy_lower=get("level_energy_lower"), A_ul=get("A_ul"),
-                  stark=get("stark") if vald and has("stark") else None,
-                  waals=get("waals") if vald and has("waals") else None)
+    cols = dict(nu=get("nu"), mass=masses, atomic_number=np.asarray(get("atomic_number"), dtype=np.int64),
+                ion_number=np.asarray(get("ion_number"), dtype=np.int64), ionization_energy=get("ionization_energy"),
+                level_energy_upper=get("level_energy_upper"), level_energy_lower=get("level_energy_lower"), A_ul=get("A_ul"))
+    if vald and has("stark") and has("waals"):
+        cols.update(stark=get("stark"), waals=get("waals"))
+    if collective:  # every rank holds the same table: each uploads 1/world of it, NVLink does the rest
+        import torch
+
+        from ....distributed import upload_columns_striped
+
+        cols = upload_columns_striped({k: np.asarray(v) for k, v in cols.items()}, torch.device("cuda", ctx.device))
+        torch.cuda.current_stream(ctx.device).synchronize()  # the gather ran on torch's stream, K1 runs on ctx's
+    ctx.set_lines(cols["nu"], alphas_array, mass=cols["mass"], atomic_number=cols["atomic_number"],
+                  ion_number=cols["ion_number"], ionization_energy=cols["ionization_energy"],
+                  level_energy_upper=cols["level_energy_upper"], level_energy_lower=cols["level_energy_lower"],
+                  A_ul=cols["A_ul"], stark=cols.get("stark"), waals=cols.get("waals"))
     if strength is not None:
         strength.run(ctx)
     ctx.calc_broadening(flags)
@@ -172,6 +183,29 @@ def calculate_molecule_broadening(lines, stellar_model, stellar_plasma, broadeni
     return gammas, dws
 
 
-def rotation_broadening(*args, **kwargs):
-    """Out of the hot-path scope (post-hoc spectrum convolution, broadening.py:824-877)."""
-    raise NotImplementedError("rotation_broadening is outside the B200 hot path; use the reference implementation")
+def rotation_broadening(velocity_per_pix, wavelength, flux, v_rot=None, limb_darkening=0.6):
+    """Convolve a spectrum with a rotational broadening profile (broadening.py:824-877; only accurate for a constant
+    velocity per pixel).  The Gray profile -- 2 (1 - eps) sqrt(1 - (v / v_rot)^2) + (pi / 2) eps (1 - (v / v_rot)^2),
+    normalised -- is formed on the host (O(v_rot / velocity_per_pix) numbers); the convolution with the reference's
+    ``scipy.ndimage.convolve1d`` semantics (reflecting boundary) runs on the device.  Returns (wavelength, fluxes
+    [erg/s/cm2/AA]); a rotational velocity below 1e-5 km/s returns the inputs unchanged."""
+    def to_kms(q):
+        if not hasattr(q, "to"):
+            return float(q)
+        try:
+            return float(q.to(u.km_s).value)     # stardis_b200.units.Quantity
+        except Exception:
+            return float(q.to("km/s").value)     # astropy Quantity
+
+    v_pix = to_kms(velocity_per_pix)
+    v = 0.0 if v_rot is None else to_kms(v_rot)
+    if np.abs(v) < 1e-5:
+        return wavelength, flux
+    v_rot_by_c = np.maximum(1e-5, np.abs(v)) / (2.99792458e10 * 1e-5)
+    half = int(np.round(v / v_pix))
+    profile_velocity = np.linspace(-half, half, 2 * half + 1) * v_pix
+    profile = np.maximum(0.0, 1.0 - (profile_velocity / v) ** 2)
+    rotational = (2 * (1 - limb_darkening) * profile ** 0.5 + 0.5 * np.pi * limb_darkening * profile) / (
+        np.pi * v_rot_by_c * (1 - limb_darkening / 3))
+    out = default_context().convolve1d_reflect(u.values_of(flux), rotational / rotational.sum())
+    return wavelength, u.Quantity(out, "erg/s/cm2/AA")

@@ -19,7 +19,7 @@ def test_depth_views_slice_every_per_depth_table():
     model, plasma = w["model"], w["plasma"]
     D = model.no_of_depth_points
     idx = depth_indices(D, 1, 4)
-    assert list(idx[:3]) == [1, 5, 9] and sum(len(depth_indices(D, r, 4)) for r in range(4)) == D
+    assert list(idx[:3]) == [1, 6, 9] and sorted(np.concatenate([depth_indices(D, r, 4) for r in range(4)])) == list(range(D))
     m, p = DepthSlicedModel(model, idx), DepthSlicedPlasma.of(plasma, idx)
     assert m.no_of_depth_points == len(idx) and p is DepthSlicedPlasma.of(plasma, idx)
     np.testing.assert_array_equal(u.values_of(m.temperatures), u.values_of(model.temperatures)[idx])
@@ -38,7 +38,8 @@ WORKER = textwrap.dedent("""
     import os, sys
     import numpy as np, torch, torch.distributed as dist
     sys.path.insert(0, os.environ["SD_ROOT"])
-    from stardis_b200.distributed import (all_shards, allgather_depth_columns, depth_indices, exchange_depth_to_nu)
+    from stardis_b200.distributed import (all_shards, allgather_depth_columns, depth_indices, exchange_depth_to_nu,
+                                          upload_columns_striped)
     dist.init_process_group("gloo")
     rank, world = dist.get_rank(), dist.get_world_size()
     D, N, Ln = 7, 101, 13
@@ -53,6 +54,11 @@ WORKER = textwrap.dedent("""
     table = np.arange(Ln * D, dtype=np.float64).reshape(Ln, D)
     cols = allgather_depth_columns(torch.from_numpy(np.ascontiguousarray(table[:, idx])), D)
     np.testing.assert_array_equal(cols.numpy(), table)
+    cols = dict(nu=np.linspace(1.0, 2.0, 37), Z=np.arange(37, dtype=np.int64) % 5, A=np.geomspace(1e6, 1e9, 37))
+    got = upload_columns_striped(cols, torch.device("cpu"))
+    for k, v in cols.items():
+        assert got[k].dtype == (torch.float64 if v.dtype.kind == "f" else torch.int64)
+        np.testing.assert_array_equal(got[k].numpy(), v)
     dist.destroy_process_group()
     print("ok", rank)
 """)

@@ -170,3 +170,16 @@ def test_alpha_line_vald_oracle_vs_reference_golden(oracle, kind):
     for col in ("atomic_number", "ion_number", "nu", "level_energy_lower", "level_energy_upper", "A_ul", "ionization_energy"):
         np.testing.assert_allclose(lines[col], g[f"{kind}_lines_{col}"], rtol=1e-14, err_msg=col)
     assert (kind == "long") == (alphas.shape[0] < (ll["atomic_number"] <= 28).sum())  # auto-ionising lines dropped (long only)
+
+
+def test_molecule_plasma_restatement_vs_reference_golden(oracle):
+    """oracle.molecule_number_density / molecule_partition_function / stimulated emission + AlphaLine against the
+    reference's unmodified classes (plasma/molecules.py:16-191, plasma/base.py:130-175) run through ref_shim_plasma."""
+    g = golden("plasma_golden.npz")
+    dens, ion_map = oracle.molecule_number_density(g["mol_ion1"], g["mol_ion2"], g["mol_eq"], g["mol_t_grid"], g["mol_ion_index"],
+                                                   g["mol_ion_number_density"], g["T"])
+    np.testing.assert_allclose(dens, g["mol_density"], rtol=1e-13, atol=1e-300)
+    np.testing.assert_array_equal(ion_map, g["mol_ion_map"])
+    assert (dens[list(g["mol_names"]).index("OH-")] == 0).all() and (dens > 0).any()
+    np.testing.assert_allclose(oracle.molecule_partition_function(g["mol_pf"], g["mol_t_grid"], g["T"]), g["mol_partition"], rtol=1e-15)
+    np.testing.assert_allclose(oracle.alpha_line(g["al_level_number_density"], g["al_lower"], g["al_sef"], g["al_f_lu"]), g["al_alpha"], rtol=1e-14)
