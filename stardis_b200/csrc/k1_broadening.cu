@@ -245,8 +245,8 @@ __global__ void __launch_bounds__(256) k_build_records(int64_t L, int D, int64_t
                                                        LineRec *__restrict__ rec, PairWin *__restrict__ win,
                                                        uint8_t *__restrict__ win_cls,
                                                        FarGeom fg, unsigned long long *__restrict__ stats) {
-    int64_t g = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    bool active = g < L * D;
+    const unsigned g = blockIdx.x * blockDim.x + threadIdx.x;  // L * D < 2^31 (checked by sd_set_lines)
+    bool active = g < (unsigned)(L * D);
     unsigned nonempty = 0, wide = 0, zero_dw = 0;
     int rad_k[SD_FAR_LEVELS];
 #pragma unroll
@@ -254,8 +254,8 @@ __global__ void __launch_bounds__(256) k_build_records(int64_t L, int D, int64_t
     bool e_lo = false, e_hi = false;
     unsigned long long key_lo = 0, key_hi = 0;
     if (active) {
-        int64_t l = g / D;
-        int d = (int)(g - l * D);
+        const unsigned l = g / (unsigned)D;
+        const int d = (int)(g - l * (unsigned)D);
         double gam = gamma_cols > 1 ? gammas[g] : gammas[l];  // base.py:547-551
         double dw = dws[g];
         double a = alpha[g];
@@ -302,7 +302,7 @@ __global__ void __launch_bounds__(256) k_build_records(int64_t L, int D, int64_t
                 int rad = 0;
                 const int tile = fg.tile[k], n_tiles = fg.n_tiles[k];
                 if (fc && hi - lo >= tile) {
-                    int tc = idx / tile;
+                    int tc = idx >> fg.tile_shift[k];  // tiles hold 2^tile_shift pixels
                     if (tc >= n_tiles) tc = n_tiles - 1;
                     int a_, b_;
                     near_interval(fg.geom[k], n_tiles, tc, r.nu, dw, y, a_, b_);
@@ -324,30 +324,55 @@ __global__ void __launch_bounds__(256) k_build_records(int64_t L, int D, int64_t
         wide = (hi > lo) && cls > 0;
         zero_dw = (hi > lo) && (dw == 0.0);
     }
+    // ---- block-level aggregation: a handful of global counters are shared by all 65 000 blocks of this kernel, and one
+    // atomic per WARP on each of them serialised in L2 (ncu: the kernel was waiting there, not on memory or math)
+    __shared__ int s_rad[SD_FAR_LEVELS];
+    __shared__ unsigned s_cnt[3];
+    __shared__ unsigned s_edges[256 / 32];
+    __shared__ unsigned long long s_base;
+    const unsigned lane = threadIdx.x & 31, wid = threadIdx.x >> 5, lt = (1u << lane) - 1u;
+    if (threadIdx.x < SD_FAR_LEVELS) s_rad[threadIdx.x] = 0;
+    if (threadIdx.x < 3) s_cnt[threadIdx.x] = 0;
+    __syncthreads();
+    const unsigned m_lo = __ballot_sync(0xffffffffu, e_lo), m_hi = __ballot_sync(0xffffffffu, e_hi);
+    const int n_lo = __popc(m_lo), n_hi = __popc(m_hi);
     if (fg.enabled) {
-        const unsigned lane = threadIdx.x & 31, lt = (1u << lane) - 1u;
 #pragma unroll
         for (int k = 0; k < SD_FAR_LEVELS; k++) {
             int m = rad_k[k];
             for (int o2 = 16; o2; o2 >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o2));
-            if (lane == 0 && m > 0) atomicMax(&fg.near_rad[k], m);
+            if (lane == 0 && m > 0) atomicMax(&s_rad[k], m);
         }
-        // warp-aggregated append of the edge keys (order irrelevant: the keys are sorted into a total order)
-        const unsigned m_lo = __ballot_sync(0xffffffffu, e_lo), m_hi = __ballot_sync(0xffffffffu, e_hi);
-        const int n_lo = __popc(m_lo), n_hi = __popc(m_hi);
-        unsigned long long base = 0;
-        if (lane == 0 && n_lo + n_hi) base = atomicAdd(fg.edge_count, (unsigned long long)(n_lo + n_hi));
-        base = __shfl_sync(0xffffffffu, base, 0);
+        if (lane == 0) s_edges[wid] = (unsigned)(n_lo + n_hi);
+    }
+    const unsigned ne_w = __popc(__ballot_sync(0xffffffffu, nonempty));
+    const unsigned wd_w = __popc(__ballot_sync(0xffffffffu, wide));
+    const unsigned zd_w = __popc(__ballot_sync(0xffffffffu, zero_dw));
+    if (lane == 0) {
+        if (ne_w) atomicAdd(&s_cnt[0], ne_w);
+        if (wd_w) atomicAdd(&s_cnt[1], wd_w);
+        if (zd_w) atomicAdd(&s_cnt[2], zd_w);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        if (s_cnt[0]) atomicAdd(&stats[4], (unsigned long long)s_cnt[0]);
+        if (s_cnt[1]) atomicAdd(&stats[5], (unsigned long long)s_cnt[1]);
+        if (s_cnt[2]) atomicAdd(&stats[6], (unsigned long long)s_cnt[2]);
+        if (fg.enabled) {
+            // the running maximum is reached early: most blocks find nothing to raise (racy read, monotone update)
+            for (int k = 0; k < SD_FAR_LEVELS; k++)
+                if (s_rad[k] > *(volatile int *)&fg.near_rad[k]) atomicMax(&fg.near_rad[k], s_rad[k]);
+            unsigned tot = 0;
+            for (int w2 = 0; w2 < 256 / 32; w2++) { const unsigned c = s_edges[w2]; s_edges[w2] = tot; tot += c; }
+            s_base = tot ? atomicAdd(fg.edge_count, (unsigned long long)tot) : 0ull;
+        }
+    }
+    __syncthreads();
+    if (fg.enabled) {
+        // append of the edge keys (order irrelevant: the keys are sorted into a total order)
+        const unsigned long long base = s_base + s_edges[wid];
         if (e_lo) fg.edge_out[base + __popc(m_lo & lt)] = key_lo;
         if (e_hi) fg.edge_out[base + n_lo + __popc(m_hi & lt)] = key_hi;
-    }
-    unsigned ne_w = __popc(__ballot_sync(0xffffffffu, nonempty));
-    unsigned wd_w = __popc(__ballot_sync(0xffffffffu, wide));
-    unsigned zd_w = __popc(__ballot_sync(0xffffffffu, zero_dw));
-    if ((threadIdx.x & 31) == 0) {
-        if (ne_w) atomicAdd(&stats[4], (unsigned long long)ne_w);
-        if (wd_w) atomicAdd(&stats[5], (unsigned long long)wd_w);
-        if (zd_w) atomicAdd(&stats[6], (unsigned long long)zd_w);
     }
 }
 
@@ -466,6 +491,9 @@ int sd_k2_prepare(sd_ctx *c) {
     FarGeom &fg = c->far_geom;
     for (int k = 0; k < SD_FAR_LEVELS; k++) {
         fg.tile[k] = (32 * c->k2_NW * c->k2_P) << (SD_FAR_SHIFT * k);
+        fg.tile_shift[k] = 0;
+        while ((1 << fg.tile_shift[k]) < fg.tile[k]) fg.tile_shift[k]++;
+        SD_CHECK(c, (1 << fg.tile_shift[k]) == fg.tile[k], SD_ERR_STATE, "tile sizes must be powers of two");
         fg.n_tiles[k] = (int)((c->N + fg.tile[k] - 1) / fg.tile[k]);
         SD_CHECK(c, fg.n_tiles[k] < 65535, SD_ERR_ARG, "grid too long for 16-bit tile indices");
         SD_TRY(sd_ensure(c, c->tile_geom[k], sizeof(double) * 2 * fg.n_tiles[k]));

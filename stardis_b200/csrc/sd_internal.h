@@ -49,7 +49,8 @@ constexpr int SD_FC_CLASS = SD_NCLS - 1;  // class of the "far-capable" pairs (w
 
 // geometry of the far-field tile hierarchy and the per-pair tables that drive it, passed by value to the kernels
 struct FarGeom {
-    int tile[SD_FAR_LEVELS];            // pixels per tile
+    int tile[SD_FAR_LEVELS];            // pixels per tile (powers of two)
+    int tile_shift[SD_FAR_LEVELS];      // log2 of them
     int n_tiles[SD_FAR_LEVELS];         // global number of tiles
     const double *geom[SD_FAR_LEVELS];  // {centre frequency, half-width} per tile
     int enabled;                        // far field on (PairWin::near is filled, edge lists exist)

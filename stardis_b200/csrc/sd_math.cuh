@@ -187,6 +187,30 @@ SD_HD double exp_cos_small(double a, double b) {
     return ea * c;
 }
 
+// exp(a) for |a| < 700 (NaN in -> NaN out), the exp of exp_cos_small on its own: 2^n e^r, |r| <= ln2/2, Taylor to r^13
+// (truncation 4e-18) -- ~20 instructions instead of the library routine's ~30 with its range checks.  The formal solver
+// spends 38 % of its instructions in exp(-tau) and in the Planck function's exponential (ncu, round 2).
+SD_HD double exp_mid(double a) {
+    const double nf = rint(a * W4K(LOG2E));
+    double r = fma(-nf, W4K(LN2_HI), a);
+    r = fma(-nf, W4K(LN2_LO), r);
+    double p = W4K(E13);
+    p = fma(p, r, W4K(E12));
+    p = fma(p, r, W4K(E11));
+    p = fma(p, r, W4K(E10));
+    p = fma(p, r, W4K(E9));
+    p = fma(p, r, W4K(E8));
+    p = fma(p, r, W4K(E7));
+    p = fma(p, r, W4K(E6));
+    p = fma(p, r, W4K(E5));
+    p = fma(p, r, W4K(E4));
+    p = fma(p, r, W4K(E3));
+    p = fma(p, r, 0.5);
+    p = fma(p, r, 1.0);
+    p = fma(p, r, 1.0);
+    return p * pow2i((int)nf);
+}
+
 SD_HD double region4_re(double x, double y) {
     double tr = y, ti = -x;
     double ur = fma(y, y, -(x * x)), ui = -(x + x) * y;
@@ -357,7 +381,8 @@ SD_HD void line_window(long long idx, long long N, double gamma, double dw, doub
 // ---------------------------------------------------------------------------- formal solver
 SD_HD double planck(double nu, double T) {  // source_functions/blackbody.py:31-35
     double pre = (2.0 * H_CGS * nu * nu * nu) / (C_CGS * C_CGS);
-    return pre / (exp((H_CGS * nu) / (KB_CGS * T)) - 1.0);
+    const double a = (H_CGS * nu) / (KB_CGS * T);
+    return pre / (((a > -700.0 && a < 700.0) ? exp_mid(a) : exp(a)) - 1.0);
 }
 SD_HD void rt_weights(double tau, double &w0, double &w1, double &w2) {  // radiation_field_solvers/base.py:6-47
     if (tau < 5e-4) {
@@ -365,7 +390,7 @@ SD_HD void rt_weights(double tau, double &w0, double &w1, double &w2) {  // radi
         w1 = tau * tau * (0.5 - tau / 3.0);
         w2 = tau * tau * tau * (1.0 / 3.0 - tau / 4.0);
     } else if (tau < 50.0) {
-        double e = exp(-tau);
+        double e = exp_mid(-tau);  // 5e-4 <= tau < 50
         w0 = 1.0 - e;
         w1 = w0 - tau * e;
         w2 = 2.0 * w1 - tau * tau * e;

@@ -358,7 +358,7 @@ def calc_alphas(stellar_plasma, stellar_model, stellar_radiation_field, opacity_
     set_device_atmosphere(ctx, stellar_model, stellar_plasma)
     ctx.set_grid(nus, p0, p1)
     n_lines, mol = _device_opacity_pass(ctx, stellar_plasma, stellar_model, nus_q, opacity_config, store_components,
-                                        collective=getattr(srf, "shard", None) is not None)
+                                        collective="nu" if getattr(srf, "shard", None) is not None else False)
     ctx.owner = getattr(srf, "token", None)
 
     def shard_array(which):
@@ -489,7 +489,7 @@ def _calc_alphas_depth_sharded(stellar_plasma, stellar_model, srf, opacity_confi
     plasma_r = DepthSlicedPlasma.of(stellar_plasma, idx)
     set_device_atmosphere(ctx_op, model_r, plasma_r)
     ctx_op.set_grid(nus)
-    n_lines, mol = _device_opacity_pass(ctx_op, plasma_r, model_r, nus_q, opacity_config, store_components, collective=True)
+    n_lines, mol = _device_opacity_pass(ctx_op, plasma_r, model_r, nus_q, opacity_config, store_components, collective="depth")
     dev = torch.device("cuda", ctx.device)
     stream = torch.cuda.current_stream(dev)
 

@@ -86,14 +86,16 @@ def _line_columns(lines):
 
 def upload_lines_and_broaden(ctx, lines, alphas_array, masses, stellar_model, stellar_plasma, flags, collective=False):
     """Upload a (sorted, range-selected) line table and run K1.  ``lines``: DataFrame or ColumnarLines.
-    ``collective``: this is a sharded multi-GPU run in which every rank holds the same table -- the (L, D) strengths
-    then travel over PCIe once in total and reach the other ranks over NVLink (``distributed.upload_rows_striped``)."""
+    ``collective``: this is a multi-GPU run in which every rank is here with the same per-line columns: each rank uploads
+    1/world of them and NVLink does the rest (``distributed.upload_columns_striped``).  "nu": the (L, D) strengths are
+    identical on every rank as well (nu sharding) and travel the same way (``distributed.upload_rows_striped``); "depth":
+    every rank holds its own depth columns of that table (depth sharding), which therefore goes up as it is."""
     get, has = _line_columns(lines)
     vald = bool(flags & L.VALD)
     strength = getattr(lines, "strength", None)
     if strength is not None:
         alphas_array = None  # O(L) producer inputs travel instead of the (L, D) table; the device fills it (8f rank 1)
-    if collective and alphas_array is not None:
+    if collective == "nu" and alphas_array is not None:
         import torch
 
         from ....distributed import upload_rows_striped

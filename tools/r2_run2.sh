@@ -1,7 +1,7 @@
 #!/bin/bash
 # Round 2: validate the new K1 / preparation pass (tests), 1-GPU and 2-GPU step times.
 mkdir -p gpurun_out
-( time python -m pytest tests -m gpu -q -x 2>&1 | tail -15 ) > gpurun_out/r2b_gpu_tests.log 2>&1
+( time python -m pytest tests -m gpu -q -x 2>&1 | tail -80 ) > gpurun_out/r2b_gpu_tests.log 2>&1
 tail -6 gpurun_out/r2b_gpu_tests.log
 ( time python bench.py --steps 10 --warmup 3 --no-direct --cpu-kind port --cpu-seconds 4 ) > gpurun_out/r2b_bench_1gpu.log 2>&1
 python tools/bench_summary.py gpurun_out/r2b_bench_1gpu.log
