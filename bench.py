@@ -481,7 +481,7 @@ def run_b200_arm(args):
         r0, r1 = 0, -(-len(sel) * len(hp.didx) // D)  # this rank's depth columns of the (L, D) table
     h2d = int(pinned_nus.numel() * 8 + sum(np.asarray(getattr(sel, k)).nbytes for k in
               ("nu", "mass", "atomic_number", "ion_number", "ionization_energy", "level_energy_upper",
-               "level_energy_lower", "A_ul")) // world + 3 * D * 8 +  # line columns: 1/world per rank, rest over NVLink
+               "level_energy_lower", "A_ul")) + 3 * D * 8 +
               (sel.strength.nbytes() if sel.strength is not None else (r1 - r0) * D * 8))
     d2h = int(W * 8)
 

@@ -45,7 +45,7 @@ constexpr int FAR_CH = 1024;                // candidates per cooperative scan c
 struct __align__(16) FarRec { double nu, dw, y, K; };  // = the first 32 bytes of LineRec
 static_assert((SD_FAR_K + 1) % 3 == 0, "the series length is tested every third term");
 static_assert(WARPS == (1 << SD_FAR_SHIFT), "k_far_coeffs maps the warps of a CTA to the children of a tile");
-constexpr size_t FAR_SMEM = (size_t)(FAR_CH + WARPS * 64) * sizeof(FarRec) + FAR_CH;
+constexpr size_t FAR_SMEM = (size_t)FAR_CH * sizeof(FarRec) + FAR_CH;
 
 struct __align__(16) WEntry {
     // far-wing path (48 B)
@@ -225,9 +225,8 @@ __global__ void __launch_bounds__(THREADS) k_far_coeffs(LineArgs a, int lev, int
     constexpr int K1 = SD_FAR_K + 1;
     __shared__ int s_ja[3], s_jb[3];
     extern __shared__ __align__(16) unsigned char far_smem[];
-    FarRec *const s_rec = reinterpret_cast<FarRec *>(far_smem);                        // [FAR_CH] staged records of the chunk
-    FarRec *const s_queue = s_rec + FAR_CH;                                            // [WARPS][64] per-warp queues
-    unsigned char *const s_mask = reinterpret_cast<unsigned char *>(s_queue + WARPS * 64);  // [FAR_CH] child masks
+    FarRec *const s_rec = reinterpret_cast<FarRec *>(far_smem);                        // [FAR_CH] dense records of the chunk
+    unsigned char *const s_mask = reinterpret_cast<unsigned char *>(s_rec + FAR_CH);   // [FAR_CH] their child masks
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int d = blockIdx.y;
     const int tile_px = a.fg.tile[lev];
@@ -319,18 +318,32 @@ __global__ void __launch_bounds__(THREADS) k_far_coeffs(LineArgs a, int lev, int
         }
     };
 
-    FarRec *const q = s_queue + warp * 64;
-    int qn = 0;  // queue length of this warp
+    // Per chunk of FAR_CH candidates:
+    //   test     a thread gathers the window record of its candidates ONCE and tests it against all eight children;
+    //   compact  the candidates wanted by ANY child (of the whole group, launched or not: the list must not depend on
+    //            the shard) are packed densely, in list order, into shared memory: record (cp.async) + child mask.  Far
+    //            from the group every covering pair is wanted by all eight children, near it by five or six, so the
+    //            dense list is (nearly) the list of every child;
+    //   expand   every warp walks the dense list 32 entries at a time, one pair per lane, skipping the few entries whose
+    //            mask lacks its child -- no per-warp queue, no ballots, no copies (they were a quarter of the kernel's
+    //            instructions when every warp compacted its own list).
+    constexpr int ROUNDS = FAR_CH / THREADS;
+    constexpr int SEGS = ROUNDS * WARPS;       // (round, warp) segments of 32 candidates, in list order
+    static_assert(SEGS == 32, "one lane per segment in the offset scan");
+    __shared__ int s_cnt[SEGS];
     for (int src = 0; src < 3; src++) {
         const int ja = s_ja[src], jb = s_jb[src];
         for (int base = ja; base < jb; base += FAR_CH) {
-            // ---- scan: one gather per candidate, acceptance mask over the eight children
+            // ---- test
+            unsigned mk[ROUNDS];
+            int ll[ROUNDS], rk[ROUNDS];
 #pragma unroll
-            for (int r = 0; r < FAR_CH / THREADS; r++) {
+            for (int r = 0; r < ROUNDS; r++) {
                 const int idx = r * THREADS + tid, j = base + idx;
                 unsigned mask = 0;
+                int l = 0;
                 if (j < jb) {
-                    const int l = (src == 0) ? list_d[j] : (int)(a.fg.edge_keys[j] & lmask);
+                    l = (src == 0) ? list_d[j] : (int)(a.fg.edge_keys[j] & lmask);
                     const PairWin pw = load_win(a.win + drow + l);
                     const int lo = pw.lo, hi = pw.hi;
                     bool okp = true;
@@ -346,50 +359,54 @@ __global__ void __launch_bounds__(THREADS) k_far_coeffs(LineArgs a, int lev, int
                         const unsigned near = near_of(pw, lev);
 #pragma unroll
                         for (int cc = 0; cc < WARPS; cc++) {
-                            const int64_t c0 = (int64_t)(child0 + cc) * tile_px;
+                            const int tcc = child0 + cc;
+                            const int64_t c0 = (int64_t)tcc * tile_px;
                             const int64_t c1 = (c0 + tile_px < a.N) ? c0 + tile_px : a.N;
-                            if (pair_is_far(lo, hi, near, c0, c1, child0 + cc)) mask |= 1u << cc;
+                            if (tcc < a.fg.n_tiles[lev] && pair_is_far(lo, hi, near, c0, c1, tcc)) mask |= 1u << cc;
                         }
-                        mask &= valid;
-                    }
-                    if (mask) {
-                        const unsigned dst = (unsigned)__cvta_generic_to_shared(s_rec + idx);
-                        const LineRec *srcp = a.rec + drow + l;
-                        asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(srcp) : "memory");
-                        asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst + 16u),
-                                     "l"(reinterpret_cast<const char *>(srcp) + 16) : "memory");
                     }
                 }
-                s_mask[idx] = (unsigned char)mask;
+                const unsigned nz = __ballot_sync(0xffffffffu, mask != 0);
+                mk[r] = mask; ll[r] = l; rk[r] = __popc(nz & lt_mask);
+                if (lane == 0) s_cnt[r * WARPS + warp] = __popc(nz);
+            }
+            __syncthreads();
+            // ---- compact: exclusive offsets of the (round, warp) segments, one segment per lane
+            const int cnt_l = s_cnt[lane];
+            int incl = cnt_l;
+#pragma unroll
+            for (int o2 = 1; o2 < 32; o2 <<= 1) {
+                const int t = __shfl_up_sync(0xffffffffu, incl, o2);
+                if (lane >= o2) incl += t;
+            }
+            const int n_dense = __shfl_sync(0xffffffffu, incl, 31);
+#pragma unroll
+            for (int r = 0; r < ROUNDS; r++) {
+                const int seg = r * WARPS + warp;
+                const int off = __shfl_sync(0xffffffffu, incl - cnt_l, seg);
+                if (mk[r]) {
+                    const int pos = off + rk[r];
+                    const unsigned dst = (unsigned)__cvta_generic_to_shared(s_rec + pos);
+                    const LineRec *srcp = a.rec + drow + ll[r];
+                    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(srcp) : "memory");
+                    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst + 16u),
+                                 "l"(reinterpret_cast<const char *>(srcp) + 16) : "memory");
+                    s_mask[pos] = (unsigned char)(mk[r] & valid);
+                }
             }
             asm volatile("cp.async.commit_group;" ::: "memory");
             asm volatile("cp.async.wait_group 0;" ::: "memory");
             __syncthreads();
-            // ---- expand: this warp's child, in list order
-            const int n_here = (jb - base < FAR_CH) ? jb - base : FAR_CH;
-            for (int i0 = 0; i0 < n_here && tile_ok; i0 += 32) {
-                const int idx = i0 + lane;
-                const bool acc = (idx < n_here) && ((s_mask[idx] >> warp) & 1u);
-                const unsigned m = __ballot_sync(0xffffffffu, acc);
-                if (!m) continue;
-                if (acc) q[qn + __popc(m & lt_mask)] = s_rec[idx];
-                qn += __popc(m);
-                __syncwarp();
-                if (qn >= 32) {
-                    expand(true, q[lane]);
-                    const int rem = qn - 32;
-                    FarRec v;
-                    if (lane < rem) v = q[32 + lane];
-                    __syncwarp();
-                    if (lane < rem) q[lane] = v;
-                    qn = rem;
-                    __syncwarp();
-                }
+            // ---- expand: this warp's child
+            for (int i0 = 0; i0 < n_dense && tile_ok; i0 += 32) {
+                const int i = i0 + lane;
+                const bool have = (i < n_dense) && ((s_mask[i] >> warp) & 1u);
+                if (!__any_sync(0xffffffffu, have)) continue;
+                expand(have, s_rec[i < n_dense ? i : 0]);
             }
-            __syncthreads();  // the chunk buffers are overwritten by the next scan
+            __syncthreads();  // the chunk buffers are overwritten by the next chunk
         }
     }
-    if (qn > 0) expand(lane < qn, q[lane < qn ? lane : 0]);
     // deterministic reduction: lanes by shuffle (every lane ends up with the sum; lane k keeps coefficient k)
     double mine = 0.0;
 #pragma unroll

@@ -86,10 +86,10 @@ def _line_columns(lines):
 
 def upload_lines_and_broaden(ctx, lines, alphas_array, masses, stellar_model, stellar_plasma, flags, collective=False):
     """Upload a (sorted, range-selected) line table and run K1.  ``lines``: DataFrame or ColumnarLines.
-    ``collective``: this is a multi-GPU run in which every rank is here with the same per-line columns: each rank uploads
-    1/world of them and NVLink does the rest (``distributed.upload_columns_striped``).  "nu": the (L, D) strengths are
-    identical on every rank as well (nu sharding) and travel the same way (``distributed.upload_rows_striped``); "depth":
-    every rank holds its own depth columns of that table (depth sharding), which therefore goes up as it is."""
+    ``collective``: this is a multi-GPU run in which every rank is here with the same per-line columns.  "nu": the (L, D)
+    strengths are identical on every rank as well (nu sharding): each rank uploads 1/world of the rows and NVLink does the
+    rest (``distributed.upload_rows_striped``); "depth": every rank holds its own depth columns of that table (depth
+    sharding), which therefore goes up as it is."""
     get, has = _line_columns(lines)
     vald = bool(flags & L.VALD)
     strength = getattr(lines, "strength", None)
@@ -108,13 +108,9 @@ def upload_lines_and_broaden(ctx, lines, alphas_array, masses, stellar_model, st
                 level_energy_upper=get("level_energy_upper"), level_energy_lower=get("level_energy_lower"), A_ul=get("A_ul"))
     if vald and has("stark") and has("waals"):
         cols.update(stark=get("stark"), waals=get("waals"))
-    if collective:  # every rank holds the same table: each uploads 1/world of it, NVLink does the rest
-        import torch
-
-        from ....distributed import upload_columns_striped
-
-        cols = upload_columns_striped({k: np.asarray(v) for k, v in cols.items()}, torch.device("cuda", ctx.device))
-        torch.cuda.current_stream(ctx.device).synchronize()  # the gather ran on torch's stream, K1 runs on ctx's
+    # (The 24 MB of per-line columns go up from every rank directly.  Striping them over the ranks as well
+    # (distributed.upload_columns_striped) was measured SLOWER on 2 GPUs -- 30.8 -> 37.8 ms per end-to-end step: the
+    # staging copy, the extra collective and its stream synchronisation cost more than the PCIe time they save.)
     ctx.set_lines(cols["nu"], alphas_array, mass=cols["mass"], atomic_number=cols["atomic_number"],
                   ion_number=cols["ion_number"], ionization_energy=cols["ionization_energy"],
                   level_energy_upper=cols["level_energy_upper"], level_energy_lower=cols["level_energy_lower"],
