@@ -206,6 +206,7 @@ int sd_raytrace(sd_ctx *ctx, int32_t n_theta, const double *ray_ds, const double
 #define SD_BUF_F_NU 6            /* (D, W) */
 #define SD_BUF_I_NUS 7           /* (D, W, n_theta) */
 #define SD_BUF_LINE_STRENGTH 8   /* (L, D) alpha_line of the line table (uploaded or sd_calc_alpha_line_vald) */
+#define SD_BUF_NUS 9             /* (1, N) the global frequency grid as uploaded by sd_set_grid */
 #define SD_BUF_SOURCE0 16        /* + source index: (D, W) */
 /* Copy a result into dst (host or device); count = number of doubles, must equal the buffer size. */
 int sd_get(sd_ctx *ctx, int32_t which, double *dst, int64_t count);

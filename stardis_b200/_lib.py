@@ -17,6 +17,7 @@ SD_OK = 0
 LINEAR_STARK, QUADRATIC_STARK, VAN_DER_WAALS, RADIATION, VALD = 1, 2, 4, 8, 16
 BUF_GAMMAS, BUF_DOPPLER, BUF_ALPHA_LINE, BUF_ALPHA_MOLECULE, BUF_TOTAL, BUF_F_NU, BUF_I_NUS = 1, 2, 3, 4, 5, 6, 7
 BUF_LINE_STRENGTH = 8
+BUF_NUS = 9
 BUF_SOURCE0 = 16
 SRC_BF, SRC_FF, SRC_RAYLEIGH, SRC_ELECTRON, SRC_TABLE0 = 0, 1, 2, 3, 4
 MAX_TABLES = 8

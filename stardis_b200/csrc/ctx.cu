@@ -470,6 +470,9 @@ static int find_buffer(sd_ctx *c, int which, DevBuf **b, int64_t *rows, int64_t 
         case SD_BUF_LINE_STRENGTH:
             SD_CHECK(c, c->have_alpha_line, SD_ERR_STATE, "line strengths not set");
             *b = &c->l_alpha; *rows = c->L; *cols = c->D; return SD_OK;
+        case SD_BUF_NUS:
+            SD_CHECK(c, c->N > 0, SD_ERR_STATE, "no grid");
+            *b = &c->nus; *rows = 1; *cols = c->N; return SD_OK;
         case SD_BUF_TOTAL:
             SD_CHECK(c, c->have_total, SD_ERR_STATE, "total opacity not computed");
             *b = &c->total; *rows = c->D; *cols = W; return SD_OK;

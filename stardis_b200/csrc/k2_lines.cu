@@ -622,8 +622,31 @@ __global__ void __launch_bounds__(32 * NW, MINB) k_lines(LineArgs a) {
                     // writes of the warp (independent thread scheduling gives no lock-step guarantee after the divergent
                     // exact path; compute-sanitizer racecheck flagged exactly this line)
                     __syncwarp();
+                } else if (e2.lo <= ws && e2.hi >= we && we - ws == SPAN) {
+                    // long overlap, window covers the whole span (a near-field pair whose core lies in this span, the
+                    // common case): register slots without any window logic
+#pragma unroll
+                    for (int p = 0; p < P; p++) {
+                        const double x = fma(nu_i[p], inv_dw, -xl);
+                        const double q = x * x;
+                        const bool fast = q > thr;
+                        const double den = fma(q, q + eb, ec);
+                        const double num = fma(Kf, q, Kc);
+                        const double v = num * (RCP == 2 ? sdm::rcp_fast2(den) : sdm::rcp_fast(den));
+                        if (fast) acc[p] += v;
+                        if (!__all_sync(0xffffffffu, fast)) {
+                            if (!fast) acc[p] += exact_contribution(nu_i[p], e2.nu, e2.dw, inv_dw, thr, e2.y, e2.K);
+                        }
+                        if (STATS) {
+                            const int64_t pix = ws + p * 32 + lane;
+                            if (pix >= p0 && pix < p1) {
+                                int r = sdm::humlicek_region((nu_i[p] - e2.nu) / e2.dw, e2.y);
+                                h0 += (r == 0); h1 += (r == 1); h2 += (r == 2); h3 += (r == 3);
+                            }
+                        }
+                    }
                 } else {
-                    // long overlap (a near-field pair whose core or window edge lies in this span): register slots
+                    // long overlap with a window edge inside the span: register slots with the window test
                     const int lo2 = e2.lo, hi2 = e2.hi;
 #pragma unroll
                     for (int p = 0; p < P; p++) {

@@ -103,6 +103,13 @@ class DeviceContext:
         self.p0, self.p1 = int(p0), int(self.N if p1 is None else p1)
         self._ck(self.lib.sd_set_grid(self.h, self.N, self._in(nus), self.p0, self.p1))
 
+    def set_grid_from(self, other, p0=0, p1=None):
+        """The grid another context of this device already holds (device-to-device copy instead of a second upload)."""
+        ptr_, n = other.buffer(L.BUF_NUS)
+        self.N = int(n)
+        self.p0, self.p1 = int(p0), int(self.N if p1 is None else p1)
+        self._ck(self.lib.sd_set_grid(self.h, self.N, ptr_, self.p0, self.p1))
+
     def set_lines(self, nu, alpha_line, mass=None, atomic_number=None, ion_number=None, ionization_energy=None,
                   level_energy_upper=None, level_energy_lower=None, A_ul=None, stark=None, waals=None):
         s = L.SdLines()

@@ -504,7 +504,7 @@ def _calc_alphas_depth_sharded(stellar_plasma, stellar_model, srf, opacity_confi
 
     total_t = to_pixel_range(L.BUF_TOTAL)
     set_device_atmosphere(ctx, stellar_model, stellar_plasma)
-    ctx.set_grid(nus, p0, p1)
+    ctx.set_grid_from(ctx_op, p0, p1)  # same device: no second upload of the grid
     ctx.set_total(total_t)
     ctx.owner = getattr(srf, "token", None)
 
