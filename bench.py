@@ -45,7 +45,7 @@ BYTES_PER_CELL = 16.0                                  # write t
 # executed work of the far-field path, FP64 flops (FMA = 2), counted from the source (csrc/k2_lines.cu):
 FLOPS_FAR_SETUP = 38.0   # per (pair, tile) expansion: pole distances, two reciprocals, recurrence constants
 FLOPS_FAR_TERM = 9.0     # per Taylor term: coefficient FMA + add, two three-term recurrences (FMA + MUL each)
-FLOPS_HORNER = 43.0      # per (pixel, depth, level): 20 Horner FMAs + scaled argument + accumulate
+FLOPS_HORNER = 55.0      # per (pixel, depth, level): 26 Horner FMAs (SD_FAR_K) + scaled argument + accumulate
 ALPHA_RTOL, F_RTOL = 1e-8, 1e-6
 
 
