@@ -39,6 +39,11 @@
 
 namespace {
 
+int env_int_early(const char *name, int dflt) {
+    const char *v = getenv(name);
+    return v ? atoi(v) : dflt;
+}
+
 constexpr int THREADS = 256;
 constexpr int WARPS = THREADS / 32;
 constexpr int FAR_CH = 1024;                // candidates per cooperative scan chunk of k_far_coeffs
@@ -435,7 +440,12 @@ __global__ void __launch_bounds__(THREADS) k_far_coeffs(LineArgs a, int lev, int
 }
 
 // slices per level (constants: the summation order must not depend on the shard)
-__host__ __device__ constexpr int far_nsplit(int lev) { return lev == SD_FAR_LEVELS - 1 ? 32 : (lev == 0 ? 2 : 8); }
+__host__ __device__ constexpr int far_nsplit_base(int lev) { return lev == SD_FAR_LEVELS - 1 ? 32 : (lev == 0 ? 2 : 8); }
+// SD_FAR_NSPLIT_SCALE (tuning experiments only: it changes the grouping of the partial sums, i.e. the last bits)
+static int far_nsplit(int lev) {
+    static const int scale = env_int_early("SD_FAR_NSPLIT_SCALE", 1);
+    return far_nsplit_base(lev) * (scale >= 1 && scale <= 8 ? scale : 1);
+}
 
 // sum of the nsplit partial coefficient sets of a level, in slice order
 __global__ void k_far_reduce(int n, int nsplit, const double *__restrict__ part, double *__restrict__ coef) {

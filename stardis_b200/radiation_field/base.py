@@ -1,6 +1,7 @@
 """RadiationField container and driver (stardis/radiation_field/base.py:12-117)."""
 from __future__ import annotations
 
+import functools
 import itertools
 import logging
 
@@ -14,6 +15,14 @@ from .source_functions.blackbody import blackbody_flux_at_nu
 
 logger = logging.getLogger(__name__)
 _tokens = itertools.count(1)
+
+
+@functools.lru_cache(maxsize=32)
+def _leggauss(n):
+    x, w = np.polynomial.legendre.leggauss(n)  # an eigenvalue problem: 0.2 ms, cached per angle count
+    x.setflags(write=False)
+    w.setflags(write=False)
+    return x, w
 
 
 class RadiationField:
@@ -40,7 +49,7 @@ class RadiationField:
         self._F_nu = None
         # Gauss-Legendre nodes mapped as in the reference (radiation_field/base.py:60-63) -- deliberately NOT the
         # usual affine map onto [0, pi/2]
-        thetas, weights = np.polynomial.legendre.leggauss(num_of_thetas)
+        thetas, weights = _leggauss(int(num_of_thetas))
         self.thetas = (thetas / 2) + 0.5 * np.pi / 2
         self.I_nus_weights = weights * np.pi / 2
         self.track_individual_intensities = track_individual_intensities

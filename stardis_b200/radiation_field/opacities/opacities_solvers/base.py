@@ -208,16 +208,19 @@ def columnar_lines_of(stellar_plasma, use_vald):
     return per_plasma[use_vald]
 
 
-def select_lines(stellar_plasma, stellar_model, tracing_nus, line_opacity_config):
+def select_lines(stellar_plasma, stellar_model, tracing_nus, line_opacity_config, extent=None):
     """Lines inside [min nu, max nu] (base.py:392-407), auto-ionising ones dropped only when VALD broadening is
-    off (:413-421), masses attached (broadening.py:723-730)."""
+    off (:413-421), masses attached (broadening.py:723-730).  ``extent``: (min, max) of the grid when the caller has
+    them already (two passes over the grid otherwise)."""
     use_vald = line_opacity_config.vald_linelist.use_linelist
     table = columnar_lines_of(stellar_plasma, use_vald)
     if not line_opacity_config.vald_linelist.use_vald_broadening:
         table = table.without_autoionizing()
     table.with_masses(stellar_model.composition.nuclide_masses)
-    nus = u.values_of(tracing_nus)
-    return table.in_range(nus.min(), nus.max())
+    if extent is None:
+        nus = u.values_of(tracing_nus)
+        extent = (nus.min(), nus.max())
+    return table.in_range(extent[0], extent[1])
 
 
 def _line_flags(line_opacity_config):
@@ -226,10 +229,10 @@ def _line_flags(line_opacity_config):
     return broadening_flags(line_opacity_config.broadening) | (L.VALD if use_vald_broadening else 0)
 
 
-def _device_line_opacity(ctx, stellar_plasma, stellar_model, tracing_nus, line_opacity_config, collective=False):
+def _device_line_opacity(ctx, stellar_plasma, stellar_model, tracing_nus, line_opacity_config, collective=False, extent=None):
     """K1 + K2 for the atomic lines on an already prepared context (atmosphere + grid set).  Returns the number of
     lines used."""
-    lines = select_lines(stellar_plasma, stellar_model, tracing_nus, line_opacity_config)
+    lines = select_lines(stellar_plasma, stellar_model, tracing_nus, line_opacity_config, extent=extent)
     upload_lines_and_broaden(ctx, lines, lines.alpha_line, lines.mass, stellar_model, stellar_plasma,
                              _line_flags(line_opacity_config), collective=collective)
     logger.info("Calculating line opacities at spectral points.")
@@ -351,14 +354,15 @@ def calc_alphas(stellar_plasma, stellar_model, stellar_radiation_field, opacity_
     p0, p1 = _shard_of(srf, N)
     W = p1 - p0
 
-    if (nus > RAYLEIGH_UPPER_BOUND_HZ).any():
+    extent = (float(nus.min()), float(nus.max()))
+    if not extent[1] <= RAYLEIGH_UPPER_BOUND_HZ:
         raise NotImplementedError(
             "frequency grids reaching above 2.3e15 Hz (lambda < 1303 A) trigger the reference's in-place frequency "
             "zeroing (base.py:98-99), after which its own line and formal-solver steps are ill-defined; not supported")
     set_device_atmosphere(ctx, stellar_model, stellar_plasma)
     ctx.set_grid(nus, p0, p1)
     n_lines, mol = _device_opacity_pass(ctx, stellar_plasma, stellar_model, nus_q, opacity_config, store_components,
-                                        collective="nu" if getattr(srf, "shard", None) is not None else False)
+                                        collective="nu" if getattr(srf, "shard", None) is not None else False, extent=extent)
     ctx.owner = getattr(srf, "token", None)
 
     def shard_array(which):
@@ -379,7 +383,8 @@ def calc_alphas(stellar_plasma, stellar_model, stellar_radiation_field, opacity_
     return total
 
 
-def _device_opacity_pass(ctx, stellar_plasma, stellar_model, nus_q, opacity_config, store_components, collective=False):
+def _device_opacity_pass(ctx, stellar_plasma, stellar_model, nus_q, opacity_config, store_components, collective=False,
+                         extent=None):
     """K1 + K2 (atomic, molecular) + K3 on a prepared context (atmosphere and grid set).  Continuum descriptors are
     assembled on the host (O(D)); evaluation order follows base.py:655-736.  Returns (n_lines or None, molecular
     (gammas, doppler_widths) or None)."""
@@ -387,7 +392,7 @@ def _device_opacity_pass(ctx, stellar_plasma, stellar_model, nus_q, opacity_conf
     n_lines, mol = None, None
     if not line_cfg.disable:
         # nu-sharded run (every rank of the job is here with the same line table): stripe the big upload
-        n_lines = _device_line_opacity(ctx, stellar_plasma, stellar_model, nus_q, line_cfg, collective=collective)
+        n_lines = _device_line_opacity(ctx, stellar_plasma, stellar_model, nus_q, line_cfg, collective=collective, extent=extent)
         if line_cfg.include_molecules:
             mol = _device_molecular_opacity(ctx, stellar_plasma, stellar_model, nus_q, line_cfg)
     # the line kernels are running now: the host assembles the O(D) continuum descriptors (pandas) in their shadow
@@ -477,7 +482,8 @@ def _calc_alphas_depth_sharded(stellar_plasma, stellar_model, srf, opacity_confi
     nus = u.values_of(nus_q)
     N = nus.shape[0]
     D = stellar_model.no_of_depth_points
-    if (nus > RAYLEIGH_UPPER_BOUND_HZ).any():
+    extent = (float(nus.min()), float(nus.max()))
+    if not extent[1] <= RAYLEIGH_UPPER_BOUND_HZ:
         raise NotImplementedError("frequency grids reaching above 2.3e15 Hz are not supported (see calc_alphas)")
     bounds = getattr(srf, "shard_bounds", None) or all_shards(N, world)
     p0, p1 = _shard_of(srf, N)
@@ -489,7 +495,8 @@ def _calc_alphas_depth_sharded(stellar_plasma, stellar_model, srf, opacity_confi
     plasma_r = DepthSlicedPlasma.of(stellar_plasma, idx)
     set_device_atmosphere(ctx_op, model_r, plasma_r)
     ctx_op.set_grid(nus)
-    n_lines, mol = _device_opacity_pass(ctx_op, plasma_r, model_r, nus_q, opacity_config, store_components, collective="depth")
+    n_lines, mol = _device_opacity_pass(ctx_op, plasma_r, model_r, nus_q, opacity_config, store_components, collective="depth",
+                                        extent=extent)
     dev = torch.device("cuda", ctx.device)
     stream = torch.cuda.current_stream(dev)
 
