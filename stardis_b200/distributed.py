@@ -91,6 +91,10 @@ def allgather_spectrum(local, shard, n_total, device=None, bounds=None):
     t = local if is_tensor else torch.from_numpy(np.ascontiguousarray(local, dtype=np.float64))
     if device is not None:
         t = t.to(device)
+    if len({b - a for a, b in bounds}) == 1 and t.is_cuda:  # equal widths: one collective straight into the result
+        full = torch.empty(n_total, dtype=torch.float64, device=t.device)
+        dist.all_gather_into_tensor(full, t.contiguous())
+        return full if is_tensor else full.cpu().numpy()
     # equal-sized contributions (gloo and NCCL both take the fast path): pad to the widest shard, trim afterwards
     wmax = max(b - a for a, b in bounds)
     padded = torch.zeros(wmax, dtype=torch.float64, device=t.device)
@@ -187,18 +191,55 @@ def depth_indices(n_depth, rank, world_size):
     return d[owner == rank]
 
 
+_index_cache = {}
+
+
+def _depth_rows(n_depth, rank, world, device):
+    """``depth_indices`` as a cached device index tensor (no host->device copy per call)."""
+    import torch
+
+    key = ("rows", int(n_depth), int(rank), int(world), str(device))
+    if key not in _index_cache:
+        _index_cache[key] = torch.as_tensor(depth_indices(n_depth, rank, world), dtype=torch.long, device=device)
+    return _index_cache[key]
+
+
+def _depth_gather_perm(n_depth, world, device):
+    """perm[d] = row of depth d in the (world * D/world) rank-major stack of the ranks' depth rows (D divisible by world)."""
+    import torch
+
+    key = ("perm", int(n_depth), int(world), str(device))
+    if key not in _index_cache:
+        per = int(n_depth) // int(world)
+        perm = np.empty(int(n_depth), dtype=np.int64)
+        for s in range(world):
+            perm[depth_indices(n_depth, s, world)] = s * per + np.arange(per)
+        _index_cache[key] = torch.as_tensor(perm, dtype=torch.long, device=device)
+    return _index_cache[key]
+
+
 def exchange_depth_to_nu(local, n_depth, n_total, bounds=None):
     """All-to-all between the two decompositions: ``local`` (D_r, N) holds this rank's depth rows (``depth_indices``) over
     the whole grid; returns (D, W_r), all depth rows over this rank's pixel range ``bounds[rank]`` (default: equal
     widths).  torch tensors (CUDA -> NCCL ``all_to_all_single``; CPU/gloo -> point-to-point sends, used by the tests);
-    returns a tensor on the same device.  Without a process group the input is returned unchanged."""
+    returns a tensor on the same device.  Without a process group the input is returned unchanged.  With D divisible by
+    the world size and equal-width ranges (the usual case) the whole exchange is three device operations: one transposing
+    copy, the all-to-all, one row gather."""
     import torch
 
     dist, rank, world = dist_info()
     if dist is None or world == 1:
         return local
     bounds = _checked_bounds(bounds, n_total, world)
-    d_pad = -(-int(n_depth) // world)
+    n_depth = int(n_depth)
+    widths = {b - a for a, b in bounds}
+    if local.is_cuda and n_depth % world == 0 and len(widths) == 1:
+        w = widths.pop()
+        send = local.view(local.shape[0], world, w).permute(1, 0, 2).contiguous()   # (R, D_r, W): block j -> rank j
+        recv = torch.empty_like(send)
+        dist.all_to_all_single(recv, send)
+        return recv.view(n_depth, w).index_select(0, _depth_gather_perm(n_depth, world, local.device))
+    d_pad = -(-n_depth // world)
     w_pad = max(b - a for a, b in bounds)
     send = torch.zeros((world, d_pad, w_pad), dtype=torch.float64, device=local.device)
     for j, (a, b) in enumerate(bounds):
@@ -217,10 +258,10 @@ def exchange_depth_to_nu(local, n_depth, n_total, bounds=None):
         for r in reqs:
             r.wait()
     a, b = bounds[rank]
-    out = torch.empty((int(n_depth), b - a), dtype=torch.float64, device=local.device)
+    out = torch.empty((n_depth, b - a), dtype=torch.float64, device=local.device)
     for s in range(world):
-        rows = depth_indices(n_depth, s, world)
-        out[torch.as_tensor(rows, device=local.device)] = recv[s, : len(rows), : b - a]
+        rows = _depth_rows(n_depth, s, world, local.device)
+        out.index_copy_(0, rows, recv[s, : rows.shape[0], : b - a])
     return out
 
 
@@ -239,8 +280,8 @@ def allgather_depth_columns(local, n_depth):
     dist.all_gather(pieces, padded)
     out = torch.empty((local.shape[0], int(n_depth)), dtype=torch.float64, device=local.device)
     for s in range(world):
-        rows = depth_indices(n_depth, s, world)
-        out[:, torch.as_tensor(rows, device=local.device)] = pieces[s][:, : len(rows)]
+        rows = _depth_rows(n_depth, s, world, local.device)
+        out.index_copy_(1, rows, pieces[s][:, : rows.shape[0]])
     return out
 
 
