@@ -336,102 +336,80 @@ __global__ void __launch_bounds__(THREADS) k_far_coeffs(LineArgs a, int lev, int
     constexpr int SEGS = ROUNDS * WARPS;       // (round, warp) segments of 32 candidates, in list order
     static_assert(SEGS == 32, "one lane per segment in the offset scan");
     __shared__ int s_cnt[SEGS];
-    unsigned mk[ROUNDS];  // per round: child mask of this thread's candidate | rank among the wanted ones of its warp << 8
-    int ll[ROUNDS];       // its line index
-    // ---- test: one gather per candidate, mask over the eight children (registers + per-segment counts only: it may run
-    // while other warps still expand the previous chunk out of the dense buffers)
-    auto test_chunk = [&](int src, int base, int jb) {
+    for (int src = 0; src < 3; src++) {
+        const int ja = s_ja[src], jb = s_jb[src];
+        for (int base = ja; base < jb; base += FAR_CH) {
+            // ---- test
+            unsigned mk[ROUNDS];
+            int ll[ROUNDS], rk[ROUNDS];
 #pragma unroll
-        for (int r = 0; r < ROUNDS; r++) {
-            const int idx = r * THREADS + tid, j = base + idx;
-            unsigned mask = 0;
-            int l = 0;
-            if (j < jb) {
-                l = (src == 0) ? list_d[j] : (int)(a.fg.edge_keys[j] & lmask);
-                const PairWin pw = load_win(a.win + drow + l);
-                const int lo = pw.lo, hi = pw.hi;
-                bool okp = true;
-                if (has_parent) {
-                    const bool covers_parent = (lo <= pt0) && (hi >= pt1);
-                    if (src == 0) {  // (A): covers the parent, parent inside the near interval
-                        okp = covers_parent && !pair_is_far(lo, hi, near_of(pw, plev), pt0, pt1, ptile);
-                    } else {         // (B): an edge strictly inside the parent; both edges inside: via its start
-                        okp = !covers_parent && !(src == 2 && lo > pt0 && lo < pt1);
+            for (int r = 0; r < ROUNDS; r++) {
+                const int idx = r * THREADS + tid, j = base + idx;
+                unsigned mask = 0;
+                int l = 0;
+                if (j < jb) {
+                    l = (src == 0) ? list_d[j] : (int)(a.fg.edge_keys[j] & lmask);
+                    const PairWin pw = load_win(a.win + drow + l);
+                    const int lo = pw.lo, hi = pw.hi;
+                    bool okp = true;
+                    if (has_parent) {
+                        const bool covers_parent = (lo <= pt0) && (hi >= pt1);
+                        if (src == 0) {  // (A): covers the parent, parent inside the near interval
+                            okp = covers_parent && !pair_is_far(lo, hi, near_of(pw, plev), pt0, pt1, ptile);
+                        } else {         // (B): an edge strictly inside the parent; both edges inside: via its start
+                            okp = !covers_parent && !(src == 2 && lo > pt0 && lo < pt1);
+                        }
+                    }
+                    if (okp) {
+                        const unsigned near = near_of(pw, lev);
+#pragma unroll
+                        for (int cc = 0; cc < WARPS; cc++) {
+                            const int tcc = child0 + cc;
+                            const int64_t c0 = (int64_t)tcc * tile_px;
+                            const int64_t c1 = (c0 + tile_px < a.N) ? c0 + tile_px : a.N;
+                            if (tcc < a.fg.n_tiles[lev] && pair_is_far(lo, hi, near, c0, c1, tcc)) mask |= 1u << cc;
+                        }
                     }
                 }
-                if (okp) {
-                    const unsigned near = near_of(pw, lev);
+                const unsigned nz = __ballot_sync(0xffffffffu, mask != 0);
+                mk[r] = mask; ll[r] = l; rk[r] = __popc(nz & lt_mask);
+                if (lane == 0) s_cnt[r * WARPS + warp] = __popc(nz);
+            }
+            __syncthreads();
+            // ---- compact: exclusive offsets of the (round, warp) segments, one segment per lane
+            const int cnt_l = s_cnt[lane];
+            int incl = cnt_l;
 #pragma unroll
-                    for (int cc = 0; cc < WARPS; cc++) {
-                        const int tcc = child0 + cc;
-                        const int64_t c0 = (int64_t)tcc * tile_px;
-                        const int64_t c1 = (c0 + tile_px < a.N) ? c0 + tile_px : a.N;
-                        if (tcc < a.fg.n_tiles[lev] && pair_is_far(lo, hi, near, c0, c1, tcc)) mask |= 1u << cc;
-                    }
+            for (int o2 = 1; o2 < 32; o2 <<= 1) {
+                const int t = __shfl_up_sync(0xffffffffu, incl, o2);
+                if (lane >= o2) incl += t;
+            }
+            const int n_dense = __shfl_sync(0xffffffffu, incl, 31);
+#pragma unroll
+            for (int r = 0; r < ROUNDS; r++) {
+                const int seg = r * WARPS + warp;
+                const int off = __shfl_sync(0xffffffffu, incl - cnt_l, seg);
+                if (mk[r]) {
+                    const int pos = off + rk[r];
+                    const unsigned dst = (unsigned)__cvta_generic_to_shared(s_rec + pos);
+                    const LineRec *srcp = a.rec + drow + ll[r];
+                    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(srcp) : "memory");
+                    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst + 16u),
+                                 "l"(reinterpret_cast<const char *>(srcp) + 16) : "memory");
+                    s_mask[pos] = (unsigned char)(mk[r] & valid);
                 }
             }
-            const unsigned nz = __ballot_sync(0xffffffffu, mask != 0);
-            mk[r] = mask | ((unsigned)__popc(nz & lt_mask) << 8);
-            ll[r] = l;
-            if (lane == 0) s_cnt[r * WARPS + warp] = __popc(nz);
-        }
-    };
-    // ---- compact: exclusive offsets of the (round, warp) segments (one segment per lane), records of the wanted
-    // candidates -> dense buffers; returns the number of dense entries
-    auto compact_chunk = [&]() -> int {
-        const int cnt_l = s_cnt[lane];
-        int incl = cnt_l;
-#pragma unroll
-        for (int o2 = 1; o2 < 32; o2 <<= 1) {
-            const int t = __shfl_up_sync(0xffffffffu, incl, o2);
-            if (lane >= o2) incl += t;
-        }
-#pragma unroll
-        for (int r = 0; r < ROUNDS; r++) {
-            const int off = __shfl_sync(0xffffffffu, incl - cnt_l, r * WARPS + warp);
-            if (mk[r] & 0xffu) {
-                const int pos = off + (int)(mk[r] >> 8);
-                const unsigned dst = (unsigned)__cvta_generic_to_shared(s_rec + pos);
-                const LineRec *srcp = a.rec + drow + ll[r];
-                asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(srcp) : "memory");
-                asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst + 16u),
-                             "l"(reinterpret_cast<const char *>(srcp) + 16) : "memory");
-                s_mask[pos] = (unsigned char)(mk[r] & valid);
-            }
-        }
-        asm volatile("cp.async.commit_group;" ::: "memory");
-        asm volatile("cp.async.wait_group 0;" ::: "memory");
-        return __shfl_sync(0xffffffffu, incl, 31);
-    };
-    // All chunks of the three sources as one sequence; the test of chunk c + 1 is issued BEFORE the expansion of chunk c
-    // (no barrier in between: while some warps of the CTA wait for their gathers, others are in the FP64 series), two
-    // barriers per chunk.
-    int src = 0, base = s_ja[0];
-    auto advance = [&]() {  // -> the next non-empty chunk (src, base), src == 3 when there is none
-        while (src < 3 && base >= s_jb[src]) { src++; if (src < 3) base = s_ja[src]; }
-    };
-    advance();
-    if (src < 3) {
-        test_chunk(src, base, s_jb[src]);
-        __syncthreads();
-        int n_dense = compact_chunk();
-        __syncthreads();
-        for (;;) {
-            base += FAR_CH;
-            advance();
-            const bool more = src < 3;   // uniform over the CTA
-            if (more) test_chunk(src, base, s_jb[src]);
-            // ---- expand the current chunk: this warp's child
+            asm volatile("cp.async.commit_group;" ::: "memory");
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+            __syncthreads();
+            // ---- expand: this warp's child
             for (int i0 = 0; i0 < n_dense && tile_ok; i0 += 32) {
                 const int i = i0 + lane;
                 const bool have = (i < n_dense) && ((s_mask[i] >> warp) & 1u);
                 if (!__any_sync(0xffffffffu, have)) continue;
                 expand(have, s_rec[i < n_dense ? i : 0]);
             }
-            if (!more) break;
-            __syncthreads();  // everyone is done with the dense buffers (and with s_cnt of the chunk just tested)
-            n_dense = compact_chunk();
-            __syncthreads();
+            __syncthreads();  // the chunk buffers are overwritten by the next chunk
         }
     }
     // deterministic reduction: lanes by shuffle (every lane ends up with the sum; lane k keeps coefficient k)
