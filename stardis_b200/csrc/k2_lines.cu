@@ -226,6 +226,22 @@ __device__ __forceinline__ bool pair_is_far(int lo, int hi, unsigned near, int64
 // (`nsplit` CTAs per group; k_far_reduce adds the partial sums in slice order).  Groups, slices, chunking and queue order
 // depend on the global tile index and the candidate lists only, never on the shard, so the summation order -- and the
 // result, bit for bit -- is the same for every partition of the grid.
+// series length by floor(-8 log2(rho^2)) (see `expand`): filled by far_terms_table(), uploaded once per device
+__constant__ unsigned char FAR_TERMS[256];
+
+void far_terms_table(unsigned char *tab) {
+    constexpr int K1 = SD_FAR_K + 1;
+    for (int t = 0; t < 256; t++) {
+        const double lg = 0.5 * (t / 8.0 - 0.087);  // lower bound of log2(1 / rho) for this index
+        int n = K1;
+        if (lg > (double)SD_FAR_LOG2_RHO_INV) {
+            n = (int)((double)K1 * (double)SD_FAR_LOG2_RHO_INV / lg + 1.02);
+            if (n > K1) n = K1;
+        }
+        tab[t] = (unsigned char)n;
+    }
+}
+
 __global__ void __launch_bounds__(THREADS) k_far_coeffs(LineArgs a, int lev, int count_stats, int nsplit, double *part) {
     constexpr int K1 = SD_FAR_K + 1;
     __shared__ int s_ja[3], s_jb[3];
@@ -297,14 +313,17 @@ __global__ void __launch_bounds__(THREADS) k_far_coeffs(LineArgs a, int lev, int
             const double i1 = -h * q1, i2 = -h * q2;
             w1r = D1 * i1; w1i = g * i1; w2r = D2 * i2; w2i = g * i2;
             // terms needed: (n + 1) rho^n <= (K1 + 1) rho_far^K1 (the bound of the full series at the far criterion)
-            // <=>  n >= ~K1 log2(1 / rho_far) / log2(1 / rho);  rho^2 = h^2 max(q1, q2)
-            const float lg = -0.5f * __log2f((float)(h * h * fmax(q1, q2)));
-            nterms = (lg > SD_FAR_LOG2_RHO_INV) ? min(K1, (int)(__fdividef((float)K1 * SD_FAR_LOG2_RHO_INV, lg) + 1.02f)) : K1;
-            n_far++;
+            // <=>  n >= ~K1 log2(1 / rho_far) / log2(1 / rho);  rho^2 = h^2 max(q1, q2).  -log2(rho^2) is read off the
+            // exponent and the top mantissa bits of rho^2 in steps of 1/8 (a lower bound: the series is never shorter
+            // than the rule asks) and indexes a 256-entry table -- six integer instructions instead of ~30 with the
+            // float logarithm and division this used to be (9 % of the kernel's instructions, ncu round 2)
+            const int t8 = (0x3ff00000 - __double2hiint(h * h * fmax(q1, q2))) >> 17;  // floor(8 * -L), L <= log2(rho^2) <= L + 0.086
+            nterms = FAR_TERMS[min(max(t8, 0), 255)];
+            if (count_stats) n_far++;
         }
         // queue neighbours are neighbours in frequency, at similar distances from the tile: warp-uniform series length
         const int nt = __reduce_max_sync(0xffffffffu, nterms);
-        if (have) n_terms += (unsigned long long)min(K1, 3 * ((nt + 2) / 3));  // terms the loop below executes
+        if (count_stats && have) n_terms += (unsigned long long)min(K1, 3 * ((nt + 2) / 3));  // terms the loop below executes
         // Im(w^(k+1)) by the real three-term recurrence of the powers of a complex number,
         //   s_(k+1) = 2 Re(w) s_k - |w|^2 s_(k-1),  s_0 = 0, s_1 = Im w,
         // two instructions per pole and term instead of the four of a complex product (the recurrence loses about one
@@ -811,8 +830,12 @@ int sd_k2_lines(sd_ctx *c, int slot) {
         }
         // CTAs per (group of eight sibling tiles, depth): the candidate lists are cut into this many fixed slices so that
         // even a narrow shard fills the chip; k_far_reduce adds the partial sums in slice order.
-        if (!c->far_attr_set) {  // per device: > 48 KB of dynamic shared memory needs the opt-in
+        if (!c->far_attr_set) {  // per device: > 48 KB of dynamic shared memory needs the opt-in; series-length table
             SD_CUDA(c, cudaFuncSetAttribute(k_far_coeffs, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FAR_SMEM));
+            unsigned char tab[256];
+            far_terms_table(tab);
+            SD_CUDA(c, cudaMemcpyToSymbolAsync(FAR_TERMS, tab, sizeof tab, 0, cudaMemcpyHostToDevice, c->stream));
+            SD_CUDA(c, cudaStreamSynchronize(c->stream));  // `tab` lives on this stack frame
             c->far_attr_set = true;
         }
         size_t part_bytes = 0;
