@@ -45,7 +45,10 @@ BYTES_PER_CELL = 16.0                                  # write t
 # executed work of the far-field path, FP64 flops (FMA = 2), counted from the source (csrc/k2_lines.cu):
 FLOPS_FAR_SETUP = 38.0   # per (pair, tile) expansion: pole distances, two reciprocals, recurrence constants
 FLOPS_FAR_TERM = 9.0     # per Taylor term: coefficient FMA + add, two three-term recurrences (FMA + MUL each)
-FLOPS_HORNER = 55.0      # per (pixel, depth, level): 26 Horner FMAs (SD_FAR_K) + scaled argument + accumulate
+FLOPS_HORNER = 65.0      # per (pixel, depth, level): 31 Horner FMAs (SD_FAR_K) + scaled argument + accumulate
+FAR_LEVELS = 4           # SD_FAR_LEVELS
+FLOPS_S2M = 38.0 + 32 * 9.0   # per (pair, level) multipole expansion: set-up + 32 moments (same recurrence as a Taylor term)
+FLOPS_M2L_STEP = 32 * 2.0 + 2.0 * 32 / 14   # per (source, target, depth, k) row step: one FMA on 32 lanes (+ the row update shared by 14 depths)
 ALPHA_RTOL, F_RTOL = 1e-8, 1e-6
 
 
@@ -531,8 +534,9 @@ def run_b200_arm(args):
             if (t.get("N"), t.get("D"), t.get("L")) == (N, D, len(sel)):
                 traffic = t.get("bytes_per_launch", {})
         # executed work of this rank's launches in the default (far-field) mode
-        flops_lines = float((ex["direct_region_evals"] * FLOPS_PER_EVAL).sum()) + FLOPS_HORNER * 3.0 * len(hp.didx) * op.W
-        flops_far = FLOPS_FAR_SETUP * ex["far_expansions"] + FLOPS_FAR_TERM * ex["far_terms"]
+        flops_lines = float((ex["direct_region_evals"] * FLOPS_PER_EVAL).sum()) + FLOPS_HORNER * FAR_LEVELS * len(hp.didx) * op.W
+        flops_far = (FLOPS_FAR_SETUP * ex["far_expansions"] + FLOPS_FAR_TERM * ex["far_terms"]
+                     + FLOPS_S2M * ex["multipole_expansions"] + FLOPS_M2L_STEP * ex["m2l_row_steps"])
         t_lines, t_far = kern.get("K2_lines", 0.0), kern.get("K2_far_coeffs", 0.0)
         tf_lines = flops_lines / max(t_lines * 1e-3, 1e-12) / 1e12
         tf_far = flops_far / max(t_far * 1e-3, 1e-12) / 1e12
@@ -547,22 +551,25 @@ def run_b200_arm(args):
                          "traffic": traffic.get("k_lines"),
                          "peak_source": "measured in this run: dependent-free DFMA loop on all SMs (sd_bench_dfma)",
                          "work": "EXECUTED Voigt evaluations per Humlicek region x SURVEY 8d flops + Horner evaluation of "
-                                 "the three far-field polynomials per (pixel, depth)",
+                                 "the four far-field polynomials per (pixel, depth)",
                          "flops_per_eval": FLOPS_PER_EVAL.tolist(), "executed_region_evals": ex["direct_region_evals"].tolist(),
                          "flops_horner_per_cell_level": FLOPS_HORNER, "kernel_ms": t_lines,
                          "share_of_step": t_lines / ms_per_step},
-            "roofline_far": {"kernel": "k_far_coeffs (+ k_far_reduce), all three levels", "bound": "fp64", "achieved": tf_far,
+            "roofline_far": {"kernel": "k_far_coeffs (+ k_far_reduce) + k_s2m + k_m2l, all four levels", "bound": "fp64", "achieved": tf_far,
                              "peak": dfma_peak, "unit": "TFLOP/s", "frac": tf_far / dfma_peak, "traffic": traffic.get("k_far_coeffs"),
-                             "work": "EXECUTED (pair, tile) expansions x setup flops + Taylor terms x flops per term",
+                             "work": "EXECUTED direct (pair, tile) expansions x setup flops + Taylor terms x flops per term + multipole "
+                                     "expansions (pair, level) + tile-to-tile translation row steps",
                              "expansions": ex["far_expansions"], "terms": ex["far_terms"],
+                             "multipole_expansions": ex["multipole_expansions"], "m2l_row_steps": ex["m2l_row_steps"],
                              "flops_setup": FLOPS_FAR_SETUP, "flops_per_term": FLOPS_FAR_TERM, "kernel_ms": t_far,
                              "share_of_step": t_far / ms_per_step},
             "roofline_hbm": {"kernel": "k_continuum + k_raytrace (K3+K4)", "bound": "hbm",
                              "achieved": BYTES_PER_CELL * cells / max(t_hbm * 1e-3, 1e-12) / 1e9, "peak": hbm_peak,
                              "unit": "GB/s", "frac": BYTES_PER_CELL * cells / max(t_hbm * 1e-3, 1e-12) / 1e9 / hbm_peak,
                              "peak_source": hbm_src, "traffic": traffic.get("k_continuum+k_raytrace"), "kernel_ms": t_hbm},
-            "farfield": {"what": "default mode: distant region-I wings summed as Taylor coefficients (degree <= 20) per pixel "
-                                 "tile on a 3-level tile hierarchy (k_far_coeffs) instead of per pixel",
+            "farfield": {"what": "default mode: distant region-I wings summed as Taylor polynomials (degree 31) per pixel tile on a "
+                                 "4-level tile hierarchy (64..32768 pixels): multipole moments + tile-to-tile translations for "
+                                 "pairs covering the neighbourhood (k_s2m, k_m2l), direct expansion otherwise (k_far_coeffs)",
                          "k2_ms": k2_far_ms, "reference_equivalent_region_evals_all_ranks": region_evals.tolist(),
                          "far_replaced_evals": ex["far_replaced_evals"]},
             "phase_ms": {name: phase[i] for i, name in enumerate(hp.PHASES)},

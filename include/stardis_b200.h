@@ -126,11 +126,14 @@ int sd_set_broadening(sd_ctx *ctx, const double *gammas, int32_t gamma_cols, con
  *          voigt_profile / _faddeeva voigt.py:17-155) -> alpha_line[slot] (D, p1-p0) --------------- */
 /* slot 0 = atomic lines ("alpha_line_at_nu"), slot 1 = molecular lines ("molecule_alpha_line_at_nu"). */
 int sd_calc_alpha_line(sd_ctx *ctx, int32_t slot);
-/* Far-field expansion of region-I wings per pixel tile (default ON).  A (line, depth) pair whose window covers a
- * whole 256*P-pixel tile and whose line centre is at least 4 tile half-widths away is not evaluated pixel by pixel:
- * its profile (two Lorentzians in Humlicek region I) is expanded in a degree-20 Taylor polynomial about the tile
- * centre, the coefficients of all such pairs of a tile are summed once and the polynomial is added per pixel
- * (relative deviation from the direct evaluation <= 6e-12, all terms positive).  sd_set_farfield(ctx, 0) evaluates
+/* Far-field expansion of region-I wings per pixel tile (default ON).  On a hierarchy of pixel tiles (64 * 8^k
+ * pixels, k = 0..3) a (line, depth) pair whose window covers a whole tile and whose line centre lies at least two
+ * tiles away is not evaluated pixel by pixel there: its profile (two Lorentzians in Humlicek region I) is analytic
+ * over the tile, the degree-31 Taylor polynomials of all such pairs of a tile are summed once -- through multipole
+ * moments of the source tiles and tile-to-tile translations (a 1-D fast multipole method) for pairs whose window
+ * covers the whole neighbourhood, by direct expansion otherwise -- and the polynomial is added per pixel (relative
+ * deviation from the direct evaluation <= 6e-12 per pair in the worst geometry, all terms positive).  Grids whose
+ * tile widths do not vary smoothly lose the upper hierarchy levels automatically.  sd_set_farfield(ctx, 0) evaluates
  * every (line, depth, pixel) triple directly, exactly like the reference's loop. */
 int sd_set_farfield(sd_ctx *ctx, int32_t on);
 /* Statistics.  sd_set_line_stats(ctx, 1) makes the following sd_calc_alpha_line calls run the counting
@@ -143,9 +146,11 @@ int sd_line_stats(sd_ctx *ctx, int64_t out[8]);
 /* EXECUTED work of the last counting pass (bench.py's roofline of the default, far-field mode), raw counters:
  * out[0..3] = Voigt evaluations k_lines performed itself per Humlicek region I..IV (pixels of this context's range),
  * out[4..6] as sd_line_stats, out[8] = region-I evaluations the far-field expansions stand for
- * (sd_line_stats()[0] = out[0] + out[8]), out[9] = far-field expansions performed ((pair, tile) products),
+ * (sd_line_stats()[0] = out[0] + out[8]), out[9] = direct far-field expansions performed ((pair, tile) products),
  * out[10] = Taylor terms summed over those expansions, out[11] = non-finite line strengths written by the last
- * sd_calc_alpha_line_vald / sd_calc_alpha_line_levels call, out[7], out[12..15] reserved. */
+ * sd_calc_alpha_line_vald / sd_calc_alpha_line_levels call, out[12] = multipole expansions ((pair, level) products,
+ * 32 moments each), out[13] = matrix-row steps of the tile-to-tile translations per lane ((source, target, depth, k)
+ * products: one FMA on each of 32 lanes), out[7], out[14..15] reserved. */
 int sd_line_stats_ex(sd_ctx *ctx, int64_t out[16]);
 
 /* ---- K3: continuum terms fused in one depth x nu pass + total ---------------------------------------- */

@@ -166,79 +166,99 @@ __global__ void __launch_bounds__(256) k_line_idx(int64_t L, int64_t N, const do
     idx[l] = (int)lo;
 }
 
-// Centre frequency and half-width [Hz] of every GLOBAL pixel tile [t*T, min((t+1)*T, N)) (far-field expansion point).
+// Centre frequency, half-width and moment scale [Hz] of every GLOBAL pixel tile [t*T, min((t+1)*T, N)) (far-field
+// expansion point).  The moment scale is the half-width, except for a ragged last tile, which takes its neighbour's.
 __global__ void __launch_bounds__(256) k_tile_geometry(int64_t N, int tile, int n_tiles, const double *__restrict__ nus,
                                                        double *__restrict__ geom) {
     int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n_tiles) return;
     int64_t a = (int64_t)t * tile, b = a + tile < N ? a + tile : N;
     double hi = nus[a], lo = nus[b - 1];
-    geom[2 * t] = 0.5 * (hi + lo);
-    geom[2 * t + 1] = 0.5 * (hi - lo);
+    geom[3 * t] = 0.5 * (hi + lo);
+    geom[3 * t + 1] = 0.5 * (hi - lo);
+    double sc = 0.5 * (hi - lo);
+    if (b - a < tile && t > 0) sc = 0.5 * (nus[a - tile] - nus[a - 1]);
+    geom[3 * t + 2] = sc;
 }
 
-// A tile is FAR from a (line, depth) pair when the Taylor expansion of the pair's region-I profile about the tile
-// centre converges with ratio <= 1/SD_FAR_RHO_INV over the whole tile and every pixel of the tile is certainly in
-// Humlicek region I.  Written as a positive condition: NaN parameters are never far.
-__device__ __forceinline__ bool tile_is_far(double nu_c, double h, double nu_l, double dw, double y) {
-    const double a_dw = 0.7071067811865476 * dw;  // the two poles of z/(z^2 - 1/2) sit at nu_l -+ dw/sqrt(2)
-    double dist = fabs(nu_c - nu_l);
-    double m = 15.0000001 - y;
-    double core = h + (m > 0.0 ? m : 0.0) * dw;
-    return (dist >= SD_FAR_RHO_INV * h + a_dw) && (dist >= core) && (dw > 0.0) && (y >= 0.0) && (y < 1e300) && (h > 0.0);
+// Which hierarchy levels are usable on this grid: the far criterion is an index distance (two tiles), so the tile
+// half-widths must vary smoothly (then the nearest far tile is the worst case of every convergence test made per
+// pair by k_build_records).  Level k is active when it and all lower levels have strictly descending frequencies and
+// neighbouring full tiles differ by less than a factor 1.6 in width.  info[0] = number of active levels.
+__global__ void __launch_bounds__(256) k_level_check(FarGeom fg, int64_t N, int *__restrict__ info) {
+    __shared__ int s_bad[SD_FAR_LEVELS];
+    if (threadIdx.x < SD_FAR_LEVELS) s_bad[threadIdx.x] = 0;
+    __syncthreads();
+    for (int k = 0; k < SD_FAR_LEVELS; k++) {
+        const int nt = fg.n_tiles[k];
+        const int n_full = (int)(N / fg.tile[k]);  // tiles [0, n_full) hold a full set of pixels
+        bool bad = false;
+        for (int t = threadIdx.x; t < nt; t += blockDim.x) {
+            const double h = fg.geom[k][3 * t + 1];
+            const bool single = (t == nt - 1) && (N - (int64_t)t * fg.tile[k] < 2);
+            if (!(h > 0.0) && !single) bad = true;
+            if (t + 1 < n_full) {
+                const double r = fg.geom[k][3 * (t + 1) + 1] / h;
+                if (!(r > 0.625 && r < 1.6)) bad = true;
+            }
+        }
+        if (bad) s_bad[k] = 1;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int n = 0;
+        while (n < SD_FAR_LEVELS && !s_bad[n]) n++;
+        info[0] = n;
+    }
 }
 
 __device__ __forceinline__ int hw_class(long long hw) {
     // class 0: hw <= 64; class k (1..5): hw <= 64 * 4^k; class 6: everything wider (walked whole by the line kernel).
-    // Class 7 (SD_FC_CLASS) is reserved for the far-capable pairs of the far-field scheme.
+    // Classes SD_FC0 + m are reserved for the far-capable pairs of the far-field scheme.
     if (hw <= SD_CLS0_HW) return 0;
     int k = 1;
     long long lim = (long long)SD_CLS0_HW * 4;
-    while (k < SD_NCLS - 2 && hw > lim) { k++; lim *= 4; }
+    while (k < SD_FC0 - 1 && hw > lim) { k++; lim *= 4; }
     return k;
 }
 
-// Tiles [a_, b_) around the centre tile tc that are NOT far.  Farness is monotone in the distance from the centre (the
-// centre distance grows by 2 h per tile, the required distance by at most ~0.5 h), so each boundary is found from an
-// estimate (required distance / tile spacing at the centre tile) plus a short walk.  The three tiles around either
-// estimate are probed up front with INDEPENDENT loads (the walk then usually needs no further memory access: the
-// dependent load -> test -> load chain of a plain walk is what kept the first version of this kernel latency bound).
-__device__ __forceinline__ void near_interval(const double *__restrict__ geom, int n_tiles, int tc, double nu_l, double dw,
-                                              double y, int &a_out, int &b_out) {
-    const double h_c = geom[2 * tc + 1];
-    const double m_c = 15.0000001 - y;
-    const double need = fmax(SD_FAR_RHO_INV * h_c + 0.7071067811865476 * dw, h_c + (m_c > 0.0 ? m_c : 0.0) * dw);
-    const double est = need / (2.0 * h_c);
-    const int n_est = (est < (double)n_tiles) ? (int)est : n_tiles;  // NaN / inf -> the whole grid
-    int a_ = max(tc - n_est, 0), b_ = min(tc + n_est + 1, n_tiles);
-    // probes: tiles a_-1, a_, a_+1 and b_-2, b_-1, b_ (clamped; out-of-range probes are never consulted)
-    const int pa = a_ - 1, pb = b_ - 2;
-    bool fa[3], fb[3];
-#pragma unroll
-    for (int k = 0; k < 3; k++) {
-        const int ta = min(max(pa + k, 0), n_tiles - 1), tb = min(max(pb + k, 0), n_tiles - 1);
-        fa[k] = tile_is_far(geom[2 * ta], geom[2 * ta + 1], nu_l, dw, y);
-        fb[k] = tile_is_far(geom[2 * tb], geom[2 * tb + 1], nu_l, dw, y);
+// Can the pair (nu_l, dw, y; centre pixel cpix) be expanded at hierarchy level k?  Everything two or more tiles away
+// from the centre tile s must (i) be certainly in Humlicek region I (x^2 > thr at the nearest such pixel on either
+// side), (ii) see the multipole series of the two poles about the centre of s converge with ratio <= SD_FAR_RHO
+// (|pole - c_s| against the distance of the nearest far pixel from c_s) and (iii) see the Taylor series about its own
+// centre converge with that ratio (half-width of the nearest far tile against its distance from the nearer pole).
+// The nearest far tile is the worst case on a smooth grid (k_level_check).  Written as positive conditions: NaN
+// parameters never qualify.  A side without far tiles imposes nothing.
+__device__ __forceinline__ bool level_ok(const FarGeom &fg, int k, int64_t N, const double *__restrict__ nus, int cpix, double nu_l,
+                                         double dw, double inv_dw, double g, double thr) {
+    const int T = fg.tile[k], nt = fg.n_tiles[k];
+    const int s = cpix >> fg.tile_shift[k];
+    const double *__restrict__ gm = fg.geom[k];
+    const double c_s = gm[3 * s];
+    const double adw = 0.7071067811865476 * dw;
+    const double off = fabs(nu_l - c_s) + adw;
+    const double pole2 = fma(off, off, g * g);
+    const double reach = (1.0 + SD_FAR_OVERHANG) * gm[3 * s + 2];  // k_m2l shortens its sums on this assumption
+    bool ok = (dw > 0.0) && (g >= 0.0) && (pole2 <= reach * reach);
+    if (s - 2 >= 0) {
+        const double nu_e = nus[(int64_t)(s - 1) * T - 1];      // last pixel of tile s - 2 (frequencies descend)
+        const double x = (nu_e - nu_l) * inv_dw, de = nu_e - c_s;
+        const double c_t = gm[3 * (s - 2)], h_t = gm[3 * (s - 2) + 1];
+        ok = ok && (x * x > thr) && (pole2 <= SD_FAR_RHO * SD_FAR_RHO * de * de) && (h_t <= SD_FAR_RHO * (c_t - nu_l - adw));
     }
-    auto far_a = [&](int t) {
-        const int k = t - pa;
-        return (k >= 0 && k < 3) ? (k == 0 ? fa[0] : (k == 1 ? fa[1] : fa[2])) : tile_is_far(geom[2 * t], geom[2 * t + 1], nu_l, dw, y);
-    };
-    auto far_b = [&](int t) {
-        const int k = t - pb;
-        return (k >= 0 && k < 3) ? (k == 0 ? fb[0] : (k == 1 ? fb[1] : fb[2])) : tile_is_far(geom[2 * t], geom[2 * t + 1], nu_l, dw, y);
-    };
-    while (a_ > 0 && !far_a(a_ - 1)) a_--;
-    while (a_ < tc && far_a(a_)) a_++;
-    while (b_ < n_tiles && !far_b(b_)) b_++;
-    while (b_ > tc + 1 && far_b(b_ - 1)) b_--;
-    a_out = a_;
-    b_out = b_;
+    if (s + 2 < nt) {
+        const double nu_e = nus[(int64_t)(s + 2) * T];          // first pixel of tile s + 2
+        const double x = (nu_e - nu_l) * inv_dw, de = nu_e - c_s;
+        const double c_t = gm[3 * (s + 2)], h_t = gm[3 * (s + 2) + 1];
+        ok = ok && (x * x > thr) && (pole2 <= SD_FAR_RHO * SD_FAR_RHO * de * de) && (h_t <= SD_FAR_RHO * (nu_l - adw - c_t));
+    }
+    return ok;
 }
 
 // One thread per (line, depth), d fastest (coalesced reads of the (L,D) inputs).  Writes depth-major
 // records/windows (64-byte records are two full sectors, so the transposing write is not wasteful).
-__global__ void __launch_bounds__(256) k_build_records(int64_t L, int D, int64_t N, const double *__restrict__ line_nu,
+__global__ void __launch_bounds__(256) k_build_records(int64_t L, int D, int64_t N, const double *__restrict__ nus,
+                                                       const double *__restrict__ line_nu,
                                                        const int *__restrict__ line_idx, const double *__restrict__ gammas,
                                                        int gamma_cols, const double *__restrict__ dws,
                                                        const double *__restrict__ alpha, const double *__restrict__ d_nu_p,
@@ -248,9 +268,6 @@ __global__ void __launch_bounds__(256) k_build_records(int64_t L, int D, int64_t
     const unsigned g = blockIdx.x * blockDim.x + threadIdx.x;  // L * D < 2^31 (checked by sd_set_lines)
     bool active = g < (unsigned)(L * D);
     unsigned nonempty = 0, wide = 0, zero_dw = 0;
-    int rad_k[SD_FAR_LEVELS];
-#pragma unroll
-    for (int k = 0; k < SD_FAR_LEVELS; k++) rad_k[k] = 0;
     bool e_lo = false, e_hi = false;
     unsigned long long key_lo = 0, key_hi = 0;
     if (active) {
@@ -286,39 +303,45 @@ __global__ void __launch_bounds__(256) k_build_records(int64_t L, int D, int64_t
         PairWin pw;
         pw.lo = (int)lo;
         pw.hi = (int)hi;
-        pw.near[0] = pw.near[1] = pw.near[2] = 0xffff0000u;
-        pw.pad0 = pw.pad1 = 0;
-        // Far-capable pair: the window holds at least one level-0 tile and all parameters are finite.  Such pairs
-        // form class 7; per hierarchy level they get the interval of tiles [nl, nh) around the line centre that are
-        // NOT far, and their window edges go to the edge list.
-        const bool fc = fg.enabled && (hi - lo >= fg.tile[0]) && (r.thr == r.thr) && (a == a) && (fabs(a) < 1e300);
-        if (fc) cls = SD_FC_CLASS;
-        win_cls[o] = (uint8_t)cls;
-        pw.cls = cls;
-        if (fg.enabled) {
-#pragma unroll
-            for (int k = 0; k < SD_FAR_LEVELS; k++) {
-                unsigned nl = 0, nh = 0xffffu;
-                int rad = 0;
-                const int tile = fg.tile[k], n_tiles = fg.n_tiles[k];
-                if (fc && hi - lo >= tile) {
-                    int tc = idx >> fg.tile_shift[k];  // tiles hold 2^tile_shift pixels
-                    if (tc >= n_tiles) tc = n_tiles - 1;
-                    int a_, b_;
-                    near_interval(fg.geom[k], n_tiles, tc, r.nu, dw, y, a_, b_);
-                    nl = (unsigned)a_;
-                    nh = (unsigned)b_;
-                    rad = max(tc - a_, b_ - 1 - tc);
-                }
-                pw.near[k] = nl | (nh << 16);
-                rad_k[k] = rad;
+        const int cpix = idx < N ? idx : (int)(N - 1);
+        pw.cpix = cpix;
+        pw.lmin = SD_FAR_LEVELS;
+        pw.sat = 0;
+        pw.pad = 0;
+        // Far-capable pair: all parameters finite, a lowest level lmin at which it (and every level above) passes
+        // level_ok, and a window of at least four level-lmin tiles (>= 512 pixels): only then can a tile two away from
+        // the centre be covered.  Such pairs form class SD_FC0 + lmin and their window edges go to the edge list.
+        if (fg.enabled && (hi - lo >= 512) && (r.thr == r.thr) && (a == a) && (fabs(a) < 1e300)) {
+            const int n_act = fg.lev_info[0];
+            int lmin = SD_FAR_LEVELS;
+            const double gl = y * dw;
+            for (int k = n_act - 1; k >= 0; k--) {
+                if (!level_ok(fg, k, N, nus, cpix, r.nu, dw, r.inv_dw, gl, r.thr)) break;
+                lmin = k;
             }
-            // window edges strictly inside the extended range (tiles only look for edges strictly inside themselves)
-            e_lo = fc && lo > fg.ext0 && lo < fg.ext1;
-            e_hi = fc && hi < N && hi > fg.ext0 && hi < fg.ext1;
-            key_lo = sd_edge_key(fg, 0, d, lo, (int)l);
-            key_hi = sd_edge_key(fg, 1, d, hi, (int)l);
+            if (lmin < n_act && hi - lo >= 4LL * fg.tile[lmin]) {
+                cls = SD_FC0 + lmin;
+                pw.lmin = (unsigned char)lmin;
+                unsigned sat = 0;
+                for (int k = lmin; k < n_act; k++) {
+                    long long nb0 = 0, nb1 = N;
+                    if (k + 1 < n_act) {  // the parent tile and its two neighbours
+                        const long long P = cpix >> fg.tile_shift[k + 1], Tp = fg.tile[k + 1];
+                        nb0 = (P - 1) * Tp > 0 ? (P - 1) * Tp : 0;
+                        nb1 = (P + 2) * Tp < N ? (P + 2) * Tp : N;
+                    }
+                    if (lo <= nb0 && hi >= nb1) sat |= 1u << k;
+                }
+                pw.sat = (unsigned char)sat;
+                // window edges strictly inside the extended range (tiles only look for edges strictly inside themselves)
+                e_lo = lo > fg.ext0 && lo < fg.ext1;
+                e_hi = hi < N && hi > fg.ext0 && hi < fg.ext1;
+                key_lo = sd_edge_key(fg, 0, d, lmin, lo, (int)l);
+                key_hi = sd_edge_key(fg, 1, d, lmin, hi, (int)l);
+            }
         }
+        win_cls[o] = (uint8_t)cls;
+        pw.cls = (unsigned char)cls;
         win[o] = pw;
         nonempty = hi > lo;
         wide = (hi > lo) && cls > 0;
@@ -326,25 +349,15 @@ __global__ void __launch_bounds__(256) k_build_records(int64_t L, int D, int64_t
     }
     // ---- block-level aggregation: a handful of global counters are shared by all 65 000 blocks of this kernel, and one
     // atomic per WARP on each of them serialised in L2 (ncu: the kernel was waiting there, not on memory or math)
-    __shared__ int s_rad[SD_FAR_LEVELS];
     __shared__ unsigned s_cnt[3];
     __shared__ unsigned s_edges[256 / 32];
     __shared__ unsigned long long s_base;
     const unsigned lane = threadIdx.x & 31, wid = threadIdx.x >> 5, lt = (1u << lane) - 1u;
-    if (threadIdx.x < SD_FAR_LEVELS) s_rad[threadIdx.x] = 0;
     if (threadIdx.x < 3) s_cnt[threadIdx.x] = 0;
     __syncthreads();
     const unsigned m_lo = __ballot_sync(0xffffffffu, e_lo), m_hi = __ballot_sync(0xffffffffu, e_hi);
     const int n_lo = __popc(m_lo), n_hi = __popc(m_hi);
-    if (fg.enabled) {
-#pragma unroll
-        for (int k = 0; k < SD_FAR_LEVELS; k++) {
-            int m = rad_k[k];
-            for (int o2 = 16; o2; o2 >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o2));
-            if (lane == 0 && m > 0) atomicMax(&s_rad[k], m);
-        }
-        if (lane == 0) s_edges[wid] = (unsigned)(n_lo + n_hi);
-    }
+    if (fg.enabled && lane == 0) s_edges[wid] = (unsigned)(n_lo + n_hi);
     const unsigned ne_w = __popc(__ballot_sync(0xffffffffu, nonempty));
     const unsigned wd_w = __popc(__ballot_sync(0xffffffffu, wide));
     const unsigned zd_w = __popc(__ballot_sync(0xffffffffu, zero_dw));
@@ -359,9 +372,6 @@ __global__ void __launch_bounds__(256) k_build_records(int64_t L, int D, int64_t
         if (s_cnt[1]) atomicAdd(&stats[5], (unsigned long long)s_cnt[1]);
         if (s_cnt[2]) atomicAdd(&stats[6], (unsigned long long)s_cnt[2]);
         if (fg.enabled) {
-            // the running maximum is reached early: most blocks find nothing to raise (racy read, monotone update)
-            for (int k = 0; k < SD_FAR_LEVELS; k++)
-                if (s_rad[k] > *(volatile int *)&fg.near_rad[k]) atomicMax(&fg.near_rad[k], s_rad[k]);
             unsigned tot = 0;
             for (int w2 = 0; w2 < 256 / 32; w2++) { const unsigned c = s_edges[w2]; s_edges[w2] = tot; tot += c; }
             s_base = tot ? atomicAdd(fg.edge_count, (unsigned long long)tot) : 0ull;
@@ -486,23 +496,21 @@ int sd_k2_prepare(sd_ctx *c) {
     SD_TRY(sd_ensure(c, c->cls_off, sizeof(int) * D * (SD_NCLS + 1)));
     k_dnu<<<1, 1024, 0, c->stream>>>(c->N, c->nus.as<double>(), c->d_nu.as<double>());
     SD_TRY(sd_launch_check(c, "k_dnu"));
-    // pixels per thread of the line kernel (level-0 tile = 256 * P pixels) and the geometry of the tile hierarchy
+    // pixels per thread of the line kernel and the geometry of the tile hierarchy (64 * 8^k pixels, fixed: the tiles
+    // decide the summation order inside a pixel and must not depend on the launch configuration or the shard)
     c->k2_P = sd_k2_choose_P(c);
     FarGeom &fg = c->far_geom;
     for (int k = 0; k < SD_FAR_LEVELS; k++) {
-        fg.tile[k] = (32 * c->k2_NW * c->k2_P) << (SD_FAR_SHIFT * k);
-        fg.tile_shift[k] = 0;
-        while ((1 << fg.tile_shift[k]) < fg.tile[k]) fg.tile_shift[k]++;
-        SD_CHECK(c, (1 << fg.tile_shift[k]) == fg.tile[k], SD_ERR_STATE, "tile sizes must be powers of two");
+        fg.tile_shift[k] = SD_FAR_TILE0_SHIFT + SD_FAR_SHIFT * k;
+        fg.tile[k] = 1 << fg.tile_shift[k];
         fg.n_tiles[k] = (int)((c->N + fg.tile[k] - 1) / fg.tile[k]);
-        SD_CHECK(c, fg.n_tiles[k] < 65535, SD_ERR_ARG, "grid too long for 16-bit tile indices");
-        SD_TRY(sd_ensure(c, c->tile_geom[k], sizeof(double) * 2 * fg.n_tiles[k]));
+        SD_TRY(sd_ensure(c, c->tile_geom[k], sizeof(double) * 3 * fg.n_tiles[k]));
         fg.geom[k] = c->tile_geom[k].as<double>();
         k_tile_geometry<<<(fg.n_tiles[k] + 255) / 256, 256, 0, c->stream>>>(c->N, fg.tile[k], fg.n_tiles[k], c->nus.as<double>(),
                                                                           c->tile_geom[k].as<double>());
         SD_TRY(sd_launch_check(c, "k_tile_geometry"));
     }
-    fg.near_rad = nullptr;
+    fg.lev_info = nullptr;
     fg.enabled = 0;
     fg.edge_keys = nullptr;
     fg.edge_off = nullptr;
@@ -518,6 +526,7 @@ int sd_k2_prepare(sd_ctx *c) {
         SD_CUDA(c, cudaMemsetAsync(c->cls_off.p, 0, sizeof(int) * D * (SD_NCLS + 1), c->stream));
         sd_phase_end(c, SD_PH_PREP);
         c->records_ready = true;
+        c->far_active = 0;
         return SD_OK;
     }
     SD_TRY(sd_ensure(c, c->line_idx, sizeof(int) * L));
@@ -530,12 +539,13 @@ int sd_k2_prepare(sd_ctx *c) {
         while ((1LL << fg.pix_bits) <= c->N) fg.pix_bits++;
         while ((1 << fg.depth_bits) < D) fg.depth_bits++;
         while ((1LL << fg.l_bits) < L) fg.l_bits++;
-        SD_CHECK(c, 1 + fg.depth_bits + fg.pix_bits + fg.l_bits <= 64, SD_ERR_ARG,
+        SD_CHECK(c, 1 + fg.depth_bits + SD_FAR_LMIN_BITS + fg.pix_bits + fg.l_bits <= 64, SD_ERR_ARG,
                  "far-field scheme: (depth, pixel, line) does not fit a 64-bit sort key (D = %d, N = %lld, L = %lld); use "
                  "sd_set_farfield(ctx, 0)", D, (long long)c->N, (long long)L);
-        SD_TRY(sd_ensure(c, c->near_rad, sizeof(int) * SD_FAR_LEVELS));
-        SD_CUDA(c, cudaMemsetAsync(c->near_rad.p, 0, sizeof(int) * SD_FAR_LEVELS, c->stream));
-        fg.near_rad = c->near_rad.as<int>();
+        SD_TRY(sd_ensure(c, c->lev_info, sizeof(int) * (SD_FAR_LEVELS + 1)));
+        k_level_check<<<1, 256, 0, c->stream>>>(fg, c->N, c->lev_info.as<int>());
+        SD_TRY(sd_launch_check(c, "k_level_check"));
+        fg.lev_info = c->lev_info.as<int>();
         SD_TRY(sd_ensure(c, c->edge_unsorted, sizeof(unsigned long long) * 2 * n));  // worst case: both edges of every pair
         SD_TRY(sd_ensure(c, c->edge_count, sizeof(unsigned long long)));
         SD_CUDA(c, cudaMemsetAsync(c->edge_count.p, 0, sizeof(unsigned long long), c->stream));
@@ -548,7 +558,7 @@ int sd_k2_prepare(sd_ctx *c) {
                                                                   c->line_idx.as<int>());
     SD_TRY(sd_launch_check(c, "k_line_idx"));
     k_build_records<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(
-        L, D, c->N, c->l_nu.as<double>(), c->line_idx.as<int>(), c->gammas.as<double>(), c->gamma_cols,
+        L, D, c->N, c->nus.as<double>(), c->l_nu.as<double>(), c->line_idx.as<int>(), c->gammas.as<double>(), c->gamma_cols,
         c->dws.as<double>(), c->l_alpha.as<double>(), c->d_nu.as<double>(), c->rec.as<LineRec>(), c->win.as<PairWin>(),
         c->win_cls.as<uint8_t>(), fg, c->stats.as<unsigned long long>());
     SD_TRY(sd_launch_check(c, "k_build_records"));

@@ -47,10 +47,14 @@ int env_int_early(const char *name, int dflt) {
 constexpr int THREADS = 256;
 constexpr int WARPS = THREADS / 32;
 constexpr int FAR_CH = 1024;                // candidates per cooperative scan chunk of k_far_coeffs
+constexpr int K1 = SD_FAR_K + 1;            // coefficients per polynomial = multipole moments per tile
 struct __align__(16) FarRec { double nu, dw, y, K; };  // = the first 32 bytes of LineRec
-static_assert((SD_FAR_K + 1) % 3 == 0, "the series length is tested every third term");
-static_assert(WARPS == (1 << SD_FAR_SHIFT), "k_far_coeffs maps the warps of a CTA to the children of a tile");
+static_assert(K1 == 32, "k_m2l maps the lanes of a warp to the coefficients; k_s2m / k_far_coeffs reduce into lane k");
+static_assert(K1 % 4 == 0, "the series length is tested every fourth term");
+static_assert(WARPS == (1 << SD_FAR_SHIFT), "k_far_coeffs / k_s2m / k_m2l map the warps of a CTA to the children of a tile");
 constexpr size_t FAR_SMEM = (size_t)FAR_CH * sizeof(FarRec) + FAR_CH;
+constexpr int FAR_MAX_SRC = 3 * SD_FAR_LEVELS;  // candidate lists of one k_far_coeffs group
+constexpr int M2L_DC = 14;                  // depth points per k_m2l CTA (accumulators per thread)
 
 struct __align__(16) WEntry {
     // far-wing path (48 B)
@@ -71,17 +75,21 @@ static_assert(sizeof(WEntry) == 96, "WEntry layout");
 struct LineArgs {
     int64_t L, N, p0, p1;
     int D;
-    int tile0;     // global index of the first tile of this launch
-    int n_tiles;   // global number of tiles
+    int tile0;     // global index of the first CTA tile of this launch
+    int n_tiles;   // global number of CTA tiles
     const double *nus;
     const int *line_idx;
     const LineRec *rec;
     const PairWin *win;   // (depth, line) window records
     const int *cls_list, *cls_off;
-    FarGeom fg;                  // tile hierarchy; fg.near[0] == nullptr: far field disabled
-    double *far_coef[SD_FAR_LEVELS];   // per level: (D, n_tiles_launch[k], SD_FAR_K + 1)
+    FarGeom fg;                  // tile hierarchy; fg.enabled == 0: far field disabled
+    int n_act;                   // usable hierarchy levels (level n_act - 1 is the top level)
+    double *far_coef[SD_FAR_LEVELS];   // per level: (D, n_tiles_launch[k], K1)
     int far_tile0[SD_FAR_LEVELS];      // first global tile of this launch, per level
     int far_ntl[SD_FAR_LEVELS];        // tiles of this launch, per level
+    double *far_mom[SD_FAR_LEVELS];    // per level: (D, n_src[k], K1) multipole moments of the saturated pairs
+    int src_tile0[SD_FAR_LEVELS];      // first global source tile of this launch, per level
+    int n_src[SD_FAR_LEVELS];          // source tiles of this launch, per level
     double *out;                 // (D, p1 - p0)
     unsigned long long *stats;
 };
@@ -120,7 +128,7 @@ __device__ __forceinline__ void class_range(const LineArgs &a, int d, int cls, i
         return;
     }
     const int lo = a.cls_off[d * (SD_NCLS + 1) + cls], hi = a.cls_off[d * (SD_NCLS + 1) + cls + 1];
-    if (cls >= SD_NCLS - 2) {  // classes 6 (unbounded half-width) and 7 (whole grid): every pair is a candidate
+    if (cls >= SD_FC0 - 1) {  // class 6 (unbounded half-width): every pair is a candidate
         ja = lo;
         jb = hi;
         return;
@@ -151,35 +159,33 @@ __device__ __forceinline__ int warp_lower_bound_u64(const unsigned long long *__
     return a;
 }
 
-// Far-capable pairs (class 7, sorted by window centre) whose centre lies within `rad` level-`lev` tiles of tile `t`.
-__device__ __forceinline__ void fc_near_range(const LineArgs &a, int d, int lev, int t, int &ja, int &jb) {
-    const int lo = a.cls_off[d * (SD_NCLS + 1) + SD_FC_CLASS], hi = a.cls_off[d * (SD_NCLS + 1) + SD_FC_CLASS + 1];
+// Far-capable pairs with lmin = m (class SD_FC0 + m, sorted by centre) whose centre pixel lies in [c0, c1).  The centre
+// pixel is line_idx clamped to N - 1, so a range that reaches the end of the grid takes the lines behind it too.
+__device__ __forceinline__ void fc_centre_range(const LineArgs &a, int d, int m, long long c0, long long c1, int &ja, int &jb) {
+    const int lo = a.cls_off[d * (SD_NCLS + 1) + SD_FC0 + m], hi = a.cls_off[d * (SD_NCLS + 1) + SD_FC0 + m + 1];
     const int *list_d = a.cls_list + (size_t)d * a.L;
     const int *line_idx = a.line_idx;
-    const long long T = a.fg.tile[lev], rad = a.fg.near_rad[lev];
     auto key = [&](int j) { return line_idx[list_d[j]]; };
-    ja = warp_first_below(key, lo, hi, clamp_i32(((long long)t + rad + 1) * T));  // centre <  (t + rad + 1) T
-    jb = warp_first_below(key, ja, hi, clamp_i32(((long long)t - rad) * T));      // centre <  (t - rad) T
+    ja = warp_first_below(key, lo, hi, c1 >= a.N ? 2147483647 : clamp_i32(c1));  // centre <  c1
+    jb = (c0 <= 0) ? hi : warp_first_below(key, ja, hi, clamp_i32(c0));           // centre <  c0
 }
 
-// Far-capable pairs of depth d with a window start (which = 0) or end (which = 1) strictly inside (t0, t1).
-__device__ __forceinline__ void fc_edge_range(const LineArgs &a, int d, int which, int64_t t0, int64_t t1, int &ja, int &jb) {
-    const int lo = a.fg.edge_off[which * (a.D + 1) + d], hi = a.fg.edge_off[which * (a.D + 1) + d + 1];
-    ja = warp_lower_bound_u64(a.fg.edge_keys, lo, hi, sd_edge_key(a.fg, which, d, t0 + 1, 0));
-    jb = warp_lower_bound_u64(a.fg.edge_keys, ja, hi, sd_edge_key(a.fg, which, d, t1, 0));
+// Far-capable pairs of depth d and lmin = m with a window start (which = 0) or end (which = 1) strictly inside (t0, t1).
+__device__ __forceinline__ void fc_edge_range(const LineArgs &a, int d, int which, int m, int64_t t0, int64_t t1, int &ja, int &jb) {
+    const int o = (which * a.D + d) * SD_FAR_LEVELS + m;
+    const int lo = a.fg.edge_off[o], hi = a.fg.edge_off[o + 1];
+    ja = warp_lower_bound_u64(a.fg.edge_keys, lo, hi, sd_edge_key(a.fg, which, d, m, t0 + 1, 0));
+    jb = warp_lower_bound_u64(a.fg.edge_keys, ja, hi, sd_edge_key(a.fg, which, d, m, t1, 0));
 }
 
-// one 32-byte gather (two 16-byte loads of the same sector)
+// one 16-byte gather
 __device__ __forceinline__ PairWin load_win(const PairWin *__restrict__ w) {
-    const int4 a = __ldg(reinterpret_cast<const int4 *>(w)), b = __ldg(reinterpret_cast<const int4 *>(w) + 1);
+    const int4 a = __ldg(reinterpret_cast<const int4 *>(w));
     PairWin r;
-    r.lo = a.x; r.hi = a.y; r.near[0] = (unsigned)a.z; r.near[1] = (unsigned)a.w;
-    r.near[2] = (unsigned)b.x; r.cls = b.y; r.pad0 = 0; r.pad1 = 0;
+    r.lo = a.x; r.hi = a.y; r.cpix = a.z;
+    r.cls = (unsigned char)(a.w & 0xff); r.lmin = (unsigned char)((a.w >> 8) & 0xff); r.sat = (unsigned char)((a.w >> 16) & 0xff);
+    r.pad = 0;
     return r;
-}
-
-__device__ __forceinline__ unsigned near_of(const PairWin &w, int lev) {  // no dynamically indexed registers
-    return lev == 0 ? w.near[0] : (lev == 1 ? w.near[1] : w.near[2]);
 }
 
 // x = (nu_i - nu_l) / dw (voigt.py:148) must be the correctly rounded quotient: the W4 regions are chosen by comparing
@@ -200,37 +206,39 @@ __device__ __noinline__ double exact_contribution(double nu_i, double nu_l, doub
     return sdm::humlicek_re(x, y) * K;
 }
 
-// The same integer test in both kernels: the pair covers the whole global tile and the tile lies outside the pair's
-// near interval -> it is expanded (k_far_coeffs) and must be skipped by the direct kernel.
-__device__ __forceinline__ bool pair_is_far(int lo, int hi, unsigned near, int64_t t0, int64_t t1, int tile) {
-    const int nl = (int)(near & 0xffffu), nh = (int)(near >> 16);
-    return (lo <= t0) && (hi >= t1) && (tile < nl || tile >= nh);
+// The same integer test in all kernels: at level `lev` (tiles of 2^shift pixels) the pair is FAR from tile `t` =
+// [t0, t1): expandable there, centre at least two tiles away, window covering the tile.  Farness by distance at one
+// level implies it at every lower level >= lmin and covering a tile implies covering its children, so "far at some
+// level" is decided at level lmin alone (k_lines) and "served at level lev" = far at lev and not far at lev + 1.
+__device__ __forceinline__ bool pair_is_far(const PairWin &w, int lev, int shift, int t, int64_t t0, int64_t t1) {
+    const int ds = (w.cpix >> shift) - t;
+    return (lev >= (int)w.lmin) && (ds >= 2 || ds <= -2) && (w.lo <= t0) && (w.hi >= t1);
 }
 
 // ------------------------------------------------------------------------------------------------------------------
-// Far-field coefficients of one (level-`lev` tile, depth): C_k = -W Im(w+^(k+1) + w-^(k+1)),  w = -h / (nu_c - p),
-// W = K dw / (2 sqrt(pi) h);  the contribution of the pair at pixel nu is  sum_k C_k ((nu - nu_c)/h)^k.
-// A pair is expanded at the HIGHEST level at which it is far: level `lev` takes the far-capable pairs that cover this
-// tile, are far from it, and are NOT far for the parent tile of level lev + 1.  Those are found without scanning:
-//   (A) pairs that cover the parent but have it in their near interval: a contiguous range (by window centre) of the
-//       class-7 list around the parent;
-//   (B) pairs that do not cover the parent (a window edge lies strictly inside it): two ranges of the edge-sorted lists.
+// Far-field coefficients of one (level-`lev` tile, depth), direct part: C_k = A Im(v w^k) summed over the two poles,
+// v = 1 / (nu_c - p), w = -h v, A = K dw / (2 sqrt(pi));  the contribution of the pair at pixel nu is
+// sum_k C_k ((nu - nu_c)/h)^k.  This kernel expands the pairs that are served at level `lev` (far there, not far for
+// the parent tile) and are NOT saturated there -- the saturated ones go through k_s2m / k_m2l.  They are found without
+// scanning, per lmin class m <= lev:
+//   (A) pairs whose centre lies in the parent tile or one of its two neighbours (never far from the parent): a
+//       contiguous range (by centre) of the class list; the saturated ones are skipped;
+//   (B) pairs far from the parent by distance that do not cover it (a window edge lies strictly inside it): two ranges
+//       of the edge-sorted lists.
 // The candidates are a property of the PARENT, so one CTA serves the eight children of a parent (warp w = child w):
-//   scan     the CTA walks the candidate lists in chunks of FAR_CH; a thread gathers the 32-byte window record of a
+//   scan     the CTA walks the candidate lists in chunks of FAR_CH; a thread gathers the 16-byte window record of a
 //            candidate ONCE, tests it against all eight children (integer compares) and leaves an 8-bit acceptance mask;
 //            the 32 bytes of LineRec the expansion needs are staged in shared memory with cp.async if any child wants
 //            them (one gather per candidate and parent instead of one per candidate and child);
-//   expand   every warp picks its child's bit out of the masks, compacts the accepted records into its own queue in list
-//            order (ballots) and expands full batches of 32, one pair per lane, all lanes busy.
-// The top level has no parent: groups of eight consecutive tiles walk a fixed slice of the whole class-7 list
-// (`nsplit` CTAs per group; k_far_reduce adds the partial sums in slice order).  Groups, slices, chunking and queue order
+//   expand   every warp walks the dense list 32 entries at a time, one pair per lane.
+// The top level has no parent: groups of eight consecutive tiles walk a fixed slice of the whole class lists
+// (`nsplit` CTAs per group; k_far_reduce adds the partial sums in slice order).  Groups, slices, chunking and list order
 // depend on the global tile index and the candidate lists only, never on the shard, so the summation order -- and the
 // result, bit for bit -- is the same for every partition of the grid.
 // series length by floor(-8 log2(rho^2)) (see `expand`): filled by far_terms_table(), uploaded once per device
 __constant__ unsigned char FAR_TERMS[256];
 
 void far_terms_table(unsigned char *tab) {
-    constexpr int K1 = SD_FAR_K + 1;
     for (int t = 0; t < 256; t++) {
         const double lg = 0.5 * (t / 8.0 - 0.087);  // lower bound of log2(1 / rho) for this index
         int n = K1;
@@ -242,17 +250,26 @@ void far_terms_table(unsigned char *tab) {
     }
 }
 
+// terms needed for ratio^2 = rho2: (n + 1) rho^n <= (K1 + 1) SD_FAR_RHO^K1 (the bound of the full series at the far
+// criterion)  <=>  n >= ~K1 log2(1 / SD_FAR_RHO) / log2(1 / rho).  -log2(rho^2) is read off the exponent and the top
+// mantissa bits of rho^2 in steps of 1/8 (a lower bound: the series is never shorter than the rule asks) and indexes
+// a 256-entry table -- six integer instructions instead of ~30 with a float logarithm and division
+__device__ __forceinline__ int far_terms(double rho2) {
+    const int t8 = (0x3ff00000 - __double2hiint(rho2)) >> 17;  // floor(8 * -L), L <= log2(rho^2) <= L + 0.086
+    return FAR_TERMS[min(max(t8, 0), 255)];
+}
+
 __global__ void __launch_bounds__(THREADS) k_far_coeffs(LineArgs a, int lev, int count_stats, int nsplit, double *part) {
-    constexpr int K1 = SD_FAR_K + 1;
-    __shared__ int s_ja[3], s_jb[3];
+    __shared__ int s_ja[FAR_MAX_SRC], s_jb[FAR_MAX_SRC];
     extern __shared__ __align__(16) unsigned char far_smem[];
     FarRec *const s_rec = reinterpret_cast<FarRec *>(far_smem);                        // [FAR_CH] dense records of the chunk
     unsigned char *const s_mask = reinterpret_cast<unsigned char *>(s_rec + FAR_CH);   // [FAR_CH] their child masks
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int d = blockIdx.y;
-    const int tile_px = a.fg.tile[lev];
-    const bool has_parent = lev + 1 < SD_FAR_LEVELS;
+    const int shift = a.fg.tile_shift[lev], tile_px = a.fg.tile[lev];
+    const bool has_parent = lev + 1 < a.n_act;
     const int plev = has_parent ? lev + 1 : lev;
+    const int pshift = a.fg.tile_shift[plev];
     const int group = (a.far_tile0[lev] >> SD_FAR_SHIFT) + (int)blockIdx.x / nsplit;  // = parent tile index
     const int split = (int)blockIdx.x % nsplit;
     const int child0 = group << SD_FAR_SHIFT;
@@ -261,7 +278,7 @@ __global__ void __launch_bounds__(THREADS) k_far_coeffs(LineArgs a, int lev, int
     const int tile = tile_ok ? tile_w : a.far_tile0[lev];
     const int64_t t0 = (int64_t)tile * tile_px;
     const int64_t t1 = (t0 + tile_px < a.N) ? t0 + tile_px : a.N;
-    const double nu_c = a.fg.geom[lev][2 * tile], h = a.fg.geom[lev][2 * tile + 1];
+    const double nu_c = a.fg.geom[lev][3 * tile], h = a.fg.geom[lev][3 * tile + 1];
     const int ptile = group;
     const int64_t pt0 = (int64_t)ptile * a.fg.tile[plev];
     const int64_t pt1 = (pt0 + a.fg.tile[plev] < a.N) ? pt0 + a.fg.tile[plev] : a.N;
@@ -275,65 +292,65 @@ __global__ void __launch_bounds__(THREADS) k_far_coeffs(LineArgs a, int lev, int
     const size_t drow = (size_t)d * a.L;
     const int *list_d = a.cls_list + drow;
     const unsigned long long lmask = (1ull << a.fg.l_bits) - 1ull;  // line index = low bits of a window-edge key
-    if (warp < 3) {
-        int ja, jb;
+    // candidate lists: source 3 m + kind (kind 0: centre range of class m; 1 / 2: window starts / ends of class m)
+    const int n_src = 3 * (lev + 1);
+    for (int src = warp; src < n_src; src += WARPS) {
+        const int m = src / 3, kind = src - 3 * m;
+        int ja = 0, jb = 0;
         if (!has_parent) {
-            ja = a.cls_off[d * (SD_NCLS + 1) + SD_FC_CLASS];
-            jb = (warp == 0) ? a.cls_off[d * (SD_NCLS + 1) + SD_FC_CLASS + 1] : ja;
-        } else if (warp == 0) {
-            fc_near_range(a, d, plev, ptile, ja, jb);
+            if (kind == 0) {
+                ja = a.cls_off[d * (SD_NCLS + 1) + SD_FC0 + m];
+                jb = a.cls_off[d * (SD_NCLS + 1) + SD_FC0 + m + 1];
+            }
+        } else if (kind == 0) {
+            fc_centre_range(a, d, m, ((long long)ptile - 1) * a.fg.tile[plev], ((long long)ptile + 2) * a.fg.tile[plev], ja, jb);
         } else {
-            fc_edge_range(a, d, warp - 1, pt0, pt1, ja, jb);
+            fc_edge_range(a, d, kind - 1, m, pt0, pt1, ja, jb);
         }
         // this CTA's slice of the range (a function of the range and nsplit only)
         const int len = (jb - ja + nsplit - 1) / nsplit;
         const int sa = min(ja + split * len, jb), sb = min(sa + len, jb);
-        if (lane == 0) { s_ja[warp] = sa; s_jb[warp] = sb; }
+        if (lane == 0) { s_ja[src] = sa; s_jb[src] = sb; }
     }
     __syncthreads();
     double C[K1];
 #pragma unroll
     for (int k = 0; k < K1; k++) C[k] = 0.0;
     unsigned long long n_far = 0, n_terms = 0;
-    const double inv_h = 1.0 / h;
     const unsigned lt_mask = (1u << lane) - 1u;
 
-    // One accepted pair: 21 Taylor coefficients of its two poles about the tile centre.  Called with a dense batch of
+    // One accepted pair: Taylor coefficients of its two poles about the tile centre.  Called with a dense batch of
     // pairs (one per lane); `have` is false only in the last, partial batch.
     auto expand = [&](bool have, const FarRec &r) {
-        double Wn = 0.0, w1r = 0.0, w1i = 0.0, w2r = 0.0, w2i = 0.0;
+        double An = 0.0, w1r = 0.0, w1i = 0.0, w2r = 0.0, w2i = 0.0, v1i = 0.0, v2i = 0.0;
         int nterms = 0;
         if (have) {
             const double g = r.y * r.dw;                                // Lorentz half-width in Hz
-            Wn = -r.K * r.dw * (0.5 * sdm::INV_SQRT_PI) * inv_h;        // -W
+            An = r.K * r.dw * (0.5 * sdm::INV_SQRT_PI);
             const double adw = 0.7071067811865476 * r.dw;
-            // w = -h / (D - i g) = -h (D + i g) / (D^2 + g^2) for the two poles
+            // v = 1 / (D - i g) = (D + i g) / (D^2 + g^2),  w = -h v  for the two poles
             const double D1 = nu_c - (r.nu + adw), D2 = nu_c - (r.nu - adw);
             const double q1 = sdm::rcp_fast(fma(D1, D1, g * g)), q2 = sdm::rcp_fast(fma(D2, D2, g * g));
+            v1i = g * q1; v2i = g * q2;
             const double i1 = -h * q1, i2 = -h * q2;
             w1r = D1 * i1; w1i = g * i1; w2r = D2 * i2; w2i = g * i2;
-            // terms needed: (n + 1) rho^n <= (K1 + 1) rho_far^K1 (the bound of the full series at the far criterion)
-            // <=>  n >= ~K1 log2(1 / rho_far) / log2(1 / rho);  rho^2 = h^2 max(q1, q2).  -log2(rho^2) is read off the
-            // exponent and the top mantissa bits of rho^2 in steps of 1/8 (a lower bound: the series is never shorter
-            // than the rule asks) and indexes a 256-entry table -- six integer instructions instead of ~30 with the
-            // float logarithm and division this used to be (9 % of the kernel's instructions, ncu round 2)
-            const int t8 = (0x3ff00000 - __double2hiint(h * h * fmax(q1, q2))) >> 17;  // floor(8 * -L), L <= log2(rho^2) <= L + 0.086
-            nterms = FAR_TERMS[min(max(t8, 0), 255)];
+            nterms = far_terms(h * h * fmax(q1, q2));
             if (count_stats) n_far++;
         }
         // queue neighbours are neighbours in frequency, at similar distances from the tile: warp-uniform series length
         const int nt = __reduce_max_sync(0xffffffffu, nterms);
-        if (count_stats && have) n_terms += (unsigned long long)min(K1, 3 * ((nt + 2) / 3));  // terms the loop below executes
-        // Im(w^(k+1)) by the real three-term recurrence of the powers of a complex number,
-        //   s_(k+1) = 2 Re(w) s_k - |w|^2 s_(k-1),  s_0 = 0, s_1 = Im w,
+        if (count_stats && have) n_terms += (unsigned long long)min(K1, 4 * ((nt + 3) / 4));  // terms the loop below executes
+        // Im(v w^k) by the real three-term recurrence of a geometric sequence of complex numbers,
+        //   s_(k+1) = 2 Re(w) s_k - |w|^2 s_(k-1),  s_0 = Im v, s_(-1) = Im(v / w) = Im(-1 / h) = 0,
         // two instructions per pole and term instead of the four of a complex product (the recurrence loses about one
-        // bit per step relative to |w|^k, i.e. < 1e-13 over 21 terms).
+        // bit per step relative to |w|^k, i.e. < 1e-13 over the series).  No division by h: a one-pixel tile (h = 0)
+        // gets its exact constant term.
         const double a1 = w1r + w1r, b1 = fma(w1r, w1r, w1i * w1i), a2 = w2r + w2r, b2 = fma(w2r, w2r, w2i * w2i);
-        double s1 = w1i, s1p = 0.0, s2 = w2i, s2p = 0.0;
+        double s1 = v1i, s1p = 0.0, s2 = v2i, s2p = 0.0;
 #pragma unroll
         for (int k = 0; k < K1; k++) {
-            if (k % 3 == 0 && k >= nt) break;  // checked every third term (the extra terms only add accuracy)
-            C[k] = fma(Wn, s1 + s2, C[k]);
+            if (k % 4 == 0 && k >= nt) break;  // checked every fourth term (the extra terms only add accuracy)
+            C[k] = fma(An, s1 + s2, C[k]);
             if (k + 1 < K1) {
                 double t;
                 t = fma(a1, s1, -(b1 * s1p)); s1p = s1; s1 = t;
@@ -345,18 +362,16 @@ __global__ void __launch_bounds__(THREADS) k_far_coeffs(LineArgs a, int lev, int
     // Per chunk of FAR_CH candidates:
     //   test     a thread gathers the window record of its candidates ONCE and tests it against all eight children;
     //   compact  the candidates wanted by ANY child (of the whole group, launched or not: the list must not depend on
-    //            the shard) are packed densely, in list order, into shared memory: record (cp.async) + child mask.  Far
-    //            from the group every covering pair is wanted by all eight children, near it by five or six, so the
-    //            dense list is (nearly) the list of every child;
-    //   expand   every warp walks the dense list 32 entries at a time, one pair per lane, skipping the few entries whose
-    //            mask lacks its child -- no per-warp queue, no ballots, no copies (they were a quarter of the kernel's
-    //            instructions when every warp compacted its own list).
+    //            the shard) are packed densely, in list order, into shared memory: record (cp.async) + child mask;
+    //   expand   every warp walks the dense list 32 entries at a time, one pair per lane, skipping the entries whose
+    //            mask lacks its child.
     constexpr int ROUNDS = FAR_CH / THREADS;
     constexpr int SEGS = ROUNDS * WARPS;       // (round, warp) segments of 32 candidates, in list order
     static_assert(SEGS == 32, "one lane per segment in the offset scan");
     __shared__ int s_cnt[SEGS];
-    for (int src = 0; src < 3; src++) {
+    for (int src = 0; src < n_src; src++) {
         const int ja = s_ja[src], jb = s_jb[src];
+        const int kind = src % 3;
         for (int base = ja; base < jb; base += FAR_CH) {
             // ---- test
             unsigned mk[ROUNDS];
@@ -367,26 +382,22 @@ __global__ void __launch_bounds__(THREADS) k_far_coeffs(LineArgs a, int lev, int
                 unsigned mask = 0;
                 int l = 0;
                 if (j < jb) {
-                    l = (src == 0) ? list_d[j] : (int)(a.fg.edge_keys[j] & lmask);
+                    l = (kind == 0) ? list_d[j] : (int)(a.fg.edge_keys[j] & lmask);
                     const PairWin pw = load_win(a.win + drow + l);
-                    const int lo = pw.lo, hi = pw.hi;
-                    bool okp = true;
-                    if (has_parent) {
-                        const bool covers_parent = (lo <= pt0) && (hi >= pt1);
-                        if (src == 0) {  // (A): covers the parent, parent inside the near interval
-                            okp = covers_parent && !pair_is_far(lo, hi, near_of(pw, plev), pt0, pt1, ptile);
-                        } else {         // (B): an edge strictly inside the parent; both edges inside: via its start
-                            okp = !covers_parent && !(src == 2 && lo > pt0 && lo < pt1);
-                        }
+                    bool okp;
+                    if (kind == 0) {  // (A) / top level: served here unless the multipole path takes the pair
+                        okp = !((pw.sat >> lev) & 1u);
+                    } else {          // (B): far from the parent by distance; both edges inside the parent: via its start
+                        const int dsp = (pw.cpix >> pshift) - ptile;
+                        okp = (dsp >= 2 || dsp <= -2) && !(kind == 2 && pw.lo > pt0 && pw.lo < pt1);
                     }
                     if (okp) {
-                        const unsigned near = near_of(pw, lev);
 #pragma unroll
                         for (int cc = 0; cc < WARPS; cc++) {
                             const int tcc = child0 + cc;
                             const int64_t c0 = (int64_t)tcc * tile_px;
                             const int64_t c1 = (c0 + tile_px < a.N) ? c0 + tile_px : a.N;
-                            if (tcc < a.fg.n_tiles[lev] && pair_is_far(lo, hi, near, c0, c1, tcc)) mask |= 1u << cc;
+                            if (tcc < a.fg.n_tiles[lev] && pair_is_far(pw, lev, shift, tcc, c0, c1)) mask |= 1u << cc;
                         }
                     }
                 }
@@ -439,7 +450,7 @@ __global__ void __launch_bounds__(THREADS) k_far_coeffs(LineArgs a, int lev, int
         for (int o2 = 16; o2; o2 >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o2);
         if (lane == k) mine = v;
     }
-    if (tile_ok && lane < K1) {
+    if (tile_ok) {
         const size_t tl = (size_t)d * a.far_ntl[lev] + (tile - a.far_tile0[lev]);
         if (nsplit > 1) part[(tl * nsplit + split) * K1 + lane] = mine;
         else a.far_coef[lev][tl * K1 + lane] = mine;
@@ -459,16 +470,15 @@ __global__ void __launch_bounds__(THREADS) k_far_coeffs(LineArgs a, int lev, int
 }
 
 // slices per level (constants: the summation order must not depend on the shard)
-__host__ __device__ constexpr int far_nsplit_base(int lev) { return lev == SD_FAR_LEVELS - 1 ? 32 : (lev == 0 ? 2 : 8); }
+__host__ __device__ constexpr int far_nsplit_base(int lev, bool top) { return top ? 32 : (lev <= 1 ? 1 : 8); }
 // SD_FAR_NSPLIT_SCALE (tuning experiments only: it changes the grouping of the partial sums, i.e. the last bits)
-static int far_nsplit(int lev) {
+static int far_nsplit(int lev, bool top) {
     static const int scale = env_int_early("SD_FAR_NSPLIT_SCALE", 1);
-    return far_nsplit_base(lev) * (scale >= 1 && scale <= 8 ? scale : 1);
+    return far_nsplit_base(lev, top) * (scale >= 1 && scale <= 8 ? scale : 1);
 }
 
 // sum of the nsplit partial coefficient sets of a level, in slice order
 __global__ void k_far_reduce(int n, int nsplit, const double *__restrict__ part, double *__restrict__ coef) {
-    constexpr int K1 = SD_FAR_K + 1;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;  // (depth, tile) * K1 + k
     if (i >= n) return;
     const int td = i / K1, k = i - td * K1;
@@ -478,13 +488,199 @@ __global__ void k_far_reduce(int n, int nsplit, const double *__restrict__ part,
 }
 
 // ------------------------------------------------------------------------------------------------------------------
+// Multipole moments of one (level-`lev` source tile s, depth):  M_k = sum_pairs A Im(u+^k + u-^k),  k = 1..K1,
+// u = (pole - c_s) / scale_s,  over the pairs centred in s that are SATURATED at this level (window covering the whole
+// interaction neighbourhood of s), so that   sum_pairs contribution(nu) = (1 / scale_s) sum_k M_k / tau^(k+1),
+// tau = (nu - c_s) / scale_s,  for every pixel at least two tiles away.  ONE expansion per pair and level -- the direct
+// scheme of round 1 expanded a whole-grid pair about ~21 target tiles per level.  The pairs of a tile are contiguous
+// ranges (by centre) of the class lists with lmin <= lev; warp w of a CTA takes tile 8 * group + w, one pair per lane,
+// Im(u^k) by the three-term recurrence, fixed shuffle reduction: the moments do not depend on the shard.
+__global__ void __launch_bounds__(THREADS) k_s2m(LineArgs a, int lev, int count_stats) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int d = blockIdx.y;
+    const int s = a.src_tile0[lev] + (int)blockIdx.x * WARPS + warp;
+    if (s >= a.src_tile0[lev] + a.n_src[lev]) return;  // warps are independent: no CTA barrier below
+    const int shift = a.fg.tile_shift[lev];
+    const long long T = a.fg.tile[lev];
+    const double c_s = a.fg.geom[lev][3 * s], sc = a.fg.geom[lev][3 * s + 2];
+    const double inv_sc = sc > 0.0 ? 1.0 / sc : 0.0;
+    const size_t drow = (size_t)d * a.L;
+    const int *list_d = a.cls_list + drow;
+    double C[K1];
+#pragma unroll
+    for (int k = 0; k < K1; k++) C[k] = 0.0;
+    unsigned long long n_pix = 0, n_exp = 0;
+    // pixels of the shard inside the interaction list of s (statistics: evaluations one saturated pair stands for)
+    long long il_pix = 0;
+    if (count_stats) {
+        long long nb0 = 0, nb1 = a.N;
+        if (lev + 1 < a.n_act) {
+            const long long P = s >> SD_FAR_SHIFT, Tp = a.fg.tile[lev + 1];
+            nb0 = (P - 1) * Tp > 0 ? (P - 1) * Tp : 0;
+            nb1 = (P + 2) * Tp < a.N ? (P + 2) * Tp : a.N;
+        }
+        long long nr0 = ((long long)s - 1) * T > 0 ? ((long long)s - 1) * T : 0;
+        long long nr1 = ((long long)s + 2) * T < a.N ? ((long long)s + 2) * T : a.N;
+        auto clip = [&](long long x0, long long x1) {
+            const long long e0 = x0 > a.p0 ? x0 : a.p0, e1 = x1 < a.p1 ? x1 : a.p1;
+            return e1 > e0 ? e1 - e0 : 0LL;
+        };
+        il_pix = clip(nb0, nb1) - clip(nr0, nr1);
+    }
+    for (int m = 0; m <= lev; m++) {
+        int ja, jb;
+        fc_centre_range(a, d, m, (long long)s * T, ((long long)s + 1) * T, ja, jb);
+        for (int j0 = ja; j0 < jb; j0 += 32) {
+            const int j = j0 + lane;
+            bool have = false;
+            int l = 0;
+            if (j < jb) {
+                l = list_d[j];
+                const PairWin pw = load_win(a.win + drow + l);
+                have = ((pw.sat >> lev) & 1u) && ((pw.cpix >> shift) == s);
+            }
+            if (!__any_sync(0xffffffffu, have)) continue;
+            double An = 0.0, u1r = 0.0, u2r = 0.0, ui = 0.0;
+            if (have) {
+                const double2 *rp = reinterpret_cast<const double2 *>(a.rec + drow + l);
+                const double2 r0 = __ldg(rp), r1 = __ldg(rp + 1);   // nu, dw, y, K
+                const double g = r1.x * r0.y, adw = 0.7071067811865476 * r0.y;
+                An = r1.y * r0.y * (0.5 * sdm::INV_SQRT_PI);
+                const double dc = r0.x - c_s;
+                u1r = (dc + adw) * inv_sc; u2r = (dc - adw) * inv_sc; ui = g * inv_sc;
+                if (count_stats) { n_pix += (unsigned long long)il_pix; n_exp++; }
+            }
+            const double a1 = u1r + u1r, b1 = fma(u1r, u1r, ui * ui), a2 = u2r + u2r, b2 = fma(u2r, u2r, ui * ui);
+            double s1 = ui, s1p = 0.0, s2 = ui, s2p = 0.0;   // Im(u^1), Im(u^0)
+#pragma unroll
+            for (int k = 0; k < K1; k++) {
+                C[k] = fma(An, s1 + s2, C[k]);
+                if (k + 1 < K1) {
+                    double t;
+                    t = fma(a1, s1, -(b1 * s1p)); s1p = s1; s1 = t;
+                    t = fma(a2, s2, -(b2 * s2p)); s2p = s2; s2 = t;
+                }
+            }
+        }
+    }
+    double mine = 0.0;
+#pragma unroll
+    for (int k = 0; k < K1; k++) {
+        double v = C[k];
+        for (int o2 = 16; o2; o2 >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o2);
+        if (lane == k) mine = v;
+    }
+    a.far_mom[lev][((size_t)d * a.n_src[lev] + (s - a.src_tile0[lev])) * K1 + lane] = mine;
+    if (count_stats) {
+        for (int o2 = 16; o2; o2 >>= 1) {
+            n_pix += __shfl_xor_sync(0xffffffffu, n_pix, o2);
+            n_exp += __shfl_xor_sync(0xffffffffu, n_exp, o2);
+        }
+        if (lane == 0 && n_exp) {
+            atomicAdd(&a.stats[8], n_pix);   // evaluations the multipole path replaces
+            atomicAdd(&a.stats[12], n_exp);  // executed multipole expansions (pair, level)
+        }
+    }
+}
+
+// Tile-to-tile translation of the multipole moments into Taylor coefficients, added to the direct part:
+//   L_n(t) += sum_s (b^n / d) sum_k C(n + k, n) a^k M_k(s),   d = c_t - c_s, a = scale_s / d, b = -h_t / d,
+// over the source tiles s of the interaction list of t: |s - t| >= 2 and parent(s) within one tile of parent(t) (all
+// tiles with |s - t| >= 2 at the top level).  The matrix is real and independent of the depth point: a CTA takes the
+// eight children of a parent (warp w = target tile) and M2L_DC depth points, lane n owns coefficient n, builds its
+// matrix row on the fly (ratio table in shared memory) and multiplies it with the moments of the chunk's depth points,
+// staged in shared memory (every lane reads the same moment: broadcast).  The k-sum stops where the multipole series
+// has converged for this tile distance (same rule as the direct expansion).  Fixed source order: shard-invariant.
+__global__ void __launch_bounds__(THREADS) k_m2l(LineArgs a, int lev, int count_stats) {
+    __shared__ double s_R[K1][K1];                           // s_R[k][n] = (n + k + 2) / (k + 2)
+    __shared__ __align__(16) double s_M[2][K1][M2L_DC + 2];   // moments of the staged source tile, [k][depth]
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const bool top = lev + 1 >= a.n_act;
+    const int nt = a.fg.n_tiles[lev];
+    const int P = (a.far_tile0[lev] >> SD_FAR_SHIFT) + (int)blockIdx.x;
+    const int t = (P << SD_FAR_SHIFT) + warp;
+    const bool tile_ok = t >= a.far_tile0[lev] && t < a.far_tile0[lev] + a.far_ntl[lev];
+    const int d0 = (int)blockIdx.y * M2L_DC;
+    const int nd = min(M2L_DC, a.D - d0);
+    for (int i = tid; i < K1 * K1; i += THREADS) {
+        const int k = i / K1, n = i - k * K1;
+        s_R[k][n] = (double)(n + k + 2) / (double)(k + 2);
+    }
+    const int s_lo = top ? 0 : max(((P - 1) << SD_FAR_SHIFT), 0);
+    const int s_hi = top ? nt : min(((P + 2) << SD_FAR_SHIFT), nt);
+    const double *__restrict__ gm = a.fg.geom[lev];
+    const double c_t = gm[3 * (tile_ok ? t : 0)], h_t = gm[3 * (tile_ok ? t : 0) + 1];
+    const double *__restrict__ mom = a.far_mom[lev];
+    const int src0 = a.src_tile0[lev], nsrc = a.n_src[lev];
+    auto stage = [&](int buf, int s) {
+        for (int i = tid; i < M2L_DC * K1; i += THREADS) {
+            const int dd = i / K1, k = i - dd * K1;
+            s_M[buf][k][dd] = (dd < nd) ? mom[((size_t)(d0 + dd) * nsrc + (s - src0)) * K1 + k] : 0.0;
+        }
+    };
+    double acc[M2L_DC];
+#pragma unroll
+    for (int dd = 0; dd < M2L_DC; dd++) acc[dd] = 0.0;
+    unsigned long long n_m2l = 0;
+    if (s_lo < s_hi) stage(0, s_lo);
+    __syncthreads();
+    for (int s = s_lo; s < s_hi; s++) {
+        const int buf = (s - s_lo) & 1;
+        if (s + 1 < s_hi) stage(buf ^ 1, s + 1);
+        const int ds = s - t;
+        if (tile_ok && (ds >= 2 || ds <= -2)) {
+            const double c_s = gm[3 * s], sc = gm[3 * s + 2];
+            const double dd_ = c_t - c_s, inv_d = 1.0 / dd_;
+            const double aa = sc * inv_d, bb = -h_t * inv_d;
+            // b^n by binary powering (lane n)
+            double f = inv_d, base = bb;
+#pragma unroll
+            for (int bit = 0; bit < 5; bit++) {
+                if ((lane >> bit) & 1) f *= base;
+                base *= base;
+            }
+            // the multipole series in (pole - c_s) / (nu - c_s): poles up to 1 + overhang scale lengths from c_s,
+            // pixels of t at least |d| - h_t away
+            const double rr = (1.0 + SD_FAR_OVERHANG) * sc / (fabs(dd_) - h_t);
+            const int kmax = min(K1, 4 * ((far_terms(rr * rr) + 3) / 4));
+            double coef = f * (double)(lane + 1) * aa;
+            for (int k = 0; k < kmax; k++) {
+                const double *__restrict__ mk = s_M[buf][k];
+#pragma unroll
+                for (int dd = 0; dd < M2L_DC; dd += 2) {
+                    const double2 mv = *reinterpret_cast<const double2 *>(mk + dd);
+                    acc[dd] = fma(coef, mv.x, acc[dd]);
+                    acc[dd + 1] = fma(coef, mv.y, acc[dd + 1]);
+                }
+                coef *= aa * s_R[k][lane];
+            }
+            if (count_stats) n_m2l += (unsigned long long)nd * kmax;
+        }
+        __syncthreads();
+    }
+    if (tile_ok) {
+#pragma unroll
+        for (int dd = 0; dd < M2L_DC; dd++)
+            if (dd < nd) a.far_coef[lev][((size_t)(d0 + dd) * a.far_ntl[lev] + (t - a.far_tile0[lev])) * K1 + lane] += acc[dd];
+    }
+    if (count_stats && lane == 0 && n_m2l) atomicAdd(&a.stats[13], n_m2l);  // executed (source, target, depth, k) row steps per lane
+}
+
+// ------------------------------------------------------------------------------------------------------------------
 template <int P, int NW, bool STATS, int RCP, int MINB>
 __global__ void __launch_bounds__(32 * NW, MINB) k_lines(LineArgs a) {
     constexpr int TILE = 32 * NW * P;
     constexpr int SPAN = 32 * P;
+    constexpr int SUB = 1 << SD_FAR_TILE0_SHIFT;        // level-0 far-field tile: 64 pixels = 2 register slots
+    constexpr int NSUB = (SPAN + SUB - 1) / SUB;        // level-0 tiles per warp span (4 for P = 8)
+    constexpr int SLOTS_PER_SUB = SUB / 32;
+    constexpr unsigned ALL_SUB = (1u << NSUB) - 1u;
     __shared__ WEntry s_ent[NW][32];  // every warp streams its own batches: no CTA barrier in the main loop
+    __shared__ unsigned char s_msk[NW][32];  // per entry: level-0 tiles of the span that are evaluated directly
     __shared__ double s_acc[NW][SPAN];  // accumulators of the pixel-parallel mixed path
-    constexpr int NSRC = SD_NCLS + 2;    // classes 0..6, far-capable pairs near the tile, their window starts / ends
+    __shared__ double s_nsub[NW][2 * NSUB];  // frequencies of the first / last pixel of every level-0 tile of the span
+    // classes 0..6, then per lmin class m: far-capable pairs centred near the tile, their window starts / ends
+    constexpr int NSRC = SD_FC0 + 3 * SD_FAR_LEVELS;
     __shared__ int s_ja[NSRC], s_jb[NSRC];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -499,7 +695,8 @@ __global__ void __launch_bounds__(32 * NW, MINB) k_lines(LineArgs a) {
     const size_t drow = (size_t)d * L;
     const int *list_d = a.cls_list + drow;
     const double *__restrict__ nus = a.nus;
-    const bool use_far = a.fg.enabled != 0;
+    constexpr bool FARCAP = (P == 8);  // the far field needs whole level-0 tiles per pair of register slots
+    const bool use_far = FARCAP && a.fg.enabled != 0 && a.n_act > 0;
     const unsigned long long lmask = (1ull << a.fg.l_bits) - 1ull;  // line index = low bits of a window-edge key
 
     // pixel frequencies and accumulators live in registers for the whole kernel
@@ -514,47 +711,73 @@ __global__ void __launch_bounds__(32 * NW, MINB) k_lines(LineArgs a) {
     for (int p = 0; p < P; p++) {
         s_acc[warp][p * 32 + lane] = 0.0;
     }
-    // frequencies at the two ends of this warp's span (x is monotone in the pixel index)
-    const double nu_first = nus[ws < N ? ws : N - 1];
-    const double nu_last = nus[(we - 1 >= ws && we - 1 < N) ? we - 1 : (ws < N ? ws : N - 1)];
+    if (lane < 2 * NSUB) {
+        const int64_t e0 = ws + (int64_t)(lane >> 1) * SUB;
+        int64_t pix = (lane & 1) ? ((e0 + SUB < we) ? e0 + SUB : we) - 1 : e0;
+        pix = pix < ws ? ws : pix;
+        s_nsub[warp][lane] = nus[pix < N ? pix : N - 1];
+    }
 
     // candidate ranges of all sources, distributed over the warps of the CTA
     for (int src = warp; src < NSRC; src += NW) {
         int ja = 0, jb = 0;
-        if (src < SD_FC_CLASS) class_range(a, d, src, t0, t1, ja, jb);
-        else if (src == SD_FC_CLASS) {
-            if (use_far) fc_near_range(a, d, 0, tile, ja, jb);
-        } else if (use_far) fc_edge_range(a, d, src - SD_NCLS, t0, t1, ja, jb);
+        if (src < SD_FC0) class_range(a, d, src, t0, t1, ja, jb);
+        else if (use_far) {
+            const int m = (src - SD_FC0) / 3, kind = (src - SD_FC0) - 3 * m;
+            if (m < a.n_act) {
+                const int sh = a.fg.tile_shift[m];
+                const long long ta = t0 >> sh, tb = (t1 - 1) >> sh;   // level-m tiles that overlap the CTA tile
+                if (kind == 0) fc_centre_range(a, d, m, (ta - 1) << sh, (tb + 2) << sh, ja, jb);
+                else {
+                    const long long e1 = ((tb + 1) << sh) < N ? ((tb + 1) << sh) : N;
+                    fc_edge_range(a, d, kind - 1, m, ta << sh, e1, ja, jb);
+                }
+            }
+        }
         if (lane == 0) { s_ja[src] = ja; s_jb[src] = jb; }
     }
     __syncthreads();
 
     unsigned long long h0 = 0, h1 = 0, h2 = 0, h3 = 0;
-    int nvalid = 0;  // this lane's pixels that belong to the shard (statistics only)
+    unsigned nvalid_sub = 0;  // this lane's pixels that belong to the shard, per level-0 tile of the span, 8 bits each (statistics only)
 #pragma unroll
     for (int p = 0; p < P; p++) {
         int64_t pix = ws + p * 32 + lane;
-        nvalid += (pix < t1) && (pix >= p0) && (pix < p1);
+        if ((pix < t1) && (pix >= p0) && (pix < p1)) nvalid_sub += 1u << (8 * (p / SLOTS_PER_SUB));
     }
 
     WEntry *const my = s_ent[warp];
+    unsigned char *const my_msk = s_msk[warp];
     const bool warp_has_pixels = (ws < t1) && (ws < p1) && (we > p0);
 
-    // far-wing (region I) evaluation of one staged entry for the P pixels of this lane
+    // far-wing (region I) evaluation of one staged entry for the pixels of this lane in the level-0 tiles of `msk`
     auto far_eval = [&](const double xl, const double inv_dw, const double eb, const double ec, const double Kc,
-                        const double Kf) {
+                        const double Kf, const unsigned msk) {
+        if (msk == ALL_SUB) {
 #pragma unroll
-        for (int p = 0; p < P; p++) {
-            double x = fma(nu_i[p], inv_dw, -xl);
-            double q = x * x;
-            double den = fma(q, q + eb, ec);
-            double num = fma(Kf, q, Kc);
-            acc[p] = fma(num, RCP == 2 ? sdm::rcp_fast2(den) : sdm::rcp_fast(den), acc[p]);
+            for (int p = 0; p < P; p++) {
+                double x = fma(nu_i[p], inv_dw, -xl);
+                double q = x * x;
+                double den = fma(q, q + eb, ec);
+                double num = fma(Kf, q, Kc);
+                acc[p] = fma(num, RCP == 2 ? sdm::rcp_fast2(den) : sdm::rcp_fast(den), acc[p]);
+            }
+        } else {
+#pragma unroll
+            for (int p = 0; p < P; p++) {
+                if (!((msk >> (p / SLOTS_PER_SUB)) & 1u)) continue;  // warp-uniform
+                double x = fma(nu_i[p], inv_dw, -xl);
+                double q = x * x;
+                double den = fma(q, q + eb, ec);
+                double num = fma(Kf, q, Kc);
+                acc[p] = fma(num, RCP == 2 ? sdm::rcp_fast2(den) : sdm::rcp_fast(den), acc[p]);
+            }
         }
     };
 
     for (int src = 0; src < NSRC && warp_has_pixels; src++) {
         const int ja = s_ja[src], jb = s_jb[src];
+        const int skind = src < SD_FC0 ? -1 : (src - SD_FC0) % 3;  // -1: half-width class, 0: centre list, 1 / 2: edge lists
         for (int base = ja; base < jb; base += 32) {
             {
             // ---- test the 32 candidates of this batch against THIS WARP's span ------------------------
@@ -562,10 +785,11 @@ __global__ void __launch_bounds__(32 * NW, MINB) k_lines(LineArgs a) {
             bool pass = false;
             size_t o = 0;
             int lo = 0, hi = 0;
+            unsigned msk = ALL_SUB;
             if (j < jb) {
                 int l;
                 if (src == 0) l = j;                                   // class 0: the nu-sorted line list itself
-                else if (src <= SD_FC_CLASS) l = list_d[j];            // class lists (7 = far-capable pairs near the tile)
+                else if (skind <= 0) l = list_d[j];                    // class lists
                 else l = (int)(a.fg.edge_keys[j] & lmask);             // far-capable pairs with an edge inside the tile
                 o = drow + l;
                 const PairWin pw = load_win(a.win + o);
@@ -573,9 +797,33 @@ __global__ void __launch_bounds__(32 * NW, MINB) k_lines(LineArgs a) {
                 hi = pw.hi;
                 pass = (lo < we) && (hi > ws) && (hi > lo);
                 if (src == 0) pass = pass && (pw.cls == 0);
-                else if (src == SD_FC_CLASS) {
-                    // covering pairs only (the others come through the edge lists); skip those expanded by k_far_coeffs
-                    pass = pass && (lo <= t0) && (hi >= t1) && !pair_is_far(lo, hi, pw.near[0], t0, t1, tile);
+                else if (skind >= 0) {
+                    // far-capable pair of class m = lmin: a level-0 tile of the span is evaluated here unless the pair
+                    // is far from the level-m tile that holds it (then the polynomials carry the contribution)
+                    const int m = pw.lmin, sh = a.fg.tile_shift[m], sj = pw.cpix >> sh;
+                    if (skind > 0) {
+                        // edge lists: only pairs the centre list of this CTA does not already deliver; both edges
+                        // inside the level-m tile range: via the start
+                        const int ta = (int)(t0 >> sh), tb = (int)((t1 - 1) >> sh);
+                        const int64_t r0 = (int64_t)ta << sh;
+                        const int64_t r1 = (((int64_t)tb + 1) << sh) < N ? (((int64_t)tb + 1) << sh) : N;
+                        pass = pass && (sj < ta - 1 || sj > tb + 1) && !(skind == 2 && lo > r0 && lo < r1);
+                    }
+                    msk = 0;
+                    if (m == 0) {
+#pragma unroll
+                        for (int i = 0; i < NSUB; i++) {
+                            const int64_t c0 = ws + (int64_t)i * SUB;
+                            const int64_t c1 = (c0 + SUB < N) ? c0 + SUB : N;
+                            if (c0 < we && !pair_is_far(pw, 0, SD_FAR_TILE0_SHIFT, (int)(c0 >> SD_FAR_TILE0_SHIFT), c0, c1)) msk |= 1u << i;
+                        }
+                    } else {
+                        const int tm = (int)(ws >> sh);
+                        const int64_t c0 = (int64_t)tm << sh;
+                        const int64_t c1 = (c0 + ((int64_t)1 << sh) < N) ? c0 + ((int64_t)1 << sh) : N;
+                        if (!pair_is_far(pw, m, sh, tm, c0, c1)) msk = ALL_SUB;
+                    }
+                    pass = pass && (msk != 0);
                 }
             }
             if (!__any_sync(0xffffffffu, pass)) continue;
@@ -599,35 +847,49 @@ __global__ void __launch_bounds__(32 * NW, MINB) k_lines(LineArgs a) {
                 e.dw = r.dw;
                 e.y = r.y;
                 e.K = r.K;
-                if (lo <= ws && hi >= we) {  // window covers the whole span: is the span entirely in region I?
-                    double xa = fma(nu_first, e.inv_dw, -e.xl);
-                    double xb = fma(nu_last, e.inv_dw, -e.xl);
+                // the hull of the level-0 tiles to evaluate: does the window cover it, does it lie entirely in region I?
+                const int i0 = __ffs(msk) - 1, i1 = 31 - __clz(msk);
+                const int64_t h0p = ws + (int64_t)i0 * SUB;
+                const int64_t h1p = (ws + (int64_t)(i1 + 1) * SUB < we) ? ws + (int64_t)(i1 + 1) * SUB : we;
+                if (lo <= h0p && hi >= h1p) {
+                    double xa = fma(s_nsub[warp][2 * i0], e.inv_dw, -e.xl);
+                    double xb = fma(s_nsub[warp][2 * i1 + 1], e.inv_dw, -e.xl);
                     ff = (xa * xb > 0.0) && (fmin(xa * xa, xb * xb) > e.thr);
                 }
             }
             const unsigned m_far = __ballot_sync(0xffffffffu, pass && ff);
             const unsigned m_mix = __ballot_sync(0xffffffffu, pass && !ff);
             const int n_far = __popc(m_far), n_mix = __popc(m_mix);
-            if (pass) my[ff ? __popc(m_far & lt_mask) : 31 - __popc(m_mix & lt_mask)] = e;
+            if (pass) {
+                const int slot = ff ? __popc(m_far & lt_mask) : 31 - __popc(m_mix & lt_mask);
+                my[slot] = e;
+                my_msk[slot] = (unsigned char)msk;
+            }
             __syncwarp();
             // ---- consume the far-wing entries ---------------------------------------------------------
             for (int k = 0; k < n_far; k++) {
                 const WEntry &w = my[k];
-                far_eval(w.xl, w.inv_dw, w.b, w.c, w.Kc, w.Kf);
+                const unsigned mk = my_msk[k];
+                far_eval(w.xl, w.inv_dw, w.b, w.c, w.Kc, w.Kf, mk);
+                if (STATS) {
+#pragma unroll
+                    for (int i = 0; i < NSUB; i++)
+                        if ((mk >> i) & 1u) h0 += (nvalid_sub >> (8 * i)) & 0xffu;
+                }
             }
-            if (STATS) h0 += (unsigned long long)n_far * nvalid;
             // ---- mixed entries: window edge inside the span and/or pixels near the line core.  Lanes take CONSECUTIVE
             // pixels of the in-window part of the span (a 20-pixel window keeps 20 lanes busy in one pass); entries are
             // processed one after the other and a pass touches distinct pixels, so the shared accumulators need no
             // atomics and the summation order stays fixed.
             for (int m = 0; m < n_mix; m++) {
                 const WEntry &e2 = my[31 - m];
+                const unsigned mk = my_msk[31 - m];
                 const int64_t pa = e2.lo > ws ? e2.lo : ws, pb = e2.hi < we ? e2.hi : we;
                 const double thr = e2.thr, xl = e2.xl, inv_dw = e2.inv_dw, eb = e2.b, ec = e2.c, Kc = e2.Kc, Kf = e2.Kf;
                 if (pb - pa <= 64) {
                     for (int64_t c0 = pa; c0 < pb; c0 += 32) {
                         const int64_t pix = c0 + lane;
-                        if (pix < pb) {
+                        if (pix < pb && ((mk >> ((int)(pix - ws) >> SD_FAR_TILE0_SHIFT)) & 1u)) {
                             const int k = (int)(pix - ws);
                             const double nu = nus[pix];
                             double x = fma(nu, inv_dw, -xl);
@@ -656,6 +918,7 @@ __global__ void __launch_bounds__(32 * NW, MINB) k_lines(LineArgs a) {
                     // common case): register slots without any window logic
 #pragma unroll
                     for (int p = 0; p < P; p++) {
+                        if (!((mk >> (p / SLOTS_PER_SUB)) & 1u)) continue;  // warp-uniform
                         const double x = fma(nu_i[p], inv_dw, -xl);
                         const double q = x * x;
                         const bool fast = q > thr;
@@ -679,6 +942,7 @@ __global__ void __launch_bounds__(32 * NW, MINB) k_lines(LineArgs a) {
                     const int lo2 = e2.lo, hi2 = e2.hi;
 #pragma unroll
                     for (int p = 0; p < P; p++) {
+                        if (!((mk >> (p / SLOTS_PER_SUB)) & 1u)) continue;  // warp-uniform
                         int64_t pix = ws + p * 32 + lane;
                         bool inwin = (pix >= lo2) && (pix < hi2) && (pix < t1);
                         if (!__any_sync(0xffffffffu, inwin)) continue;
@@ -706,14 +970,13 @@ __global__ void __launch_bounds__(32 * NW, MINB) k_lines(LineArgs a) {
 #pragma unroll
     for (int p = 0; p < P; p++) acc[p] += s_acc[warp][p * 32 + lane];
 
-    // ---- far field: one polynomial per hierarchy level (Horner in t = (nu - nu_c) / h of that level's tile) -------
-    if (use_far && warp_has_pixels) {
-        constexpr int K1 = SD_FAR_K + 1;
-#pragma unroll
-        for (int lev = 0; lev < SD_FAR_LEVELS; lev++) {
-            const int tk = tile >> (SD_FAR_SHIFT * lev);
-            const double nu_c = a.fg.geom[lev][2 * tk], h_k = a.fg.geom[lev][2 * tk + 1];
-            const double inv_h = (h_k > 0.0) ? 1.0 / h_k : 0.0;  // a one-pixel tile has h = 0: nothing is ever far from it, C = 0
+    // ---- far field: one polynomial per hierarchy level (Horner in t = (nu - nu_c) / h of that level's tile); at level 0
+    // every pair of register slots has its own tile
+    if constexpr (FARCAP) if (use_far && warp_has_pixels) {
+        for (int lev = a.n_act - 1; lev >= 1; lev--) {
+            const int tk = (int)(ws >> a.fg.tile_shift[lev]);
+            const double nu_c = a.fg.geom[lev][3 * tk], h_k = a.fg.geom[lev][3 * tk + 1];
+            const double inv_h = (h_k > 0.0) ? 1.0 / h_k : 0.0;  // a one-pixel tile has h = 0: only the constant term counts
             const double *__restrict__ C = a.far_coef[lev] + ((size_t)d * a.far_ntl[lev] + (tk - a.far_tile0[lev])) * K1;
             double tt[P], poly[P];
             const double ck = C[K1 - 1];
@@ -730,6 +993,30 @@ __global__ void __launch_bounds__(32 * NW, MINB) k_lines(LineArgs a) {
             }
 #pragma unroll
             for (int p = 0; p < P; p++) acc[p] += poly[p];
+        }
+#pragma unroll
+        for (int i = 0; i < NSUB; i++) {
+            const int64_t c0 = ws + (int64_t)i * SUB;
+            if (c0 >= we || c0 + SUB <= p0 || c0 >= p1) continue;  // warp-uniform; tiles outside the shard have no coefficients
+            const int tk = (int)(c0 >> SD_FAR_TILE0_SHIFT);
+            const double nu_c = a.fg.geom[0][3 * tk], h_k = a.fg.geom[0][3 * tk + 1];
+            const double inv_h = (h_k > 0.0) ? 1.0 / h_k : 0.0;
+            const double *__restrict__ C = a.far_coef[0] + ((size_t)d * a.far_ntl[0] + (tk - a.far_tile0[0])) * K1;
+            double tt[SLOTS_PER_SUB], poly[SLOTS_PER_SUB];
+            const double ck = C[K1 - 1];
+#pragma unroll
+            for (int q = 0; q < SLOTS_PER_SUB; q++) {
+                tt[q] = (nu_i[i * SLOTS_PER_SUB + q] - nu_c) * inv_h;
+                poly[q] = ck;
+            }
+#pragma unroll
+            for (int k = K1 - 2; k >= 0; k--) {
+                const double c = C[k];
+#pragma unroll
+                for (int q = 0; q < SLOTS_PER_SUB; q++) poly[q] = fma(poly[q], tt[q], c);
+            }
+#pragma unroll
+            for (int q = 0; q < SLOTS_PER_SUB; q++) acc[i * SLOTS_PER_SUB + q] += poly[q];
         }
     }
 
@@ -781,8 +1068,8 @@ int sd_k2_choose_P(sd_ctx *c) {
     const int64_t W = c->N;
     int P, NW = 8;
     if (c->farfield) {
-        // Small level-0 tiles keep the directly evaluated near field small (the hierarchy absorbs the rest), wide
-        // per-warp spans keep the per-pair staging amortised: 2 warps x 256 pixels (1 warp on small grids).
+        // The hierarchy absorbs everything but the level-0 tiles around a line; wide per-warp spans keep the per-pair
+        // staging amortised: 2 warps x 256 pixels (1 warp on small grids).
         P = 8;
         NW = (((W + 511) / 512) * c->D >= 2LL * c->sm_count) ? 2 : 1;
     } else if (((W + 2047) / 2048) * c->D >= 8LL * c->sm_count) P = 8;
@@ -791,6 +1078,10 @@ int sd_k2_choose_P(sd_ctx *c) {
     else P = 1;
     if (force_p == 1 || force_p == 2 || force_p == 4 || force_p == 8) P = force_p;
     if (force_nw == 1 || force_nw == 2 || force_nw == 8) NW = force_nw;
+    if (c->farfield) {  // level-0 tiles are pairs of register slots and a warp span must not straddle a level-1 tile
+        P = 8;
+        if (NW == 8) NW = 2;
+    }
     if (NW != 8 && P != 8) P = 8;  // only P = 8 is instantiated for the narrow CTAs
     c->k2_NW = NW;
     return P;
@@ -806,6 +1097,7 @@ int sd_k2_lines(sd_ctx *c, int slot) {
     if (c->line_stats) {
         SD_CUDA(c, cudaMemsetAsync(c->stats.p, 0, 4 * sizeof(unsigned long long), c->stream));
         SD_CUDA(c, cudaMemsetAsync(c->stats.as<unsigned long long>() + 8, 0, 3 * sizeof(unsigned long long), c->stream));
+        SD_CUDA(c, cudaMemsetAsync(c->stats.as<unsigned long long>() + 12, 0, 2 * sizeof(unsigned long long), c->stream));
     }
     static const int rcp = env_int("SD_K2_RCP", 2);
     const int P = c->k2_P, NW = c->k2_NW, tile = 32 * NW * P;
@@ -818,18 +1110,33 @@ int sd_k2_lines(sd_ctx *c, int slot) {
     a.win = c->win.as<PairWin>();
     a.cls_list = c->cls_list.as<int>(); a.cls_off = c->cls_off.as<int>();
     a.fg = c->far_geom;
+    a.n_act = c->farfield ? c->far_active : 0;
     a.out = c->alpha_line[slot].as<double>();
     a.stats = c->stats.as<unsigned long long>();
-    if (c->farfield) {
-        for (int k = SD_FAR_LEVELS - 1; k >= 0; k--) {
+    if (c->farfield && a.n_act > 0) {
+        const int n_act = a.n_act;
+        for (int k = n_act - 1; k >= 0; k--) {
             const int tk = a.fg.tile[k];
             a.far_tile0[k] = (int)(c->p0 / tk);
             a.far_ntl[k] = (int)((c->p1 + tk - 1) / tk) - a.far_tile0[k];
-            SD_TRY(sd_ensure(c, c->far_coef[k], sizeof(double) * c->D * a.far_ntl[k] * (SD_FAR_K + 1)));
+            SD_TRY(sd_ensure(c, c->far_coef[k], sizeof(double) * c->D * a.far_ntl[k] * K1));
             a.far_coef[k] = c->far_coef[k].as<double>();
+            // source tiles whose moments the targets of this launch need: the children of the parents of the targets
+            // and of their two neighbours (every tile at the top level)
+            if (k == n_act - 1) {
+                a.src_tile0[k] = 0;
+                a.n_src[k] = a.fg.n_tiles[k];
+            } else {
+                const int P0 = a.far_tile0[k] >> SD_FAR_SHIFT, P1 = (a.far_tile0[k] + a.far_ntl[k] - 1) >> SD_FAR_SHIFT;
+                const int s0 = (P0 - 1 > 0 ? P0 - 1 : 0) << SD_FAR_SHIFT;
+                int s1 = (P1 + 2) << SD_FAR_SHIFT;
+                if (s1 > a.fg.n_tiles[k]) s1 = a.fg.n_tiles[k];
+                a.src_tile0[k] = s0;
+                a.n_src[k] = s1 - s0;
+            }
+            SD_TRY(sd_ensure(c, c->far_mom[k], sizeof(double) * c->D * a.n_src[k] * K1));
+            a.far_mom[k] = c->far_mom[k].as<double>();
         }
-        // CTAs per (group of eight sibling tiles, depth): the candidate lists are cut into this many fixed slices so that
-        // even a narrow shard fills the chip; k_far_reduce adds the partial sums in slice order.
         if (!c->far_attr_set) {  // per device: > 48 KB of dynamic shared memory needs the opt-in; series-length table
             SD_CUDA(c, cudaFuncSetAttribute(k_far_coeffs, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FAR_SMEM));
             unsigned char tab[256];
@@ -838,25 +1145,33 @@ int sd_k2_lines(sd_ctx *c, int slot) {
             SD_CUDA(c, cudaStreamSynchronize(c->stream));  // `tab` lives on this stack frame
             c->far_attr_set = true;
         }
+        // CTAs per (group of eight sibling tiles, depth) of the direct expansion: the candidate lists are cut into this
+        // many fixed slices so that even a narrow shard fills the chip; k_far_reduce adds the partial sums in slice order.
         size_t part_bytes = 0;
-        for (int k = 0; k < SD_FAR_LEVELS; k++) {
-            const size_t b = sizeof(double) * c->D * a.far_ntl[k] * far_nsplit(k) * (SD_FAR_K + 1);
+        for (int k = 0; k < n_act; k++) {
+            const int ns = far_nsplit(k, k == n_act - 1);
+            const size_t b = ns > 1 ? sizeof(double) * c->D * a.far_ntl[k] * ns * K1 : 0;
             part_bytes = b > part_bytes ? b : part_bytes;
         }
-        SD_TRY(sd_ensure(c, c->far_part, part_bytes));
+        SD_TRY(sd_ensure(c, c->far_part, part_bytes > 0 ? part_bytes : 8));
         sd_phase_begin(c, SD_PH_FAR);
-        for (int k = SD_FAR_LEVELS - 1; k >= 0; k--) {
-            const int nsplit = far_nsplit(k);
-            // one CTA per group of eight sibling tiles that has a member in the launched range, times the slices
-            const int n_cta = (((a.far_tile0[k] + a.far_ntl[k] - 1) >> SD_FAR_SHIFT) - (a.far_tile0[k] >> SD_FAR_SHIFT) + 1) * nsplit;
-            k_far_coeffs<<<dim3((unsigned)n_cta, (unsigned)c->D), THREADS, FAR_SMEM, c->stream>>>(
-                a, k, c->line_stats ? 1 : 0, nsplit, c->far_part.as<double>());
+        const int cs = c->line_stats ? 1 : 0;
+        for (int k = n_act - 1; k >= 0; k--) {
+            const int nsplit = far_nsplit(k, k == n_act - 1);
+            // one CTA per group of eight sibling tiles that has a member in the launched range (times the slices)
+            const int n_grp = ((a.far_tile0[k] + a.far_ntl[k] - 1) >> SD_FAR_SHIFT) - (a.far_tile0[k] >> SD_FAR_SHIFT) + 1;
+            k_far_coeffs<<<dim3((unsigned)(n_grp * nsplit), (unsigned)c->D), THREADS, FAR_SMEM, c->stream>>>(
+                a, k, cs, nsplit, c->far_part.as<double>());
             SD_TRY(sd_launch_check(c, "k_far_coeffs"));
             if (nsplit > 1) {
-                const int n = c->D * a.far_ntl[k] * (SD_FAR_K + 1);
+                const int n = c->D * a.far_ntl[k] * K1;
                 k_far_reduce<<<(n + 255) / 256, 256, 0, c->stream>>>(n, nsplit, c->far_part.as<double>(), a.far_coef[k]);
                 SD_TRY(sd_launch_check(c, "k_far_reduce"));
             }
+            k_s2m<<<dim3((unsigned)((a.n_src[k] + WARPS - 1) / WARPS), (unsigned)c->D), THREADS, 0, c->stream>>>(a, k, cs);
+            SD_TRY(sd_launch_check(c, "k_s2m"));
+            k_m2l<<<dim3((unsigned)n_grp, (unsigned)((c->D + M2L_DC - 1) / M2L_DC)), THREADS, 0, c->stream>>>(a, k, cs);
+            SD_TRY(sd_launch_check(c, "k_m2l"));
         }
         sd_phase_end(c, SD_PH_FAR);
     }

@@ -3,7 +3,7 @@
 // Part of the K2 PREPARATION pass of the far-field scheme (not of the per-pixel hot loop): the pairs whose window
 // starts (ends) strictly inside a given tile are found by two binary searches in ONE sorted array instead of by
 // scanning whole class lists per tile.  k_build_records appends a 64-bit key
-//     kind (0 start / 1 end) | depth | edge pixel | line index
+//     kind (0 start / 1 end) | depth | lmin | edge pixel | line index
 // only for edges that exist (inside the grid) and can matter to this context (inside its extended pixel range), so a
 // nu shard sorts ~1/R of what a whole-grid run sorts.  The key is a total order: the sorted array -- and every
 // summation order derived from it -- is independent of the (atomic) append order.  The radix sort itself is the one
@@ -14,17 +14,18 @@
 #include "sd_internal.h"
 
 namespace {
-// off[kind * (D + 1) + d] = first sorted key of (kind, d); the entry d == D closes the kind's range
+// off[(kind * D + d) * SD_FAR_LEVELS + m] = first sorted key of (kind, d, lmin = m); one more entry closes the array
 __global__ void k_edge_offsets(FarGeom fg, const unsigned long long *__restrict__ keys, const unsigned long long *__restrict__ count,
                                int D, int *__restrict__ off) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= 2 * (D + 1)) return;
-    const int kind = i / (D + 1), d = i - kind * (D + 1);
+    const int n = 2 * D * SD_FAR_LEVELS;
+    if (i > n) return;
     const long long M = (long long)count[0];
     long long lo = 0, hi = M;
-    if (kind == 1 && d == D) lo = M;
+    if (i == n) lo = M;
     else {
-        const unsigned long long X = (d == D) ? sd_edge_key(fg, kind + 1, 0, 0, 0) : sd_edge_key(fg, kind, d, 0, 0);
+        const int m = i % SD_FAR_LEVELS, kd = i / SD_FAR_LEVELS, kind = kd / D, d = kd - kind * D;
+        const unsigned long long X = sd_edge_key(fg, kind, d, m, 0, 0);
         while (lo < hi) {
             const long long mid = lo + ((hi - lo) >> 1);
             if (keys[mid] < X) lo = mid + 1; else hi = mid;
@@ -36,15 +37,17 @@ __global__ void k_edge_offsets(FarGeom fg, const unsigned long long *__restrict_
 
 int sd_sort_edges(sd_ctx *c) {
     FarGeom &fg = c->far_geom;
-    if (!c->h_edge_count) SD_CUDA(c, cudaHostAlloc((void **)&c->h_edge_count, sizeof(unsigned long long), cudaHostAllocDefault));
+    if (!c->h_edge_count) SD_CUDA(c, cudaHostAlloc((void **)&c->h_edge_count, 2 * sizeof(unsigned long long), cudaHostAllocDefault));
     SD_CUDA(c, cudaMemcpyAsync(c->h_edge_count, c->edge_count.p, sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
+    SD_CUDA(c, cudaMemcpyAsync(c->h_edge_count + 1, c->lev_info.p, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
     SD_CUDA(c, cudaStreamSynchronize(c->stream));
     const long long M = (long long)*c->h_edge_count;
+    c->far_active = *reinterpret_cast<const int *>(c->h_edge_count + 1);  // usable hierarchy levels on this grid
     SD_CHECK(c, M >= 0 && M < 2147483647LL, SD_ERR_STATE, "window-edge list too long (%lld entries)", M);
     SD_TRY(sd_ensure(c, c->edge_keys, sizeof(unsigned long long) * (size_t)(M > 0 ? M : 1)));
-    SD_TRY(sd_ensure(c, c->edge_off, sizeof(int) * 2 * (c->D + 1)));
+    SD_TRY(sd_ensure(c, c->edge_off, sizeof(int) * (2 * c->D * SD_FAR_LEVELS + 1)));
     if (M > 0) {
-        const int end_bit = 1 + fg.depth_bits + fg.pix_bits + fg.l_bits;
+        const int end_bit = 1 + fg.depth_bits + SD_FAR_LMIN_BITS + fg.pix_bits + fg.l_bits;
         const unsigned long long *in = c->edge_unsorted.as<unsigned long long>();
         unsigned long long *out = c->edge_keys.as<unsigned long long>();
         size_t bytes = 0;
@@ -55,7 +58,7 @@ int sd_sort_edges(sd_ctx *c) {
     }
     fg.edge_keys = c->edge_keys.as<unsigned long long>();
     fg.edge_off = c->edge_off.as<int>();
-    k_edge_offsets<<<(2 * (c->D + 1) + 127) / 128, 128, 0, c->stream>>>(fg, fg.edge_keys, c->edge_count.as<unsigned long long>(), c->D,
+    k_edge_offsets<<<(2 * c->D * SD_FAR_LEVELS + 1 + 127) / 128, 128, 0, c->stream>>>(fg, fg.edge_keys, c->edge_count.as<unsigned long long>(), c->D,
                                                                       c->edge_off.as<int>());
     return sd_launch_check(c, "k_edge_offsets");
 }

@@ -21,45 +21,58 @@ struct __align__(16) LineRec {
 };
 static_assert(sizeof(LineRec) == 64, "LineRec must be 64 bytes");
 
-// ---- per-(depth, line) window record: everything the candidate tests of k_lines / k_far_coeffs need, in ONE 32-byte
-// sector (one gather per candidate instead of one per array)
+// ---- per-(depth, line) window record: everything the candidate tests of k_lines / k_far_coeffs / k_s2m need, in ONE
+// 16-byte load per candidate
 struct __align__(16) PairWin {
     int lo, hi;         // window [lo, hi) in global pixels (base.py:563-592 semantics, see sdm::line_window)
-    unsigned near[3];   // per hierarchy level: tiles [lo16, hi16) around the line centre that are NOT far
-    int cls;            // half-width class (0..6) or SD_FC_CLASS
-    int pad0, pad1;
+    int cpix;           // pixel of the line centre (line_idx clamped to the grid): tile of level k = cpix >> tile_shift[k]
+    unsigned char cls;  // half-width class (0..6) or SD_FC0 + lmin for far-capable pairs
+    unsigned char lmin; // lowest hierarchy level at which the pair may be expanded (SD_FAR_LEVELS: never)
+    unsigned char sat;  // bit k: the window covers the whole interaction neighbourhood of the pair's level-k tile
+    unsigned char pad;
 };
-static_assert(sizeof(PairWin) == 32, "PairWin must be 32 bytes");
+static_assert(sizeof(PairWin) == 16, "PairWin must be 16 bytes");
 
-constexpr int SD_NCLS = 8;          // half-width classes
-constexpr int SD_CLS0_HW = 64;      // class 0: hw <= 64; class k: hw <= 64 * 4^k; last class: everything wider
+constexpr int SD_CLS0_HW = 64;      // class 0: hw <= 64; class k: hw <= 64 * 4^k; class 6: everything wider
 constexpr int SD_MAX_SOURCES = 4 + SD_MAX_TABLES;
-// far-field (Taylor) expansion of region-I wings per pixel tile: order and convergence radius
-// Convergence radius 1/3 with 27 coefficients has the truncation error of the round-1 choice (1/4, 21 coefficients:
-// worst case of one expansion ~5e-12, tests/test_farfield_model.py) but admits the tiles at index distance 2 for every
-// pair: the directly evaluated near field is 3 tiles instead of 5 on average and a pair is expanded at ~21 instead of
-// ~42 tiles per level.
-constexpr int SD_FAR_K = 26;            // polynomial degree (27 coefficients)
-constexpr double SD_FAR_RHO_INV = 3.0;  // a (line, depth) pair is expanded only if |nu_c - pole| >= 3 h
-constexpr float SD_FAR_LOG2_RHO_INV = 1.5849625f;  // log2(SD_FAR_RHO_INV)
-constexpr int SD_FAR_LEVELS = 3;        // tile hierarchy: level k tiles hold 256 * P * 8^k pixels
-constexpr int SD_FAR_SHIFT = 3;         // log2 of the branching factor
-static_assert(SD_FAR_LEVELS == 3, "PairWin::near holds three levels");
-constexpr int SD_FC_CLASS = SD_NCLS - 1;  // class of the "far-capable" pairs (window >= one level-0 tile, finite parameters)
+// Far field of the region-I wings on a hierarchy of pixel tiles (64 / 512 / 4096 / 32768 pixels, branching 8).
+// A (line, depth) pair whose centre lies in tile s of level k is FAR from tile t of that level when |s - t| >= 2, its
+// window covers t, t has at least two pixels and k >= lmin(pair) (lmin: the lowest level at which every pixel two tiles
+// away is certainly in Humlicek region I and the pair's two poles sit close enough to their own tile for the
+// expansions below to converge with ratio <= SD_FAR_RHO).  A far (pair, pixel) product is served at the HIGHEST level
+// at which it is far, by a polynomial of degree SD_FAR_K in (nu - nu_c) / h per tile and depth:
+//   * pairs whose window covers the whole interaction neighbourhood of their tile ("saturated": the 24 children of
+//     the parent tile and its two neighbours; the whole grid at the top level) go through multipole moments of their
+//     own tile (k_s2m, ONE expansion per pair and level) and tile-to-tile translations (k_m2l), as in a 1-D fast
+//     multipole method -- the translation matrices are real because the tile centres are;
+//   * the others (a window edge inside the neighbourhood) are expanded directly about the target tiles
+//     (k_far_coeffs), as every far pair was in round 1.
+constexpr int SD_FAR_K = 31;             // polynomial degree (32 coefficients); multipole moments k = 1..32
+constexpr double SD_FAR_RHO = 0.40;      // largest admitted convergence ratio: 33 * 0.4^32 = 6e-12
+constexpr float SD_FAR_LOG2_RHO_INV = 1.3219281f;  // log2(1 / SD_FAR_RHO)
+constexpr double SD_FAR_OVERHANG = 0.2;  // the poles may leave their tile by at most this fraction of its half-width
+constexpr int SD_FAR_LEVELS = 4;         // tile hierarchy: level k tiles hold 64 * 8^k pixels
+constexpr int SD_FAR_SHIFT = 3;          // log2 of the branching factor
+constexpr int SD_FAR_TILE0_SHIFT = 6;    // level-0 tiles: 64 pixels = two register slots of a k_lines warp
+constexpr int SD_FC0 = 7;                // classes SD_FC0 + m: far-capable pairs with lmin = m (sorted by centre)
+constexpr int SD_NCLS = SD_FC0 + SD_FAR_LEVELS;  // half-width classes 0..6 + far-capable classes
 
 // geometry of the far-field tile hierarchy and the per-pair tables that drive it, passed by value to the kernels
 struct FarGeom {
     int tile[SD_FAR_LEVELS];            // pixels per tile (powers of two)
     int tile_shift[SD_FAR_LEVELS];      // log2 of them
     int n_tiles[SD_FAR_LEVELS];         // global number of tiles
-    const double *geom[SD_FAR_LEVELS];  // {centre frequency, half-width} per tile
-    int enabled;                        // far field on (PairWin::near is filled, edge lists exist)
-    int *near_rad;                      // [SD_FAR_LEVELS] largest half-extent (in tiles) of any near interval
+    const double *geom[SD_FAR_LEVELS];  // {centre frequency, half-width, moment scale} per tile (3 doubles)
+    int enabled;                        // far field on (far-capable classes and edge lists exist)
+    // [SD_FAR_LEVELS + 1] written by k_level_check: n_active (levels 0 .. n_active-1 are usable on this grid; level
+    // n_active-1 is the top level, whose interaction neighbourhood is the whole grid), then per level the admitted
+    // pole overhang as a fraction of the tile half-width (float bits)
+    const int *lev_info;
     // Window edges of the far-capable pairs that lie inside the grid AND inside this context's extended pixel range
     // (the top-level tiles its range touches), as ONE sorted array of 64-bit keys
-    //   kind (0 = window start, 1 = window end) | depth | edge pixel | line index      (see sd_edge_key)
+    //   kind (0 = window start, 1 = window end) | depth | lmin | edge pixel | line index      (see sd_edge_key)
     // -- a total order, so the result does not depend on the order in which k_build_records appended them.
-    // edge_off[kind * (D + 1) + d] = first entry of (kind, d); [.. + D] = end of the kind's entries.
+    // edge_off[(kind * D + d) * SD_FAR_LEVELS + m] = first entry of (kind, d, m); one more entry closes the array.
     const unsigned long long *edge_keys;
     const int *edge_off;
     int l_bits, pix_bits, depth_bits;
@@ -67,10 +80,13 @@ struct FarGeom {
     unsigned long long *edge_count;      // [1] number of appended keys
     long long ext0, ext1;                // extended pixel range [ext0, ext1): pairs whose window misses it get no LineRec
 };
+constexpr int SD_FAR_LMIN_BITS = 2;
+static_assert((1 << SD_FAR_LMIN_BITS) >= SD_FAR_LEVELS, "lmin field of the edge key");
 
-__host__ __device__ __forceinline__ unsigned long long sd_edge_key(const FarGeom &fg, int kind, int d, long long pixel, int l) {
-    return ((((unsigned long long)kind << fg.depth_bits | (unsigned long long)d) << fg.pix_bits | (unsigned long long)pixel)
-            << fg.l_bits) | (unsigned long long)(unsigned)l;
+__host__ __device__ __forceinline__ unsigned long long sd_edge_key(const FarGeom &fg, int kind, int d, int lmin, long long pixel,
+                                                                   int l) {
+    return (((((unsigned long long)kind << fg.depth_bits | (unsigned long long)d) << SD_FAR_LMIN_BITS | (unsigned long long)lmin)
+             << fg.pix_bits | (unsigned long long)pixel) << fg.l_bits) | (unsigned long long)(unsigned)l;
 }
 
 struct DevBuf {
@@ -126,17 +142,19 @@ struct sd_ctx {
     DevBuf cls_off;    // int32 [D*(NCLS+1)] offsets into cls_list row d (class 0 is not listed)
     DevBuf chunk_cnt;  // int32 [D * nchunks * NCLS]
     DevBuf stats;      // uint64 [8]
-    DevBuf near_rad;                   // int [SD_FAR_LEVELS]
+    DevBuf lev_info;                   // int [SD_FAR_LEVELS + 1], see FarGeom::lev_info
+    int far_active = 0;                // host copy of lev_info[0] (read at the edge-sort synchronisation)
     DevBuf edge_keys, edge_unsorted;   // 64-bit window-edge keys (sorted / as appended), see FarGeom
     DevBuf edge_off, edge_count, edge_sort_tmp;
     DevBuf line_pre, depth_pre;        // K1: per-line / per-depth factors of the broadening formulae (pow() hoisted)
     unsigned long long *h_edge_count = nullptr;  // pinned host copy of the edge counter
-    DevBuf tile_geom[SD_FAR_LEVELS];   // double [2 * n_tiles]: centre frequency and half-width of every global tile
+    DevBuf tile_geom[SD_FAR_LEVELS];   // double [3 * n_tiles]: centre frequency, half-width, moment scale of every global tile
     DevBuf far_coef[SD_FAR_LEVELS];    // double [D * n_tiles_shard * (SD_FAR_K + 1)]
-    DevBuf far_part;                   // partial top-level coefficient sets (8 slices of the pair list per tile)
+    DevBuf far_mom[SD_FAR_LEVELS];     // double [D * n_src_tiles * (SD_FAR_K + 1)]: multipole moments of the saturated pairs
+    DevBuf far_part;                   // partial coefficient sets (slices of the pair list per tile)
     FarGeom far_geom{};
     int k2_P = 4;      // pixels per thread chosen for the current grid
-    int k2_NW = 8;     // warps per CTA of the line kernel (level-0 tile = 32 * k2_NW * k2_P pixels)
+    int k2_NW = 8;     // warps per CTA of the line kernel (CTA tile = 32 * k2_NW * k2_P pixels)
     bool farfield = true;
     bool far_attr_set = false;  // dynamic shared memory opt-in of k_far_coeffs done on this device
     DevBuf alpha_line[2];

@@ -193,7 +193,7 @@ class DeviceContext:
         out = np.zeros(16, dtype=np.int64)
         self._ck(self.lib.sd_line_stats_ex(self.h, out.ctypes.data_as(C.POINTER(C.c_int64))))
         return dict(direct_region_evals=out[:4].copy(), far_replaced_evals=int(out[8]), far_expansions=int(out[9]),
-                    far_terms=int(out[10]))
+                    far_terms=int(out[10]), multipole_expansions=int(out[12]), m2l_row_steps=int(out[13]))
 
     PHASES = ("K1_broadening", "K2_prepare", "K2_edge_sort", "K2_far_coeffs", "K2_lines", "K3_continuum", "K4_raytrace",
               "line_strengths")
