@@ -95,7 +95,7 @@ void sd_destroy(sd_ctx *c) {
     DevBuf *all[] = {&c->T, &c->ne, &c->nH, &c->nus, &c->d_nu, &c->l_nu, &c->l_Z, &c->l_ion, &c->l_eion, &c->l_eup,
                      &c->l_elo, &c->l_A, &c->l_mass, &c->l_stark, &c->l_waals, &c->l_alpha, &c->gammas, &c->dws,
                      &c->vald_stage, &c->line_idx, &c->rec, &c->win, &c->win_cls, &c->cls_list, &c->cls_off,
-                     &c->chunk_cnt, &c->stats, &c->lev_info, &c->edge_keys, &c->edge_unsorted, &c->edge_off, &c->edge_count,
+                     &c->chunk_cnt, &c->stats, &c->lev_info, &c->fc_tab, &c->edge_tab, &c->edge_keys, &c->edge_unsorted, &c->edge_off, &c->edge_count,
                      &c->line_pre, &c->depth_pre, &c->edge_sort_tmp, &c->alpha_line[0], &c->alpha_line[1], &c->total, &c->cont_small,
                      &c->F, &c->I_nus, &c->ray_small};
     for (DevBuf *b : all) free_buf(*b);

@@ -514,6 +514,8 @@ int sd_k2_prepare(sd_ctx *c) {
     fg.enabled = 0;
     fg.edge_keys = nullptr;
     fg.edge_off = nullptr;
+    fg.fc_tab = nullptr;
+    fg.edge_tab = nullptr;
     fg.edge_out = nullptr;
     fg.edge_count = nullptr;
     fg.l_bits = fg.pix_bits = fg.depth_bits = 1;

@@ -140,42 +140,25 @@ __device__ __forceinline__ void class_range(const LineArgs &a, int d, int cls, i
     jb = warp_first_below(key, ja, hi, clamp_i32(t0 - H + 1));
 }
 
-// first j in [a, b) with keys[j] >= X (keys ascending), b if none.  Warp-cooperative 32-ary search.
-__device__ __forceinline__ int warp_lower_bound_u64(const unsigned long long *__restrict__ keys, int a, int b, unsigned long long X) {
-    const int lane = threadIdx.x & 31;
-    while (b > a) {
-        int n = b - a;
-        int step = (n + 31) >> 5;
-        long long pj = (long long)a + (long long)lane * step;
-        bool pred = (pj >= b) ? true : (keys[pj] >= X);
-        unsigned m = __ballot_sync(0xffffffffu, pred);
-        int f = m ? (__ffs(m) - 1) : 32;
-        if (f == 0) return a;
-        int na = a + (f - 1) * step + 1;
-        long long nb = (f < 32) ? (long long)a + (long long)f * step : (long long)b;
-        a = na;
-        b = (int)(nb < b ? nb : b);
-    }
-    return a;
-}
-
-// Far-capable pairs with lmin = m (class SD_FC0 + m, sorted by centre) whose centre pixel lies in [c0, c1).  The centre
-// pixel is line_idx clamped to N - 1, so a range that reaches the end of the grid takes the lines behind it too.
+// Far-capable pairs with lmin = m (class SD_FC0 + m, sorted by centre) whose centre pixel lies in [c0, c1), both
+// multiples of the level-0 tile size (or beyond the grid): two loads from the range table (FarGeom::fc_tab).
 __device__ __forceinline__ void fc_centre_range(const LineArgs &a, int d, int m, long long c0, long long c1, int &ja, int &jb) {
-    const int lo = a.cls_off[d * (SD_NCLS + 1) + SD_FC0 + m], hi = a.cls_off[d * (SD_NCLS + 1) + SD_FC0 + m + 1];
-    const int *list_d = a.cls_list + (size_t)d * a.L;
-    const int *line_idx = a.line_idx;
-    auto key = [&](int j) { return line_idx[list_d[j]]; };
-    ja = warp_first_below(key, lo, hi, c1 >= a.N ? 2147483647 : clamp_i32(c1));  // centre <  c1
-    jb = (c0 <= 0) ? hi : warp_first_below(key, ja, hi, clamp_i32(c0));           // centre <  c0
+    const int nt0 = a.fg.n_tiles[0];
+    const int *__restrict__ row = a.fg.fc_tab + (size_t)(d * SD_FAR_LEVELS + m) * (nt0 + 1);
+    const long long ta = c0 <= 0 ? 0 : (c0 >> SD_FAR_TILE0_SHIFT), tb = c1 >= a.N ? nt0 : (c1 >> SD_FAR_TILE0_SHIFT);
+    ja = row[tb < nt0 ? tb : nt0];
+    jb = row[ta < nt0 ? ta : nt0];
 }
 
-// Far-capable pairs of depth d and lmin = m with a window start (which = 0) or end (which = 1) strictly inside (t0, t1).
+// Far-capable pairs of depth d and lmin = m with a window start (which = 0) or end (which = 1) at a pixel in [t0, t1),
+// t0 a multiple of the level-0 tile size, t1 one or the end of the grid: two loads from the range table
+// (FarGeom::edge_tab).  Callers that need the edge STRICTLY inside (t0, t1) reject an edge at t0 themselves.
 __device__ __forceinline__ void fc_edge_range(const LineArgs &a, int d, int which, int m, int64_t t0, int64_t t1, int &ja, int &jb) {
-    const int o = (which * a.D + d) * SD_FAR_LEVELS + m;
-    const int lo = a.fg.edge_off[o], hi = a.fg.edge_off[o + 1];
-    ja = warp_lower_bound_u64(a.fg.edge_keys, lo, hi, sd_edge_key(a.fg, which, d, m, t0 + 1, 0));
-    jb = warp_lower_bound_u64(a.fg.edge_keys, ja, hi, sd_edge_key(a.fg, which, d, m, t1, 0));
+    const int nt0 = a.fg.n_tiles[0];
+    const int *__restrict__ row = a.fg.edge_tab + (size_t)((which * a.D + d) * SD_FAR_LEVELS + m) * (nt0 + 1);
+    const int64_t ta = t0 >> SD_FAR_TILE0_SHIFT, tb = t1 >= a.N ? nt0 : (t1 >> SD_FAR_TILE0_SHIFT);
+    ja = row[ta < nt0 ? ta : nt0];
+    jb = row[tb < nt0 ? tb : nt0];
 }
 
 // one 16-byte gather
@@ -259,7 +242,7 @@ __device__ __forceinline__ int far_terms(double rho2) {
     return FAR_TERMS[min(max(t8, 0), 255)];
 }
 
-__global__ void __launch_bounds__(THREADS) k_far_coeffs(LineArgs a, int lev, int count_stats, int nsplit, double *part) {
+__global__ void __launch_bounds__(THREADS, 2) k_far_coeffs(LineArgs a, int lev, int count_stats, int nsplit, double *part) {
     __shared__ int s_ja[FAR_MAX_SRC], s_jb[FAR_MAX_SRC];
     extern __shared__ __align__(16) unsigned char far_smem[];
     FarRec *const s_rec = reinterpret_cast<FarRec *>(far_smem);                        // [FAR_CH] dense records of the chunk
@@ -369,19 +352,37 @@ __global__ void __launch_bounds__(THREADS) k_far_coeffs(LineArgs a, int lev, int
     constexpr int SEGS = ROUNDS * WARPS;       // (round, warp) segments of 32 candidates, in list order
     static_assert(SEGS == 32, "one lane per segment in the offset scan");
     __shared__ int s_cnt[SEGS];
-    for (int src = 0; src < n_src; src++) {
-        const int ja = s_ja[src], jb = s_jb[src];
-        const int kind = src % 3;
-        for (int base = ja; base < jb; base += FAR_CH) {
+    // one candidate stream: the slices of all sources, concatenated in source order
+    __shared__ int s_pre[FAR_MAX_SRC + 1];
+    if (tid == 0) {
+        int acc = 0;
+        for (int src = 0; src < FAR_MAX_SRC; src++) {
+            s_pre[src] = acc;
+            if (src < n_src) acc += s_jb[src] - s_ja[src];
+        }
+        s_pre[FAR_MAX_SRC] = acc;
+    }
+    __syncthreads();
+    const int total = s_pre[FAR_MAX_SRC];
+    {
+        for (int base = 0; base < total; base += FAR_CH) {
             // ---- test
             unsigned mk[ROUNDS];
             int ll[ROUNDS], rk[ROUNDS];
 #pragma unroll
             for (int r = 0; r < ROUNDS; r++) {
-                const int idx = r * THREADS + tid, j = base + idx;
+                const int v = base + r * THREADS + tid;
                 unsigned mask = 0;
                 int l = 0;
-                if (j < jb) {
+                if (v < total) {
+                    int src = 0, off = 0;
+#pragma unroll
+                    for (int q = 1; q < FAR_MAX_SRC; q++) {
+                        const int pq = s_pre[q];   // non-decreasing
+                        if (v >= pq) { src = q; off = pq; }
+                    }
+                    const int j = s_ja[src] + (v - off);
+                    const int kind = src % 3;
                     l = (kind == 0) ? list_d[j] : (int)(a.fg.edge_keys[j] & lmask);
                     const PairWin pw = load_win(a.win + drow + l);
                     bool okp;
@@ -389,7 +390,7 @@ __global__ void __launch_bounds__(THREADS) k_far_coeffs(LineArgs a, int lev, int
                         okp = !((pw.sat >> lev) & 1u);
                     } else {          // (B): far from the parent by distance; both edges inside the parent: via its start
                         const int dsp = (pw.cpix >> pshift) - ptile;
-                        okp = (dsp >= 2 || dsp <= -2) && !(kind == 2 && pw.lo > pt0 && pw.lo < pt1);
+                        okp = (dsp >= 2 || dsp <= -2) && ((kind == 1 ? pw.lo : pw.hi) > pt0) && !(kind == 2 && pw.lo > pt0 && pw.lo < pt1);
                     }
                     if (okp) {
 #pragma unroll
@@ -477,6 +478,9 @@ static int far_nsplit(int lev, bool top) {
     return far_nsplit_base(lev, top) * (scale >= 1 && scale <= 8 ? scale : 1);
 }
 
+// slices of the pair ranges per source tile in k_s2m (constants, like far_nsplit_base)
+__host__ __device__ constexpr int s2m_nsplit(int lev, bool top) { return top ? 64 : (lev == 0 ? 1 : (lev == 1 ? 2 : 16)); }
+
 // sum of the nsplit partial coefficient sets of a level, in slice order
 __global__ void k_far_reduce(int n, int nsplit, const double *__restrict__ part, double *__restrict__ coef) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;  // (depth, tile) * K1 + k
@@ -495,10 +499,11 @@ __global__ void k_far_reduce(int n, int nsplit, const double *__restrict__ part,
 // scheme of round 1 expanded a whole-grid pair about ~21 target tiles per level.  The pairs of a tile are contiguous
 // ranges (by centre) of the class lists with lmin <= lev; warp w of a CTA takes tile 8 * group + w, one pair per lane,
 // Im(u^k) by the three-term recurrence, fixed shuffle reduction: the moments do not depend on the shard.
-__global__ void __launch_bounds__(THREADS) k_s2m(LineArgs a, int lev, int count_stats) {
+__global__ void __launch_bounds__(THREADS) k_s2m(LineArgs a, int lev, int count_stats, int nsplit, double *part) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int d = blockIdx.y;
-    const int s = a.src_tile0[lev] + (int)blockIdx.x * WARPS + warp;
+    const int split = (int)blockIdx.x % nsplit;   // this CTA's slice of every pair range (few, populous tiles at the upper levels)
+    const int s = a.src_tile0[lev] + ((int)blockIdx.x / nsplit) * WARPS + warp;
     if (s >= a.src_tile0[lev] + a.n_src[lev]) return;  // warps are independent: no CTA barrier below
     const int shift = a.fg.tile_shift[lev];
     const long long T = a.fg.tile[lev];
@@ -530,6 +535,11 @@ __global__ void __launch_bounds__(THREADS) k_s2m(LineArgs a, int lev, int count_
     for (int m = 0; m <= lev; m++) {
         int ja, jb;
         fc_centre_range(a, d, m, (long long)s * T, ((long long)s + 1) * T, ja, jb);
+        if (nsplit > 1) {  // a function of the range and nsplit only
+            const int len = (jb - ja + nsplit - 1) / nsplit;
+            ja = min(ja + split * len, jb);
+            jb = min(ja + len, jb);
+        }
         for (int j0 = ja; j0 < jb; j0 += 32) {
             const int j = j0 + lane;
             bool have = false;
@@ -570,7 +580,9 @@ __global__ void __launch_bounds__(THREADS) k_s2m(LineArgs a, int lev, int count_
         for (int o2 = 16; o2; o2 >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o2);
         if (lane == k) mine = v;
     }
-    a.far_mom[lev][((size_t)d * a.n_src[lev] + (s - a.src_tile0[lev])) * K1 + lane] = mine;
+    const size_t tl = (size_t)d * a.n_src[lev] + (s - a.src_tile0[lev]);
+    if (nsplit > 1) part[(tl * nsplit + split) * K1 + lane] = mine;
+    else a.far_mom[lev][tl * K1 + lane] = mine;
     if (count_stats) {
         for (int o2 = 16; o2; o2 >>= 1) {
             n_pix += __shfl_xor_sync(0xffffffffu, n_pix, o2);
@@ -807,7 +819,7 @@ __global__ void __launch_bounds__(32 * NW, MINB) k_lines(LineArgs a) {
                         const int ta = (int)(t0 >> sh), tb = (int)((t1 - 1) >> sh);
                         const int64_t r0 = (int64_t)ta << sh;
                         const int64_t r1 = (((int64_t)tb + 1) << sh) < N ? (((int64_t)tb + 1) << sh) : N;
-                        pass = pass && (sj < ta - 1 || sj > tb + 1) && !(skind == 2 && lo > r0 && lo < r1);
+                        pass = pass && (sj < ta - 1 || sj > tb + 1) && ((skind == 1 ? lo : hi) > r0) && !(skind == 2 && lo > r0 && lo < r1);
                     }
                     msk = 0;
                     if (m == 0) {
@@ -1052,7 +1064,12 @@ int launch(sd_ctx *c, const LineArgs &a, dim3 grid, bool stats, int rcp) {
     // the counting instantiation uses the production arithmetic (Newton reciprocal) so that both are bitwise equal
     if (stats) k_lines<P, NW, true, 2, MINB><<<grid, 32 * NW, 0, c->stream>>>(a);
     else if (rcp == 3) k_lines<P, NW, false, 3, MINB><<<grid, 32 * NW, 0, c->stream>>>(a);
-    else k_lines<P, NW, false, 2, MINB><<<grid, 32 * NW, 0, c->stream>>>(a);
+    else {
+        static const int minb = env_int("SD_K2_MINB", 0);  // tuning experiments: more resident CTAs, fewer registers
+        if (NW == 2 && P == 8 && minb == 10) k_lines<8, 2, false, 2, 10><<<grid, 64, 0, c->stream>>>(a);
+        else if (NW == 2 && P == 8 && minb == 12) k_lines<8, 2, false, 2, 12><<<grid, 64, 0, c->stream>>>(a);
+        else k_lines<P, NW, false, 2, MINB><<<grid, 32 * NW, 0, c->stream>>>(a);
+    }
     return sd_launch_check(c, "k_lines");
 }
 
@@ -1149,9 +1166,11 @@ int sd_k2_lines(sd_ctx *c, int slot) {
         // many fixed slices so that even a narrow shard fills the chip; k_far_reduce adds the partial sums in slice order.
         size_t part_bytes = 0;
         for (int k = 0; k < n_act; k++) {
-            const int ns = far_nsplit(k, k == n_act - 1);
+            const int ns = far_nsplit(k, k == n_act - 1), nm = s2m_nsplit(k, k == n_act - 1);
             const size_t b = ns > 1 ? sizeof(double) * c->D * a.far_ntl[k] * ns * K1 : 0;
+            const size_t bm = nm > 1 ? sizeof(double) * c->D * a.n_src[k] * nm * K1 : 0;
             part_bytes = b > part_bytes ? b : part_bytes;
+            part_bytes = bm > part_bytes ? bm : part_bytes;
         }
         SD_TRY(sd_ensure(c, c->far_part, part_bytes > 0 ? part_bytes : 8));
         sd_phase_begin(c, SD_PH_FAR);
@@ -1168,8 +1187,15 @@ int sd_k2_lines(sd_ctx *c, int slot) {
                 k_far_reduce<<<(n + 255) / 256, 256, 0, c->stream>>>(n, nsplit, c->far_part.as<double>(), a.far_coef[k]);
                 SD_TRY(sd_launch_check(c, "k_far_reduce"));
             }
-            k_s2m<<<dim3((unsigned)((a.n_src[k] + WARPS - 1) / WARPS), (unsigned)c->D), THREADS, 0, c->stream>>>(a, k, cs);
+            const int nm = s2m_nsplit(k, k == n_act - 1);
+            k_s2m<<<dim3((unsigned)(((a.n_src[k] + WARPS - 1) / WARPS) * nm), (unsigned)c->D), THREADS, 0, c->stream>>>(
+                a, k, cs, nm, c->far_part.as<double>());
             SD_TRY(sd_launch_check(c, "k_s2m"));
+            if (nm > 1) {
+                const int n = c->D * a.n_src[k] * K1;
+                k_far_reduce<<<(n + 255) / 256, 256, 0, c->stream>>>(n, nm, c->far_part.as<double>(), a.far_mom[k]);
+                SD_TRY(sd_launch_check(c, "k_far_reduce"));
+            }
             k_m2l<<<dim3((unsigned)n_grp, (unsigned)((c->D + M2L_DC - 1) / M2L_DC)), THREADS, 0, c->stream>>>(a, k, cs);
             SD_TRY(sd_launch_check(c, "k_m2l"));
         }

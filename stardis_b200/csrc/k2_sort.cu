@@ -33,6 +33,40 @@ __global__ void k_edge_offsets(FarGeom fg, const unsigned long long *__restrict_
     }
     off[i] = (int)lo;
 }
+// Range tables (FarGeom::fc_tab / edge_tab): one thread per (row, level-0 tile boundary), a binary search each.
+__global__ void __launch_bounds__(256) k_range_tables(FarGeom fg, int D, int64_t L, const int *__restrict__ line_idx,
+                                                      const int *__restrict__ cls_list, const int *__restrict__ cls_off,
+                                                      const unsigned long long *__restrict__ keys, int *__restrict__ fc_tab,
+                                                      int *__restrict__ edge_tab) {
+    const int nb = fg.n_tiles[0] + 1;
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long n_fc = (long long)D * SD_FAR_LEVELS * nb;
+    if (i < n_fc) {
+        const int t = (int)(i % nb), row = (int)(i / nb), m = row % SD_FAR_LEVELS, d = row / SD_FAR_LEVELS;
+        // first entry of the class list whose line index (= centre pixel unless the line lies behind the last pixel,
+        // which belongs to the last tile) is below 64 t; the indices descend along the list
+        int lo = cls_off[d * (SD_NCLS + 1) + SD_FC0 + m], hi = cls_off[d * (SD_NCLS + 1) + SD_FC0 + m + 1];
+        const int *list_d = cls_list + (size_t)d * L;
+        const long long X = (t == nb - 1) ? (1LL << 40) : ((long long)t << SD_FAR_TILE0_SHIFT);
+        while (lo < hi) {
+            const int mid = lo + ((hi - lo) >> 1);
+            if ((long long)line_idx[list_d[mid]] < X) hi = mid; else lo = mid + 1;
+        }
+        fc_tab[i] = lo;
+    } else if (i < 3 * n_fc) {
+        const long long e = i - n_fc;
+        const int t = (int)(e % nb), row = (int)(e / nb);   // row = (kind * D + d) * SD_FAR_LEVELS + m
+        int lo = fg.edge_off[row], hi = fg.edge_off[row + 1];
+        const int m = row % SD_FAR_LEVELS, kd = row / SD_FAR_LEVELS, kind = kd / D, d = kd - kind * D;
+        const unsigned long long X = sd_edge_key(fg, kind, d, m, (long long)t << SD_FAR_TILE0_SHIFT, 0);
+        if (t == nb - 1) lo = hi;  // every listed edge lies inside the grid (the key field may not hold 64 t here)
+        while (lo < hi) {
+            const int mid = lo + ((hi - lo) >> 1);
+            if (keys[mid] < X) lo = mid + 1; else hi = mid;
+        }
+        edge_tab[e] = lo;
+    }
+}
 }  // namespace
 
 int sd_sort_edges(sd_ctx *c) {
@@ -60,5 +94,14 @@ int sd_sort_edges(sd_ctx *c) {
     fg.edge_off = c->edge_off.as<int>();
     k_edge_offsets<<<(2 * c->D * SD_FAR_LEVELS + 1 + 127) / 128, 128, 0, c->stream>>>(fg, fg.edge_keys, c->edge_count.as<unsigned long long>(), c->D,
                                                                       c->edge_off.as<int>());
-    return sd_launch_check(c, "k_edge_offsets");
+    SD_TRY(sd_launch_check(c, "k_edge_offsets"));
+    const long long n_fc = (long long)c->D * SD_FAR_LEVELS * (fg.n_tiles[0] + 1);
+    SD_TRY(sd_ensure(c, c->fc_tab, sizeof(int) * (size_t)n_fc));
+    SD_TRY(sd_ensure(c, c->edge_tab, sizeof(int) * (size_t)(2 * n_fc)));
+    fg.fc_tab = c->fc_tab.as<int>();
+    fg.edge_tab = c->edge_tab.as<int>();
+    k_range_tables<<<(unsigned)((3 * n_fc + 255) / 256), 256, 0, c->stream>>>(
+        fg, c->D, c->L, c->line_idx.as<int>(), c->cls_list.as<int>(), c->cls_off.as<int>(), fg.edge_keys, c->fc_tab.as<int>(),
+        c->edge_tab.as<int>());
+    return sd_launch_check(c, "k_range_tables");
 }

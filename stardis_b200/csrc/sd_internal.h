@@ -75,6 +75,13 @@ struct FarGeom {
     // edge_off[(kind * D + d) * SD_FAR_LEVELS + m] = first entry of (kind, d, m); one more entry closes the array.
     const unsigned long long *edge_keys;
     const int *edge_off;
+    // Range tables per level-0 tile boundary t = 0..n_tiles[0] (k_range_tables): the far-capable pairs of (depth d,
+    // lmin m) centred in the level-0 tiles [ta, tb) are the entries [fc_tab[row + tb], fc_tab[row + ta]) of the depth's
+    // class list (centres descend along the list), row = (d * SD_FAR_LEVELS + m) * (n_tiles[0] + 1); their window edges
+    // at pixels [64 ta, 64 tb) are the keys [edge_tab[erow + ta], edge_tab[erow + tb)), erow = ((kind * D + d) *
+    // SD_FAR_LEVELS + m) * (n_tiles[0] + 1).  Two loads instead of two binary searches per candidate range.
+    const int *fc_tab;
+    const int *edge_tab;
     int l_bits, pix_bits, depth_bits;
     unsigned long long *edge_out;        // unsorted append buffer (k_build_records)
     unsigned long long *edge_count;      // [1] number of appended keys
@@ -146,6 +153,7 @@ struct sd_ctx {
     int far_active = 0;                // host copy of lev_info[0] (read at the edge-sort synchronisation)
     DevBuf edge_keys, edge_unsorted;   // 64-bit window-edge keys (sorted / as appended), see FarGeom
     DevBuf edge_off, edge_count, edge_sort_tmp;
+    DevBuf fc_tab, edge_tab;           // range tables per level-0 tile boundary, see FarGeom
     DevBuf line_pre, depth_pre;        // K1: per-line / per-depth factors of the broadening formulae (pow() hoisted)
     unsigned long long *h_edge_count = nullptr;  // pinned host copy of the edge counter
     DevBuf tile_geom[SD_FAR_LEVELS];   // double [3 * n_tiles]: centre frequency, half-width, moment scale of every global tile
