@@ -104,6 +104,7 @@ void sd_destroy(sd_ctx *c) {
         free_buf(c->tile_geom[k]);
         free_buf(c->far_coef[k]);
         free_buf(c->far_mom[k]);
+        for (int h = 0; h < SD_FAR_LEVELS; h++) free_buf(c->far_bkt[k][h]);
     }
     free_buf(c->far_part);
     if (c->h_edge_count) cudaFreeHost(c->h_edge_count);

@@ -87,9 +87,10 @@ struct LineArgs {
     double *far_coef[SD_FAR_LEVELS];   // per level: (D, n_tiles_launch[k], K1)
     int far_tile0[SD_FAR_LEVELS];      // first global tile of this launch, per level
     int far_ntl[SD_FAR_LEVELS];        // tiles of this launch, per level
-    double *far_mom[SD_FAR_LEVELS];    // per level: (D, n_src[k], K1) multipole moments of the saturated pairs
-    int src_tile0[SD_FAR_LEVELS];      // first global source tile of this launch, per level
-    int n_src[SD_FAR_LEVELS];          // source tiles of this launch, per level
+    double *far_mom[SD_FAR_LEVELS];    // per level: (D, n_tiles[k], K1) multipole moments of the pairs saturated at level k
+    // far_bkt[k][h], h >= k: (D, n_tiles[k], K1) moments about the level-k tile centres of the pairs with lmin <= k
+    // whose HIGHEST saturated level is h (k_s2m fills level lmin, k_m2m translates upwards and sums far_mom)
+    double *far_bkt[SD_FAR_LEVELS][SD_FAR_LEVELS];
     double *out;                 // (D, p1 - p0)
     unsigned long long *stats;
 };
@@ -364,6 +365,14 @@ __global__ void __launch_bounds__(THREADS, 2) k_far_coeffs(LineArgs a, int lev, 
     }
     __syncthreads();
     const int total = s_pre[FAR_MAX_SRC];
+    if (total == 0) {  // nothing to expand for this group (CTA-uniform): zeros
+        if (tile_ok) {
+            const size_t tl = (size_t)d * a.far_ntl[lev] + (tile - a.far_tile0[lev]);
+            if (nsplit > 1) part[(tl * nsplit + split) * K1 + lane] = 0.0;
+            else a.far_coef[lev][tl * K1 + lane] = 0.0;
+        }
+        return;
+    }
     {
         for (int base = 0; base < total; base += FAR_CH) {
             // ---- test
@@ -443,18 +452,28 @@ __global__ void __launch_bounds__(THREADS, 2) k_far_coeffs(LineArgs a, int lev, 
             __syncthreads();  // the chunk buffers are overwritten by the next chunk
         }
     }
-    // deterministic reduction: lanes by shuffle (every lane ends up with the sum; lane k keeps coefficient k)
-    double mine = 0.0;
+    // deterministic reduction over the lanes through shared memory (the chunk buffers are free now): two halves of 16
+    // coefficients, lane k sums coefficient k of the 32 lanes in lane order -- a third of the instructions of 32
+    // butterfly reductions
+    static_assert(FAR_SMEM >= sizeof(double) * WARPS * (K1 / 2) * 33, "reduction scratch fits the chunk buffers");
+    double (*red)[33] = reinterpret_cast<double (*)[33]>(far_smem) + warp * (K1 / 2);
+    const size_t tl = (size_t)d * a.far_ntl[lev] + (tile - a.far_tile0[lev]);
 #pragma unroll
-    for (int k = 0; k < K1; k++) {
-        double v = C[k];
-        for (int o2 = 16; o2; o2 >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o2);
-        if (lane == k) mine = v;
-    }
-    if (tile_ok) {
-        const size_t tl = (size_t)d * a.far_ntl[lev] + (tile - a.far_tile0[lev]);
-        if (nsplit > 1) part[(tl * nsplit + split) * K1 + lane] = mine;
-        else a.far_coef[lev][tl * K1 + lane] = mine;
+    for (int half = 0; half < 2; half++) {
+#pragma unroll
+        for (int kk = 0; kk < K1 / 2; kk++) red[kk][lane] = C[half * (K1 / 2) + kk];
+        __syncwarp();
+        if (lane < K1 / 2) {
+            double v = 0.0;
+#pragma unroll 8
+            for (int i = 0; i < 32; i++) v += red[lane][i];
+            if (tile_ok) {
+                const int k = half * (K1 / 2) + lane;
+                if (nsplit > 1) part[(tl * nsplit + split) * K1 + k] = v;
+                else a.far_coef[lev][tl * K1 + k] = v;
+            }
+        }
+        __syncwarp();
     }
     if (count_stats) {  // every far pair stands for one region-I evaluation per tile pixel inside the shard
         for (int o2 = 16; o2; o2 >>= 1) {
@@ -478,9 +497,6 @@ static int far_nsplit(int lev, bool top) {
     return far_nsplit_base(lev, top) * (scale >= 1 && scale <= 8 ? scale : 1);
 }
 
-// slices of the pair ranges per source tile in k_s2m (constants, like far_nsplit_base)
-__host__ __device__ constexpr int s2m_nsplit(int lev, bool top) { return top ? 64 : (lev == 0 ? 1 : (lev == 1 ? 2 : 16)); }
-
 // sum of the nsplit partial coefficient sets of a level, in slice order
 __global__ void k_far_reduce(int n, int nsplit, const double *__restrict__ part, double *__restrict__ coef) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;  // (depth, tile) * K1 + k
@@ -492,97 +508,138 @@ __global__ void k_far_reduce(int n, int nsplit, const double *__restrict__ part,
 }
 
 // ------------------------------------------------------------------------------------------------------------------
-// Multipole moments of one (level-`lev` source tile s, depth):  M_k = sum_pairs A Im(u+^k + u-^k),  k = 1..K1,
-// u = (pole - c_s) / scale_s,  over the pairs centred in s that are SATURATED at this level (window covering the whole
-// interaction neighbourhood of s), so that   sum_pairs contribution(nu) = (1 / scale_s) sum_k M_k / tau^(k+1),
-// tau = (nu - c_s) / scale_s,  for every pixel at least two tiles away.  ONE expansion per pair and level -- the direct
-// scheme of round 1 expanded a whole-grid pair about ~21 target tiles per level.  The pairs of a tile are contiguous
-// ranges (by centre) of the class lists with lmin <= lev; warp w of a CTA takes tile 8 * group + w, one pair per lane,
-// Im(u^k) by the three-term recurrence, fixed shuffle reduction: the moments do not depend on the shard.
-__global__ void __launch_bounds__(THREADS) k_s2m(LineArgs a, int lev, int count_stats, int nsplit, double *part) {
+// Multipole moments:  M_k(s) = sum_pairs A Im(u+^k + u-^k),  k = 1..K1,  u = (pole - c_s) / scale_s,  over the pairs
+// centred in tile s that are SATURATED at the tile's level (window covering the whole interaction neighbourhood), so that
+//   sum_pairs contribution(nu) = (1 / scale_s) sum_k M_k / tau^(k+1),  tau = (nu - c_s) / scale_s,
+// for every pixel at least two tiles away.  Every pair is expanded ONCE, about its tile of level lmin (k_s2m), into the
+// bucket of its highest saturated level hs (saturation is monotone: saturated at a level => at every lower level >=
+// lmin); k_m2m translates the buckets to the parent tiles level by level (exact: a finite binomial sum) and adds up, per
+// level k, the buckets hs >= k -- the moments k_m2l needs there.  (The direct scheme of round 1 expanded a whole-grid
+// pair about ~21 target tiles per level.)
+//
+// k_s2m(m): one warp per run of eight level-m tiles (the children of one level-(m+1) tile) and depth.  The pairs of the
+// run are one contiguous piece of the class list of lmin = m (centres descend along it).  Per batch of 32 pairs every
+// lane expands ITS pair about the pair's own tile (three-term recurrence for Im(u^k)) and writes the 32 moments to
+// shared memory; then lane k walks the batch in list order and adds moment k of every pair to the accumulator of the
+// pair's bucket, flushing to global memory whenever the tile changes (tiles without pairs get zeros).  All lanes busy,
+// fixed order, nothing depends on the shard.
+constexpr int S2M_WARPS = 4;
+
+// pixels of the shard inside the interaction list of level-`lev` tile s (statistics: evaluations one saturated pair stands for)
+__device__ __forceinline__ long long il_pixels(const LineArgs &a, int lev, int s) {
+    const long long T = a.fg.tile[lev];
+    long long nb0 = 0, nb1 = a.N;
+    if (lev + 1 < a.n_act) {
+        const long long P = s >> SD_FAR_SHIFT, Tp = a.fg.tile[lev + 1];
+        nb0 = (P - 1) * Tp > 0 ? (P - 1) * Tp : 0;
+        nb1 = (P + 2) * Tp < a.N ? (P + 2) * Tp : a.N;
+    }
+    const long long nr0 = ((long long)s - 1) * T > 0 ? ((long long)s - 1) * T : 0;
+    const long long nr1 = ((long long)s + 2) * T < a.N ? ((long long)s + 2) * T : a.N;
+    auto clip = [&](long long x0, long long x1) {
+        const long long e0 = x0 > a.p0 ? x0 : a.p0, e1 = x1 < a.p1 ? x1 : a.p1;
+        return e1 > e0 ? e1 - e0 : 0LL;
+    };
+    return clip(nb0, nb1) - clip(nr0, nr1);
+}
+
+__global__ void __launch_bounds__(32 * S2M_WARPS) k_s2m(LineArgs a, int m, int count_stats) {
+    __shared__ double s_buf[S2M_WARPS][K1][33];
+    __shared__ int s_tile[S2M_WARPS][32];
+    __shared__ int s_hs[S2M_WARPS][32];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int d = blockIdx.y;
-    const int split = (int)blockIdx.x % nsplit;   // this CTA's slice of every pair range (few, populous tiles at the upper levels)
-    const int s = a.src_tile0[lev] + ((int)blockIdx.x / nsplit) * WARPS + warp;
-    if (s >= a.src_tile0[lev] + a.n_src[lev]) return;  // warps are independent: no CTA barrier below
-    const int shift = a.fg.tile_shift[lev];
-    const long long T = a.fg.tile[lev];
-    const double c_s = a.fg.geom[lev][3 * s], sc = a.fg.geom[lev][3 * s + 2];
-    const double inv_sc = sc > 0.0 ? 1.0 / sc : 0.0;
+    const int nt = a.fg.n_tiles[m];
+    const int run = (int)blockIdx.x * S2M_WARPS + warp;
+    const int t_lo = run << SD_FAR_SHIFT;
+    if (t_lo >= nt) return;  // warps are independent: no CTA barrier below
+    const int t_hi = min(t_lo + (1 << SD_FAR_SHIFT), nt) - 1;
+    const int shift = a.fg.tile_shift[m];
+    const long long T = a.fg.tile[m];
+    const double *__restrict__ gm = a.fg.geom[m];
     const size_t drow = (size_t)d * a.L;
     const int *list_d = a.cls_list + drow;
-    double C[K1];
-#pragma unroll
-    for (int k = 0; k < K1; k++) C[k] = 0.0;
+    double (*buf)[33] = s_buf[warp];
+    int *const b_tile = s_tile[warp], *const b_hs = s_hs[warp];
+    const int nb = a.n_act - m;  // buckets hs = m .. n_act - 1
+    double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0, acc3 = 0.0;
+    int cur = -1;              // tile whose sums are in the accumulators (-1: none)
+    int next_out = t_hi;       // highest tile of the run not written yet
     unsigned long long n_pix = 0, n_exp = 0;
-    // pixels of the shard inside the interaction list of s (statistics: evaluations one saturated pair stands for)
-    long long il_pix = 0;
-    if (count_stats) {
-        long long nb0 = 0, nb1 = a.N;
-        if (lev + 1 < a.n_act) {
-            const long long P = s >> SD_FAR_SHIFT, Tp = a.fg.tile[lev + 1];
-            nb0 = (P - 1) * Tp > 0 ? (P - 1) * Tp : 0;
-            nb1 = (P + 2) * Tp < a.N ? (P + 2) * Tp : a.N;
+    auto store_tile = [&](int tile, double v0, double v1, double v2, double v3) {
+        const size_t o = ((size_t)d * nt + tile) * K1 + lane;
+        a.far_bkt[m][m][o] = v0;
+        if (nb > 1) a.far_bkt[m][m + 1][o] = v1;
+        if (nb > 2) a.far_bkt[m][m + 2][o] = v2;
+        if (nb > 3) a.far_bkt[m][m + 3][o] = v3;
+    };
+    auto close_down_to = [&](int tile) {  // write the open tile and zeros for the untouched ones above `tile`
+        if (cur >= 0) {
+            store_tile(cur, acc0, acc1, acc2, acc3);
+            next_out = cur - 1;
+            acc0 = acc1 = acc2 = acc3 = 0.0;
+            cur = -1;
         }
-        long long nr0 = ((long long)s - 1) * T > 0 ? ((long long)s - 1) * T : 0;
-        long long nr1 = ((long long)s + 2) * T < a.N ? ((long long)s + 2) * T : a.N;
-        auto clip = [&](long long x0, long long x1) {
-            const long long e0 = x0 > a.p0 ? x0 : a.p0, e1 = x1 < a.p1 ? x1 : a.p1;
-            return e1 > e0 ? e1 - e0 : 0LL;
-        };
-        il_pix = clip(nb0, nb1) - clip(nr0, nr1);
-    }
-    for (int m = 0; m <= lev; m++) {
-        int ja, jb;
-        fc_centre_range(a, d, m, (long long)s * T, ((long long)s + 1) * T, ja, jb);
-        if (nsplit > 1) {  // a function of the range and nsplit only
-            const int len = (jb - ja + nsplit - 1) / nsplit;
-            ja = min(ja + split * len, jb);
-            jb = min(ja + len, jb);
-        }
-        for (int j0 = ja; j0 < jb; j0 += 32) {
-            const int j = j0 + lane;
-            bool have = false;
-            int l = 0;
-            if (j < jb) {
-                l = list_d[j];
-                const PairWin pw = load_win(a.win + drow + l);
-                have = ((pw.sat >> lev) & 1u) && ((pw.cpix >> shift) == s);
-            }
-            if (!__any_sync(0xffffffffu, have)) continue;
-            double An = 0.0, u1r = 0.0, u2r = 0.0, ui = 0.0;
-            if (have) {
+        for (; next_out > tile; next_out--) store_tile(next_out, 0.0, 0.0, 0.0, 0.0);
+    };
+    int ja, jb;
+    fc_centre_range(a, d, m, (long long)t_lo * T, ((long long)t_hi + 1) * T, ja, jb);
+    for (int j0 = ja; j0 < jb; j0 += 32) {
+        const int j = j0 + lane;
+        int hs = -1, tile = 0;
+        double An = 0.0, u1r = 0.0, u2r = 0.0, ui = 0.0;
+        if (j < jb) {
+            const int l = list_d[j];
+            const PairWin pw = load_win(a.win + drow + l);
+            tile = pw.cpix >> shift;
+            hs = pw.sat ? 31 - __clz((unsigned)pw.sat) : -1;
+            if (hs >= m) {
                 const double2 *rp = reinterpret_cast<const double2 *>(a.rec + drow + l);
                 const double2 r0 = __ldg(rp), r1 = __ldg(rp + 1);   // nu, dw, y, K
+                const double c_s = gm[3 * tile], sc = gm[3 * tile + 2];
+                const double inv_sc = sc > 0.0 ? 1.0 / sc : 0.0;
                 const double g = r1.x * r0.y, adw = 0.7071067811865476 * r0.y;
                 An = r1.y * r0.y * (0.5 * sdm::INV_SQRT_PI);
                 const double dc = r0.x - c_s;
                 u1r = (dc + adw) * inv_sc; u2r = (dc - adw) * inv_sc; ui = g * inv_sc;
-                if (count_stats) { n_pix += (unsigned long long)il_pix; n_exp++; }
-            }
-            const double a1 = u1r + u1r, b1 = fma(u1r, u1r, ui * ui), a2 = u2r + u2r, b2 = fma(u2r, u2r, ui * ui);
-            double s1 = ui, s1p = 0.0, s2 = ui, s2p = 0.0;   // Im(u^1), Im(u^0)
-#pragma unroll
-            for (int k = 0; k < K1; k++) {
-                C[k] = fma(An, s1 + s2, C[k]);
-                if (k + 1 < K1) {
-                    double t;
-                    t = fma(a1, s1, -(b1 * s1p)); s1p = s1; s1 = t;
-                    t = fma(a2, s2, -(b2 * s2p)); s2p = s2; s2 = t;
+                if (count_stats) {
+                    for (int lv = m; lv <= hs; lv++) n_pix += (unsigned long long)il_pixels(a, lv, pw.cpix >> a.fg.tile_shift[lv]);
+                    n_exp += (unsigned long long)(hs - m + 1);
                 }
             }
         }
-    }
-    double mine = 0.0;
+        b_tile[lane] = tile;
+        b_hs[lane] = hs;
+        const double a1 = u1r + u1r, b1 = fma(u1r, u1r, ui * ui), a2 = u2r + u2r, b2 = fma(u2r, u2r, ui * ui);
+        double s1 = ui, s1p = 0.0, s2 = ui, s2p = 0.0;   // Im(u^1), Im(u^0)
 #pragma unroll
-    for (int k = 0; k < K1; k++) {
-        double v = C[k];
-        for (int o2 = 16; o2; o2 >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o2);
-        if (lane == k) mine = v;
+        for (int k = 0; k < K1; k++) {
+            buf[k][lane] = An * (s1 + s2);
+            if (k + 1 < K1) {
+                double t;
+                t = fma(a1, s1, -(b1 * s1p)); s1p = s1; s1 = t;
+                t = fma(a2, s2, -(b2 * s2p)); s2p = s2; s2 = t;
+            }
+        }
+        __syncwarp();
+        const int nin = min(32, jb - j0);
+        for (int i = 0; i < nin; i++) {
+            const int h = b_hs[i] - m;   // warp-uniform
+            if (h < 0) continue;
+            const int ti = b_tile[i];
+            if (ti != cur) {
+                close_down_to(ti);
+                cur = ti;
+            }
+            const double v = buf[lane][i];
+            if (h == 0) acc0 += v;
+            else if (h == 1) acc1 += v;
+            else if (h == 2) acc2 += v;
+            else acc3 += v;
+        }
+        __syncwarp();
     }
-    const size_t tl = (size_t)d * a.n_src[lev] + (s - a.src_tile0[lev]);
-    if (nsplit > 1) part[(tl * nsplit + split) * K1 + lane] = mine;
-    else a.far_mom[lev][tl * K1 + lane] = mine;
+    close_down_to(t_lo - 1);
     if (count_stats) {
         for (int o2 = 16; o2; o2 >>= 1) {
             n_pix += __shfl_xor_sync(0xffffffffu, n_pix, o2);
@@ -590,8 +647,85 @@ __global__ void __launch_bounds__(THREADS) k_s2m(LineArgs a, int lev, int count_
         }
         if (lane == 0 && n_exp) {
             atomicAdd(&a.stats[8], n_pix);   // evaluations the multipole path replaces
-            atomicAdd(&a.stats[12], n_exp);  // executed multipole expansions (pair, level)
+            atomicAdd(&a.stats[12], n_exp);  // (pair, level) products served by multipole moments
         }
+    }
+}
+
+// k_m2m(lev): one warp per (level-`lev` parent tile P, depth), lane k = moment k.  For each child s of P at level lev - 1:
+//   * far_mom[lev-1][s] = sum_{h >= lev-1} far_bkt[lev-1][h][s]  (what k_m2l uses at the children's level);
+//   * far_bkt[lev][h][P] += translate(far_bkt[lev-1][h][s]) for h >= lev:
+//       M'_k = sum_{j=1..k} C(k, j) r^j delta^(k-j) M_j,   r = scale_s / scale_P,  delta = (c_s - c_P) / scale_P
+//     (children in index order; the parent's own pairs with lmin = lev were written by k_s2m(lev) before).
+// lev == n_act: only the first step, for the top level.
+__constant__ double M2M_INV[K1 + 2];  // 1 / j
+
+__global__ void __launch_bounds__(128) k_m2m(LineArgs a, int lev) {
+    __shared__ double s_m[4][3][K1 + 1];   // child moments M_1..M_K1 of up to three buckets (index j; [0] unused = 0)
+    __shared__ double s_dp[4][K1 + 1];     // delta^i, i = 0..K1
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int d = blockIdx.y;
+    const int cl = lev - 1;                          // children's level
+    const int ntc = a.fg.n_tiles[cl];
+    const int P = (int)blockIdx.x * 4 + warp;
+    if ((P << SD_FAR_SHIFT) >= ntc) return;
+    const bool translate = lev < a.n_act;
+    const int ntp = translate ? a.fg.n_tiles[lev] : 0;
+    const int nh = a.n_act - lev;                    // buckets h = lev .. n_act - 1 go up (<= 3)
+    const int kk = lane + 1;                         // this lane's moment index (power)
+    double up0 = 0.0, up1 = 0.0, up2 = 0.0;
+    double c_P = 0.0, inv_sP = 0.0;
+    if (translate) {
+        c_P = a.fg.geom[lev][3 * P];
+        const double sP = a.fg.geom[lev][3 * P + 2];
+        inv_sP = sP > 0.0 ? 1.0 / sP : 0.0;
+    }
+    double (*mm)[K1 + 1] = s_m[warp];
+    double *dp = s_dp[warp];
+    for (int c = 0; c < (1 << SD_FAR_SHIFT); c++) {
+        const int s = (P << SD_FAR_SHIFT) + c;
+        if (s >= ntc) break;
+        const size_t o = ((size_t)d * ntc + s) * K1 + lane;
+        double tot = a.far_bkt[cl][cl][o];
+        double b0 = 0.0, b1 = 0.0, b2 = 0.0;
+        if (nh > 0) { b0 = a.far_bkt[cl][lev][o]; tot += b0; }
+        if (nh > 1) { b1 = a.far_bkt[cl][lev + 1][o]; tot += b1; }
+        if (nh > 2) { b2 = a.far_bkt[cl][lev + 2][o]; tot += b2; }
+        a.far_mom[cl][o] = tot;
+        if (!translate) continue;
+        const unsigned any = __ballot_sync(0xffffffffu, b0 != 0.0 || b1 != 0.0 || b2 != 0.0);
+        if (any == 0) continue;
+        const double r = a.fg.geom[cl][3 * s + 2] * inv_sP, delta = (a.fg.geom[cl][3 * s] - c_P) * inv_sP;
+        __syncwarp();
+        mm[0][kk] = b0; mm[1][kk] = b1; mm[2][kk] = b2;
+        {   // delta^i by binary powering: lane i -> delta^i (i = 0..31), lane 0 also writes delta^32
+            double pw = 1.0, base = delta;
+#pragma unroll
+            for (int bit = 0; bit < 5; bit++) {
+                if ((lane >> bit) & 1) pw *= base;
+                base *= base;
+            }
+            dp[lane] = pw;
+            if (lane == 0) dp[K1] = base;   // delta^32 after five squarings
+        }
+        __syncwarp();
+        // row kk: coefficient of M_j is C(kk, j) r^j delta^(kk - j); walk j upwards with the running C(kk, j) r^j
+        double cf = (double)kk * r;   // j = 1
+        for (int j = 1; j <= K1; j++) {
+            if (j <= kk) {
+                const double w = cf * dp[kk - j];
+                up0 = fma(w, mm[0][j], up0);
+                up1 = fma(w, mm[1][j], up1);
+                up2 = fma(w, mm[2][j], up2);
+                cf *= r * (double)(kk - j) * M2M_INV[j + 1];
+            }
+        }
+    }
+    if (translate && P < ntp) {
+        const size_t o = ((size_t)d * ntp + P) * K1 + lane;
+        if (nh > 0) a.far_bkt[lev][lev][o] += up0;
+        if (nh > 1) a.far_bkt[lev][lev + 1][o] += up1;
+        if (nh > 2) a.far_bkt[lev][lev + 2][o] += up2;
     }
 }
 
@@ -623,24 +757,30 @@ __global__ void __launch_bounds__(THREADS) k_m2l(LineArgs a, int lev, int count_
     const double *__restrict__ gm = a.fg.geom[lev];
     const double c_t = gm[3 * (tile_ok ? t : 0)], h_t = gm[3 * (tile_ok ? t : 0) + 1];
     const double *__restrict__ mom = a.far_mom[lev];
-    const int src0 = a.src_tile0[lev], nsrc = a.n_src[lev];
-    auto stage = [&](int buf, int s) {
+    const int src0 = 0, nsrc = nt;
+    auto stage = [&](int buf, int s) {  // returns whether this thread staged a non-zero moment
+        int nz = 0;
         for (int i = tid; i < M2L_DC * K1; i += THREADS) {
             const int dd = i / K1, k = i - dd * K1;
-            s_M[buf][k][dd] = (dd < nd) ? mom[((size_t)(d0 + dd) * nsrc + (s - src0)) * K1 + k] : 0.0;
+            const double v = (dd < nd) ? mom[((size_t)(d0 + dd) * nsrc + (s - src0)) * K1 + k] : 0.0;
+            s_M[buf][k][dd] = v;
+            nz |= (v != 0.0);
         }
+        return nz;
     };
     double acc[M2L_DC];
 #pragma unroll
     for (int dd = 0; dd < M2L_DC; dd++) acc[dd] = 0.0;
     unsigned long long n_m2l = 0;
-    if (s_lo < s_hi) stage(0, s_lo);
-    __syncthreads();
+    int nz0 = 0;
+    if (s_lo < s_hi) nz0 = stage(0, s_lo);
+    int nz_cur = __syncthreads_or(nz0);   // source tiles without saturated pairs (all moments zero) are skipped
     for (int s = s_lo; s < s_hi; s++) {
         const int buf = (s - s_lo) & 1;
-        if (s + 1 < s_hi) stage(buf ^ 1, s + 1);
+        int nz_next = 0;
+        if (s + 1 < s_hi) nz_next = stage(buf ^ 1, s + 1);
         const int ds = s - t;
-        if (tile_ok && (ds >= 2 || ds <= -2)) {
+        if (nz_cur && tile_ok && (ds >= 2 || ds <= -2)) {
             const double c_s = gm[3 * s], sc = gm[3 * s + 2];
             const double dd_ = c_t - c_s, inv_d = 1.0 / dd_;
             const double aa = sc * inv_d, bb = -h_t * inv_d;
@@ -668,7 +808,7 @@ __global__ void __launch_bounds__(THREADS) k_m2l(LineArgs a, int lev, int count_
             }
             if (count_stats) n_m2l += (unsigned long long)nd * kmax;
         }
-        __syncthreads();
+        nz_cur = __syncthreads_or(nz_next);
     }
     if (tile_ok) {
 #pragma unroll
@@ -1138,46 +1278,52 @@ int sd_k2_lines(sd_ctx *c, int slot) {
             a.far_ntl[k] = (int)((c->p1 + tk - 1) / tk) - a.far_tile0[k];
             SD_TRY(sd_ensure(c, c->far_coef[k], sizeof(double) * c->D * a.far_ntl[k] * K1));
             a.far_coef[k] = c->far_coef[k].as<double>();
-            // source tiles whose moments the targets of this launch need: the children of the parents of the targets
-            // and of their two neighbours (every tile at the top level)
-            if (k == n_act - 1) {
-                a.src_tile0[k] = 0;
-                a.n_src[k] = a.fg.n_tiles[k];
-            } else {
-                const int P0 = a.far_tile0[k] >> SD_FAR_SHIFT, P1 = (a.far_tile0[k] + a.far_ntl[k] - 1) >> SD_FAR_SHIFT;
-                const int s0 = (P0 - 1 > 0 ? P0 - 1 : 0) << SD_FAR_SHIFT;
-                int s1 = (P1 + 2) << SD_FAR_SHIFT;
-                if (s1 > a.fg.n_tiles[k]) s1 = a.fg.n_tiles[k];
-                a.src_tile0[k] = s0;
-                a.n_src[k] = s1 - s0;
-            }
-            SD_TRY(sd_ensure(c, c->far_mom[k], sizeof(double) * c->D * a.n_src[k] * K1));
+            // multipole moments: every tile of every level (the top level reaches the whole grid)
+            SD_TRY(sd_ensure(c, c->far_mom[k], sizeof(double) * c->D * a.fg.n_tiles[k] * K1));
             a.far_mom[k] = c->far_mom[k].as<double>();
+            for (int h = k; h < n_act; h++) {
+                SD_TRY(sd_ensure(c, c->far_bkt[k][h], sizeof(double) * c->D * a.fg.n_tiles[k] * K1));
+                a.far_bkt[k][h] = c->far_bkt[k][h].as<double>();
+            }
         }
         if (!c->far_attr_set) {  // per device: > 48 KB of dynamic shared memory needs the opt-in; series-length table
             SD_CUDA(c, cudaFuncSetAttribute(k_far_coeffs, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FAR_SMEM));
             unsigned char tab[256];
             far_terms_table(tab);
             SD_CUDA(c, cudaMemcpyToSymbolAsync(FAR_TERMS, tab, sizeof tab, 0, cudaMemcpyHostToDevice, c->stream));
-            SD_CUDA(c, cudaStreamSynchronize(c->stream));  // `tab` lives on this stack frame
+            double inv[K1 + 2];
+            inv[0] = 0.0;
+            for (int j = 1; j < K1 + 2; j++) inv[j] = 1.0 / (double)j;
+            SD_CUDA(c, cudaMemcpyToSymbolAsync(M2M_INV, inv, sizeof inv, 0, cudaMemcpyHostToDevice, c->stream));
+            SD_CUDA(c, cudaStreamSynchronize(c->stream));  // `tab` and `inv` live on this stack frame
             c->far_attr_set = true;
         }
         // CTAs per (group of eight sibling tiles, depth) of the direct expansion: the candidate lists are cut into this
         // many fixed slices so that even a narrow shard fills the chip; k_far_reduce adds the partial sums in slice order.
         size_t part_bytes = 0;
         for (int k = 0; k < n_act; k++) {
-            const int ns = far_nsplit(k, k == n_act - 1), nm = s2m_nsplit(k, k == n_act - 1);
-            const size_t b = ns > 1 ? sizeof(double) * c->D * a.far_ntl[k] * ns * K1 : 0;
-            const size_t bm = nm > 1 ? sizeof(double) * c->D * a.n_src[k] * nm * K1 : 0;
-            part_bytes = b > part_bytes ? b : part_bytes;
-            part_bytes = bm > part_bytes ? bm : part_bytes;
+            const int ns = far_nsplit(k, k == n_act - 1);
+            const size_t bb = ns > 1 ? sizeof(double) * c->D * a.far_ntl[k] * ns * K1 : 0;
+            part_bytes = bb > part_bytes ? bb : part_bytes;
         }
         SD_TRY(sd_ensure(c, c->far_part, part_bytes > 0 ? part_bytes : 8));
         sd_phase_begin(c, SD_PH_FAR);
         const int cs = c->line_stats ? 1 : 0;
+        // multipole moments: one expansion per saturated pair at its level lmin, then upwards tile to tile
+        for (int m = 0; m < n_act; m++) {
+            const int runs = (a.fg.n_tiles[m] + (1 << SD_FAR_SHIFT) - 1) >> SD_FAR_SHIFT;
+            k_s2m<<<dim3((unsigned)((runs + S2M_WARPS - 1) / S2M_WARPS), (unsigned)c->D), 32 * S2M_WARPS, 0, c->stream>>>(a, m, cs);
+            SD_TRY(sd_launch_check(c, "k_s2m"));
+        }
+        for (int lev = 1; lev <= n_act; lev++) {
+            const int parents = (a.fg.n_tiles[lev - 1] + (1 << SD_FAR_SHIFT) - 1) >> SD_FAR_SHIFT;
+            k_m2m<<<dim3((unsigned)((parents + 3) / 4), (unsigned)c->D), 128, 0, c->stream>>>(a, lev);
+            SD_TRY(sd_launch_check(c, "k_m2m"));
+        }
         for (int k = n_act - 1; k >= 0; k--) {
             const int nsplit = far_nsplit(k, k == n_act - 1);
-            // one CTA per group of eight sibling tiles that has a member in the launched range (times the slices)
+            // direct expansions: one CTA per group of eight sibling tiles that has a member in the launched range (times
+            // the slices of the candidate lists; k_far_reduce adds the partial sums in slice order)
             const int n_grp = ((a.far_tile0[k] + a.far_ntl[k] - 1) >> SD_FAR_SHIFT) - (a.far_tile0[k] >> SD_FAR_SHIFT) + 1;
             k_far_coeffs<<<dim3((unsigned)(n_grp * nsplit), (unsigned)c->D), THREADS, FAR_SMEM, c->stream>>>(
                 a, k, cs, nsplit, c->far_part.as<double>());
@@ -1185,15 +1331,6 @@ int sd_k2_lines(sd_ctx *c, int slot) {
             if (nsplit > 1) {
                 const int n = c->D * a.far_ntl[k] * K1;
                 k_far_reduce<<<(n + 255) / 256, 256, 0, c->stream>>>(n, nsplit, c->far_part.as<double>(), a.far_coef[k]);
-                SD_TRY(sd_launch_check(c, "k_far_reduce"));
-            }
-            const int nm = s2m_nsplit(k, k == n_act - 1);
-            k_s2m<<<dim3((unsigned)(((a.n_src[k] + WARPS - 1) / WARPS) * nm), (unsigned)c->D), THREADS, 0, c->stream>>>(
-                a, k, cs, nm, c->far_part.as<double>());
-            SD_TRY(sd_launch_check(c, "k_s2m"));
-            if (nm > 1) {
-                const int n = c->D * a.n_src[k] * K1;
-                k_far_reduce<<<(n + 255) / 256, 256, 0, c->stream>>>(n, nm, c->far_part.as<double>(), a.far_mom[k]);
                 SD_TRY(sd_launch_check(c, "k_far_reduce"));
             }
             k_m2l<<<dim3((unsigned)n_grp, (unsigned)((c->D + M2L_DC - 1) / M2L_DC)), THREADS, 0, c->stream>>>(a, k, cs);

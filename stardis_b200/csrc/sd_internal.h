@@ -158,7 +158,8 @@ struct sd_ctx {
     unsigned long long *h_edge_count = nullptr;  // pinned host copy of the edge counter
     DevBuf tile_geom[SD_FAR_LEVELS];   // double [3 * n_tiles]: centre frequency, half-width, moment scale of every global tile
     DevBuf far_coef[SD_FAR_LEVELS];    // double [D * n_tiles_shard * (SD_FAR_K + 1)]
-    DevBuf far_mom[SD_FAR_LEVELS];     // double [D * n_src_tiles * (SD_FAR_K + 1)]: multipole moments of the saturated pairs
+    DevBuf far_mom[SD_FAR_LEVELS];     // double [D * n_tiles * (SD_FAR_K + 1)]: multipole moments of the saturated pairs
+    DevBuf far_bkt[SD_FAR_LEVELS][SD_FAR_LEVELS];  // [level][highest saturated level]: moment buckets, see k_s2m / k_m2m
     DevBuf far_part;                   // partial coefficient sets (slices of the pair list per tile)
     FarGeom far_geom{};
     int k2_P = 4;      // pixels per thread chosen for the current grid
