@@ -711,13 +711,15 @@ __global__ void __launch_bounds__(128) k_m2m(LineArgs a, int lev) {
         __syncwarp();
         // row kk: coefficient of M_j is C(kk, j) r^j delta^(kk - j); walk j upwards with the running C(kk, j) r^j
         double cf = (double)kk * r;   // j = 1
+        double rem = (double)(kk - 1);   // kk - j as a double (integer-to-double conversions are slow)
         for (int j = 1; j <= K1; j++) {
             if (j <= kk) {
                 const double w = cf * dp[kk - j];
                 up0 = fma(w, mm[0][j], up0);
                 up1 = fma(w, mm[1][j], up1);
                 up2 = fma(w, mm[2][j], up2);
-                cf *= r * (double)(kk - j) * M2M_INV[j + 1];
+                cf *= (r * M2M_INV[j + 1]) * rem;
+                rem -= 1.0;
             }
         }
     }
@@ -758,13 +760,26 @@ __global__ void __launch_bounds__(THREADS) k_m2l(LineArgs a, int lev, int count_
     const double c_t = gm[3 * (tile_ok ? t : 0)], h_t = gm[3 * (tile_ok ? t : 0) + 1];
     const double *__restrict__ mom = a.far_mom[lev];
     const int src0 = 0, nsrc = nt;
-    auto stage = [&](int buf, int s) {  // returns whether this thread staged a non-zero moment
-        int nz = 0;
-        for (int i = tid; i < M2L_DC * K1; i += THREADS) {
+    // staging of a source tile's moments in two steps, so that the global loads of the NEXT tile are in flight while
+    // the current one is multiplied: fetch() issues the loads into registers, commit() writes them to shared memory
+    constexpr int NST = (M2L_DC * K1 + THREADS - 1) / THREADS;
+    double pre[NST];
+    auto fetch = [&](int s) {
+#pragma unroll
+        for (int r = 0; r < NST; r++) {
+            const int i = tid + r * THREADS;
             const int dd = i / K1, k = i - dd * K1;
-            const double v = (dd < nd) ? mom[((size_t)(d0 + dd) * nsrc + (s - src0)) * K1 + k] : 0.0;
-            s_M[buf][k][dd] = v;
-            nz |= (v != 0.0);
+            pre[r] = (i < M2L_DC * K1 && dd < nd) ? __ldg(mom + ((size_t)(d0 + dd) * nsrc + (s - src0)) * K1 + k) : 0.0;
+        }
+    };
+    auto commit = [&](int buf) {  // returns whether this thread staged a non-zero moment
+        int nz = 0;
+#pragma unroll
+        for (int r = 0; r < NST; r++) {
+            const int i = tid + r * THREADS;
+            const int dd = i / K1, k = i - dd * K1;
+            if (i < M2L_DC * K1) s_M[buf][k][dd] = pre[r];
+            nz |= (pre[r] != 0.0);
         }
         return nz;
     };
@@ -773,12 +788,11 @@ __global__ void __launch_bounds__(THREADS) k_m2l(LineArgs a, int lev, int count_
     for (int dd = 0; dd < M2L_DC; dd++) acc[dd] = 0.0;
     unsigned long long n_m2l = 0;
     int nz0 = 0;
-    if (s_lo < s_hi) nz0 = stage(0, s_lo);
+    if (s_lo < s_hi) { fetch(s_lo); nz0 = commit(0); }
     int nz_cur = __syncthreads_or(nz0);   // source tiles without saturated pairs (all moments zero) are skipped
     for (int s = s_lo; s < s_hi; s++) {
         const int buf = (s - s_lo) & 1;
-        int nz_next = 0;
-        if (s + 1 < s_hi) nz_next = stage(buf ^ 1, s + 1);
+        if (s + 1 < s_hi) fetch(s + 1);
         const int ds = s - t;
         if (nz_cur && tile_ok && (ds >= 2 || ds <= -2)) {
             const double c_s = gm[3 * s], sc = gm[3 * s + 2];
@@ -808,6 +822,8 @@ __global__ void __launch_bounds__(THREADS) k_m2l(LineArgs a, int lev, int count_
             }
             if (count_stats) n_m2l += (unsigned long long)nd * kmax;
         }
+        int nz_next = 0;
+        if (s + 1 < s_hi) nz_next = commit(buf ^ 1);
         nz_cur = __syncthreads_or(nz_next);
     }
     if (tile_ok) {
