@@ -54,7 +54,7 @@ static_assert(K1 % 4 == 0, "the series length is tested every fourth term");
 static_assert(WARPS == (1 << SD_FAR_SHIFT), "k_far_coeffs / k_s2m / k_m2l map the warps of a CTA to the children of a tile");
 constexpr size_t FAR_SMEM = (size_t)FAR_CH * sizeof(FarRec) + FAR_CH;
 constexpr int FAR_MAX_SRC = 3 * SD_FAR_LEVELS;  // candidate lists of one k_far_coeffs group
-constexpr int M2L_DC = 14;                  // depth points per k_m2l CTA (accumulators per thread)
+constexpr int M2L_DC_MAX = 14;              // depth points per k_m2l CTA (accumulators per thread); 8 when few depths are local
 
 struct __align__(16) WEntry {
     // far-wing path (48 B)
@@ -739,6 +739,7 @@ __global__ void __launch_bounds__(128) k_m2m(LineArgs a, int lev) {
 // matrix row on the fly (ratio table in shared memory) and multiplies it with the moments of the chunk's depth points,
 // staged in shared memory (every lane reads the same moment: broadcast).  The k-sum stops where the multipole series
 // has converged for this tile distance (same rule as the direct expansion).  Fixed source order: shard-invariant.
+template <int M2L_DC>
 __global__ void __launch_bounds__(THREADS) k_m2l(LineArgs a, int lev, int count_stats) {
     __shared__ double s_R[K1][K1];                           // s_R[k][n] = (n + k + 2) / (k + 2)
     __shared__ __align__(16) double s_M[2][K1][M2L_DC + 2];   // moments of the staged source tile, [k][depth]
@@ -1349,7 +1350,10 @@ int sd_k2_lines(sd_ctx *c, int slot) {
                 k_far_reduce<<<(n + 255) / 256, 256, 0, c->stream>>>(n, nsplit, c->far_part.as<double>(), a.far_coef[k]);
                 SD_TRY(sd_launch_check(c, "k_far_reduce"));
             }
-            k_m2l<<<dim3((unsigned)n_grp, (unsigned)((c->D + M2L_DC - 1) / M2L_DC)), THREADS, 0, c->stream>>>(a, k, cs);
+            // depth chunks of 14, or of 8 when that wastes fewer accumulator slots (a depth-sharded rank holds D / R depths)
+            const int w14 = ((c->D + 13) / 14) * 14 - c->D, w8 = ((c->D + 7) / 8) * 8 - c->D;
+            if (w8 < w14) k_m2l<8><<<dim3((unsigned)n_grp, (unsigned)((c->D + 7) / 8)), THREADS, 0, c->stream>>>(a, k, cs);
+            else k_m2l<M2L_DC_MAX><<<dim3((unsigned)n_grp, (unsigned)((c->D + 13) / 14)), THREADS, 0, c->stream>>>(a, k, cs);
             SD_TRY(sd_launch_check(c, "k_m2l"));
         }
         sd_phase_end(c, SD_PH_FAR);

@@ -106,3 +106,43 @@ def test_far_field_with_degenerate_line_parameters(ctx, oracle):
         ok = np.isfinite(ref)
         np.testing.assert_allclose(out[ok], ref[ok], rtol=1e-10, atol=0)
         assert st["evals"] == evals
+
+
+@pytest.mark.parametrize("kind", ["jump", "log", "jitter"])
+def test_far_field_on_non_uniform_grids(ctx, oracle, kind):
+    """The far criterion is an index distance, valid only where the tile widths vary smoothly: a grid with a jump in its
+    step must lose the affected hierarchy levels (k_level_check) and still agree with the oracle; a logarithmic grid
+    (smooth, strongly non-uniform) and a jittered one keep working through the per-pair convergence tests."""
+    rng = np.random.default_rng(17)
+    N, Ln, D = 50000, 600, 2
+    if kind == "jump":      # 0.01 A steps, then 0.06 A steps: tile widths jump by a factor 6 in the middle of the grid
+        lam = 4000.0 + np.concatenate([0.01 * np.arange(N // 2), 0.01 * (N // 2) + 0.06 * np.arange(1, N - N // 2 + 1)])
+    elif kind == "log":     # constant resolving power: the step grows by a factor 2.7 along the grid
+        lam = 3000.0 * np.exp(np.arange(N) * 2.0e-5)
+    else:                   # 30 % jitter of every step
+        lam = 4000.0 + np.cumsum(0.01 * rng.uniform(0.7, 1.3, N))
+    nus = C_A / lam
+    assert (np.diff(nus) < 0).all()
+    line_nus = np.sort(rng.uniform(nus.min(), nus.max(), Ln))
+    dws = rng.uniform(1.5e9, 5e9, (Ln, D))
+    gam = 10.0 ** rng.uniform(6.5, 10.0, (Ln, D))
+    target_hw = 10.0 ** rng.uniform(1.0, 6.5, (Ln, D))
+    al = target_hw * oracle.d_nu(nus) / 20.0 / (gam + dws)
+    ref, evals, hist = oracle.calc_alan_entries(D, nus, line_nus, dws, gam, al, with_stats=True)
+    far, st = _run(ctx, nus, line_nus, dws, gam, al, True, stats=True)
+    assert st["evals"] == evals and np.array_equal(st["region_evals"], hist)
+    np.testing.assert_allclose(far, ref, rtol=1e-10, atol=0)
+    direct, _ = _run(ctx, nus, line_nus, dws, gam, al, False)
+    np.testing.assert_allclose(far, direct, rtol=2e-11, atol=0)
+    assert np.array_equal(far == 0, ref == 0)
+    p0, p1 = N // 3 + 5, (2 * N) // 3 - 7
+    part, _ = _run(ctx, nus, line_nus, dws, gam, al, True, shard=(p0, p1))
+    assert np.array_equal(part, far[:, p0:p1])
+    if kind != "jump":  # the far field really is in use on the smooth grids: most evaluations are not done pixel by pixel
+        ctx.set_grid(nus)
+        ctx.set_line_stats(True)
+        ctx.calc_alpha_line(0)
+        ex = ctx.line_stats_ex()
+        ctx.set_line_stats(False)
+        assert ex["far_replaced_evals"] > 0.5 * evals
+        assert ex["multipole_expansions"] > 0 and ex["m2l_row_steps"] > 0
