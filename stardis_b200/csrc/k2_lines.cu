@@ -10,7 +10,8 @@
 //     registers for the whole kernel; the result is written exactly once, coalesced;
 //   * the (line, depth) pairs that can touch the tile are found per half-width class (class 0: contiguous range of
 //     the nu-sorted line list; class k >= 1: contiguous range of the per-depth class list built by k1_broadening.cu;
-//     32-ary warp binary searches on the monotone window centres);
+//     32-ary warp binary searches on the monotone window centres) and, for the far-capable classes, from range
+//     tables per 64-pixel tile boundary (two loads);
 //   * k_lines: every WARP streams the candidates in batches of 32 on its own (no CTA barrier in the main loop): test
 //     against the warp's 32*P-pixel span, expand the passing (line, depth) records into 96-byte shared-memory entries
 //     (constants hoisted once per warp), entries whose window covers the span and whose span lies entirely in
@@ -19,17 +20,17 @@
 //   * far-wing hot loop (region I):  Kf (q + c1) / (q (q + b) + c),  q = x^2:  8 FP64 instructions + 1 MUFU.RCP64H
 //     per evaluation (x, q, 2 for the denominator, numerator, 2 for the Newton step on the reciprocal seed,
 //     accumulate), no branches, no divisions;
-//   * pixels that are not certainly in region I take the exact path: x = dnu / dw (IEEE division) and the
+//   * pixels that are not certainly in region I take the exact path: x = dnu / dw (correctly rounded) and the
 //     reference's own region tests, so the Humlicek classification is identical to the reference's;
-//   * FAR FIELD (k_far_coeffs + polynomial epilogue of k_lines): a pair whose window covers the whole tile and whose
-//     line centre is at least 4 tile half-widths away contributes a function that is analytic over the tile.  In
-//     region I,  Re w = (1/(2 sqrt(pi))) [ y/((x-a)^2+y^2) + y/((x+a)^2+y^2) ],  a = 1/sqrt(2): two Lorentzians, i.e.
-//     the imaginary part of two simple poles p = nu_l -+ dw/sqrt(2) + i y dw.  Their Taylor series about the tile
-//     centre nu_c,  1/(nu - p) = sum_k (-1)^k (nu - nu_c)^k / (nu_c - p)^(k+1),  converges with ratio <= 1/4; degree
-//     20 reproduces the direct evaluation to <= 6e-12 (relative, worst case; all terms are positive).
-//     k_far_coeffs accumulates the 21 coefficients of ALL far pairs of a tile (one pair per thread, ~230 FP64
-//     operations instead of 8 per pixel), k_lines skips exactly those pairs (same integer test on the per-pair
-//     "near tile interval" computed by k_build_records) and adds the polynomial at the end.
+//   * FAR FIELD (k_s2m, k_m2m, k_m2l, k_far_coeffs + polynomial epilogue of k_lines): in region I,
+//     Re w = (1/(2 sqrt(pi))) [ y/((x-a)^2+y^2) + y/((x+a)^2+y^2) ],  a = 1/sqrt(2): two Lorentzians, i.e. the
+//     imaginary part of two simple poles p = nu_l -+ dw/sqrt(2) + i y dw with a real weight.  On a hierarchy of pixel
+//     tiles (64 * 8^k pixels) a pair whose window covers a tile at least two tiles away from its centre contributes a
+//     function that is analytic over that tile: the degree-31 Taylor polynomials of all such pairs of a tile are
+//     summed once -- through multipole moments of the source tiles and real tile-to-tile translation matrices (a 1-D
+//     fast multipole method) for pairs whose window covers the whole neighbourhood, by direct expansion otherwise --
+//     k_lines skips exactly those (pair, 64-pixel tile) products (same integer test on the 16-byte window record)
+//     and adds the polynomials at the end.  See sd_internal.h and the kernels below.
 //
 // Roofline: FP64 FMA pipe (no dense contraction -> no tensor cores).  Memory traffic is negligible.
 #include <stdlib.h>
