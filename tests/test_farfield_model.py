@@ -149,3 +149,41 @@ def test_multipole_translation_matches_region_one_profile():
     assert used > 1500
     assert worst < 2e-11, worst
     assert shortest <= 16   # distant source tiles need far fewer moments
+
+
+def _translate_up(m, c_s, scale_s, c_p, scale_p):
+    """k_m2m: moments about (c_s, scale_s) -> moments about the parent's (c_p, scale_p):
+    M'_k = sum_{j=1..k} C(k, j) r^j delta^(k-j) M_j,  r = scale_s / scale_p,  delta = (c_s - c_p) / scale_p,
+    with the kernel's running coefficient C(k, j) r^j."""
+    r, delta = scale_s / scale_p, (c_s - c_p) / scale_p
+    dp = delta ** np.arange(K1 + 1)
+    out = np.zeros(K1)
+    for kk in range(1, K1 + 1):
+        cf, rem, acc = kk * r, float(kk - 1), 0.0
+        for j in range(1, kk + 1):
+            acc += cf * dp[kk - j] * m[j - 1]
+            cf *= (r * (1.0 / (j + 1))) * rem
+            rem -= 1.0
+        out[kk - 1] = acc
+    return out
+
+
+def test_moment_translation_to_the_parent_tile_is_exact():
+    """Moments of a child tile translated to its parent equal the moments taken about the parent directly (a finite
+    binomial sum: no truncation, only rounding), for every child position of a branching-8 hierarchy."""
+    rng = np.random.default_rng(5)
+    worst = 0.0
+    for _ in range(400):
+        h_p = 10.0 ** rng.uniform(10.0, 12.5)
+        c_p = 6.0e14
+        child = rng.integers(0, 8)
+        h_s = h_p / 8.0 * rng.uniform(0.95, 1.05)                  # smooth non-uniform grid
+        c_s = c_p + h_p * (-1.0 + (2 * child + 1) / 8.0)
+        dw = rng.uniform(0.0, 0.1) * h_s + 1.0
+        y = rng.uniform(0.0, 0.1) * h_s / dw
+        nu_l = c_s + rng.uniform(-1.0, 1.0) * h_s
+        direct = _moments(nu_l, dw, y, 1.0, c_p, h_p)
+        up = _translate_up(_moments(nu_l, dw, y, 1.0, c_s, h_s), c_s, h_s, c_p, h_p)
+        scale = np.max(np.abs(direct))
+        worst = max(worst, np.max(np.abs(up - direct)) / scale)
+    assert worst < 1e-13, worst
