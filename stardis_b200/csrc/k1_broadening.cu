@@ -255,8 +255,10 @@ __device__ __forceinline__ bool level_ok(const FarGeom &fg, int k, int64_t N, co
     return ok;
 }
 
-// One thread per (line, depth), d fastest (coalesced reads of the (L,D) inputs).  Writes depth-major
-// records/windows (64-byte records are two full sectors, so the transposing write is not wasteful).
+// One thread per (line, depth).  A block takes a tile of 32 lines x 8 depth points: the (L,D) inputs are read as 64-byte
+// segments (8 depths of a line), the depth-major outputs are staged in shared memory and written as contiguous rows --
+// 32 records = 2 KB, 32 window records = 512 B, 32 classes per depth point (one thread per pair with the depth fastest
+// wrote 64-byte records 19 MB apart and half-sector window records).
 __global__ void __launch_bounds__(256) k_build_records(int64_t L, int D, int64_t N, const double *__restrict__ nus,
                                                        const double *__restrict__ line_nu,
                                                        const int *__restrict__ line_idx, const double *__restrict__ gammas,
@@ -265,14 +267,22 @@ __global__ void __launch_bounds__(256) k_build_records(int64_t L, int D, int64_t
                                                        LineRec *__restrict__ rec, PairWin *__restrict__ win,
                                                        uint8_t *__restrict__ win_cls,
                                                        FarGeom fg, unsigned long long *__restrict__ stats) {
-    const unsigned g = blockIdx.x * blockDim.x + threadIdx.x;  // L * D < 2^31 (checked by sd_set_lines)
-    bool active = g < (unsigned)(L * D);
+    constexpr int TL = 32, TD = 8;                       // tile: lines x depth points (TL * TD = blockDim.x)
+    __shared__ __align__(16) LineRec s_rec[TD][TL];
+    __shared__ __align__(16) PairWin s_win[TD][TL];
+    __shared__ uint8_t s_wcls[TD][TL];
+    const int n_dt = (D + TD - 1) / TD;
+    const unsigned l0 = (blockIdx.x / (unsigned)n_dt) * TL;
+    const int d0 = (int)(blockIdx.x % (unsigned)n_dt) * TD;
+    const int tl = threadIdx.x / TD, td = threadIdx.x % TD;
+    const unsigned l = l0 + tl;
+    const int d = d0 + td;
+    const unsigned g = l * (unsigned)D + d;                  // L * D < 2^31 (checked by sd_set_lines)
+    bool active = (l < (unsigned)L) && (d < D);
     unsigned nonempty = 0, wide = 0, zero_dw = 0;
     bool e_lo = false, e_hi = false;
     unsigned long long key_lo = 0, key_hi = 0;
     if (active) {
-        const unsigned l = g / (unsigned)D;
-        const int d = (int)(g - l * (unsigned)D);
         double gam = gamma_cols > 1 ? gammas[g] : gammas[l];  // base.py:547-551
         double dw = dws[g];
         double a = alpha[g];
@@ -296,10 +306,7 @@ __global__ void __launch_bounds__(256) k_build_records(int64_t L, int D, int64_t
         r.thr = (m > 0.0) ? m * m : ((m <= 0.0) ? -1.0 : m);  // NaN y -> NaN thr -> never "far"
         if (!(r.inv_dw > 0.0) || !(r.inv_dw < 1e300)) r.thr = NAN;  // dw <= 0, inf or NaN: exact path only
         r.pad0 = r.pad1 = 0.0;
-        size_t o = (size_t)d * L + l;
-        // The record is read only after a window test passed for a tile of this context: pairs whose window is empty
-        // or misses the extended pixel range never get that far (nu sharding: ~half of the record traffic per rank).
-        if (hi > lo && hi > fg.ext0 && lo < fg.ext1) rec[o] = r;
+        s_rec[td][tl] = r;
         PairWin pw;
         pw.lo = (int)lo;
         pw.hi = (int)hi;
@@ -340,9 +347,9 @@ __global__ void __launch_bounds__(256) k_build_records(int64_t L, int D, int64_t
                 key_hi = sd_edge_key(fg, 1, d, lmin, hi, (int)l);
             }
         }
-        win_cls[o] = (uint8_t)cls;
+        s_wcls[td][tl] = (uint8_t)cls;
         pw.cls = (unsigned char)cls;
-        win[o] = pw;
+        s_win[td][tl] = pw;
         nonempty = hi > lo;
         wide = (hi > lo) && cls > 0;
         zero_dw = (hi > lo) && (dw == 0.0);
@@ -383,6 +390,21 @@ __global__ void __launch_bounds__(256) k_build_records(int64_t L, int D, int64_t
         const unsigned long long base = s_base + s_edges[wid];
         if (e_lo) fg.edge_out[base + __popc(m_lo & lt)] = key_lo;
         if (e_hi) fg.edge_out[base + n_lo + __popc(m_hi & lt)] = key_hi;
+    }
+    // ---- the tile's rows (the barriers above ordered the shared-memory writes): 16-byte chunks, consecutive threads on
+    // consecutive chunks of a depth row
+    const int nl = (int)min((unsigned)TL, (unsigned)L - l0), nd = min(TD, D - d0);
+    for (int c = threadIdx.x; c < TD * TL * 4; c += blockDim.x) {        // records: 4 chunks each
+        const int row = c / (TL * 4), col = c % (TL * 4);
+        if (row < nd && col < nl * 4)
+            reinterpret_cast<int4 *>(rec + (size_t)(d0 + row) * L + l0)[col] = reinterpret_cast<const int4 *>(&s_rec[row][0])[col];
+    }
+    {
+        const int row = threadIdx.x / TL, col = threadIdx.x % TL;            // window records: 1 chunk each; classes: 1 byte
+        if (row < nd && col < nl) {
+            reinterpret_cast<int4 *>(win + (size_t)(d0 + row) * L + l0)[col] = reinterpret_cast<const int4 *>(&s_win[row][0])[col];
+            win_cls[(size_t)(d0 + row) * L + l0 + col] = s_wcls[row][col];
+        }
     }
 }
 
@@ -559,7 +581,7 @@ int sd_k2_prepare(sd_ctx *c) {
     k_line_idx<<<(unsigned)((L + 255) / 256), 256, 0, c->stream>>>(L, c->N, c->nus.as<double>(), c->l_nu.as<double>(),
                                                                   c->line_idx.as<int>());
     SD_TRY(sd_launch_check(c, "k_line_idx"));
-    k_build_records<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(
+    k_build_records<<<(unsigned)(((L + 31) / 32) * ((D + 7) / 8)), 256, 0, c->stream>>>(
         L, D, c->N, c->nus.as<double>(), c->l_nu.as<double>(), c->line_idx.as<int>(), c->gammas.as<double>(), c->gamma_cols,
         c->dws.as<double>(), c->l_alpha.as<double>(), c->d_nu.as<double>(), c->rec.as<LineRec>(), c->win.as<PairWin>(),
         c->win_cls.as<uint8_t>(), fg, c->stats.as<unsigned long long>());
