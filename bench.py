@@ -527,12 +527,13 @@ def run_b200_arm(args):
         cells = D * W
         # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` captures of this
         # workload (profiles/ncu_traffic.json, written by tools/ncu_summary.py runs); null for any other configuration
-        traffic = {}
+        traffic, pipe_busy = {}, {}
         tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
         if os.path.exists(tpath) and world == 1:
             t = json.load(open(tpath))
             if (t.get("N"), t.get("D"), t.get("L")) == (N, D, len(sel)):
                 traffic = t.get("bytes_per_launch", {})
+                pipe_busy = t.get("fp64_pipe_busy", {})
         # executed work of this rank's launches in the default (far-field) mode
         flops_lines = float((ex["direct_region_evals"] * FLOPS_PER_EVAL).sum()) + FLOPS_HORNER * FAR_LEVELS * len(hp.didx) * op.W
         flops_far = (FLOPS_FAR_SETUP * ex["far_expansions"] + FLOPS_FAR_TERM * ex["far_terms"]
@@ -548,7 +549,7 @@ def run_b200_arm(args):
             "config": config_block(desc, len(sel), D, cells, world, bounds, args.partition),
             "roofline": {"kernel": "k_lines, default (far-field) mode: the dominant kernel of the timed step", "bound": "fp64",
                          "achieved": tf_lines, "peak": dfma_peak, "unit": "TFLOP/s", "frac": tf_lines / dfma_peak,
-                         "traffic": traffic.get("k_lines"),
+                         "traffic": traffic.get("k_lines"), "fp64_pipe_busy_ncu": pipe_busy.get("k_lines"),
                          "peak_source": "measured in this run: dependent-free DFMA loop on all SMs (sd_bench_dfma)",
                          "work": "EXECUTED Voigt evaluations per Humlicek region x SURVEY 8d flops + Horner evaluation of "
                                  "the four far-field polynomials per (pixel, depth)",
@@ -557,6 +558,7 @@ def run_b200_arm(args):
                          "share_of_step": t_lines / ms_per_step},
             "roofline_far": {"kernel": "k_far_coeffs (+ k_far_reduce) + k_s2m + k_m2l, all four levels", "bound": "fp64", "achieved": tf_far,
                              "peak": dfma_peak, "unit": "TFLOP/s", "frac": tf_far / dfma_peak, "traffic": traffic.get("k_far_coeffs"),
+                             "fp64_pipe_busy_ncu": {k: pipe_busy.get(k) for k in ("k_far_coeffs", "k_m2l", "k_m2m", "k_s2m")},
                              "work": "EXECUTED direct (pair, tile) expansions x setup flops + Taylor terms x flops per term + multipole "
                                      "expansions (pair, level) + tile-to-tile translation row steps",
                              "expansions": ex["far_expansions"], "terms": ex["far_terms"],
