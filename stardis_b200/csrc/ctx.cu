@@ -388,7 +388,7 @@ int sd_calc_alpha_line(sd_ctx *c, int32_t slot) {
 
 int sd_set_farfield(sd_ctx *c, int32_t on) {
     if (!c) return SD_ERR_ARG;
-    if (c->farfield != (on != 0)) c->records_ready = false;  // the near-tile intervals belong to the preparation pass
+    if (c->farfield != (on != 0)) c->records_ready = false;  // the far-capable classes and edge lists belong to the preparation pass
     c->farfield = on != 0;
     return SD_OK;
 }

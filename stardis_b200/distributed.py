@@ -170,7 +170,7 @@ def upload_rows_striped(host_array, device):
 
 # ------------------------------------------------------------------------------------------------- depth sharding
 # Under nu sharding every rank repeats the per-(line, depth) preparation of the line kernel for the whole line list
-# (windows, near-tile intervals, class lists, edge sort: independent of the rank's pixel range for the ~40 % of the pairs
+# (windows, far-field levels, class lists, edge sort: independent of the rank's pixel range for the ~40 % of the pairs
 # whose window spans the whole grid), which caps the 8-GPU efficiency near 0.5.  All opacity stages (K1, preparation, K2,
 # K3) are independent per DEPTH POINT, so the multi-GPU driver shards those by depth instead -- rank r evaluates every
 # R-th depth point (dealt in serpentine order, ``depth_indices``: neighbouring depths cost about the same, so the ranks are
