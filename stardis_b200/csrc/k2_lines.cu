@@ -244,7 +244,7 @@ __device__ __forceinline__ int far_terms(double rho2) {
     return FAR_TERMS[min(max(t8, 0), 255)];
 }
 
-__global__ void __launch_bounds__(THREADS, 2) k_far_coeffs(LineArgs a, int lev, int count_stats, int nsplit, double *part) {
+__global__ void __launch_bounds__(THREADS, 3) k_far_coeffs(LineArgs a, int lev, int count_stats, int nsplit, double *part) {
     __shared__ int s_ja[FAR_MAX_SRC], s_jb[FAR_MAX_SRC];
     extern __shared__ __align__(16) unsigned char far_smem[];
     FarRec *const s_rec = reinterpret_cast<FarRec *>(far_smem);                        // [FAR_CH] dense records of the chunk
